@@ -1,0 +1,506 @@
+// Fused multi-head self-attention forward / backward for sm_100a on the PACKED qkv tensor [B, T, 3*H*64].
+//
+// Replaces, per transformer block of the reference:
+//   qkv.chunk(3) + _to_heads permutes + .contiguous() copies   cflearn/modules/core/attentions.py:216,180-185,245
+//   F.scaled_dot_product_attention (via sdp_attn)               cflearn/toolkit.py:911-974
+//   output.transpose(1,2).contiguous()                          cflearn/modules/core/attentions.py:270
+// and their autograd.  T <= 256 (197 for ViT-B/16, 50 / 77 for CLIP) so one KV tile covers the whole
+// sequence: no online-softmax rescaling is needed and every score row lives in one TMEM lane.
+//
+// Forward, one CTA per (batch, head, 128-query tile), 2 CTAs / SM:
+//   TMA: Q[128x64], K[Tp x64], V[Tp x64] (3-D tensor map over qkv, rows >= T zero-filled)
+//   tcgen05.mma  S = Q K^T            (128 x Tp x 64, fp32 in TMEM)
+//   4 warps      row-per-thread softmax straight out of TMEM (tcgen05.ld), P -> bf16 -> 128B-swizzled smem
+//   tcgen05.mma  O = P V              (A = P K-major from smem, B = V MN-major from smem)
+//   4 warps      O / rowsum -> bf16 -> out[B, T, H*64]  (already in the layout the out-projection GEMM reads)
+//
+// Backward, one CTA per (batch, head): outer loop over 128-key tiles, inner loop over 128-query tiles.
+//   S = Q K^T, dP = dO V^T            (TMEM cols [0,128) and [128,256))
+//   8 warps: P = exp2(S*c - lse), dS = P * (dP - delta) -> bf16 -> swizzled smem (one tile serves as K-major A
+//            for dQ and as MN-major A for dK / dV: the 128B swizzle is purely address based)
+//   dV += P^T dO, dK += dS^T Q        (TMEM cols [256,320), [320,384); accumulate over query tiles)
+//   dQ_mt += dS K                     (TMEM cols [384,448), [448,512); accumulate over key tiles)
+// Numerics mirror the flash kernels torch dispatches to: fp32 scores / softmax / row sums, P and dS rounded to
+// bf16 only as MMA operands, softmax scale folded into exp2, dQ / dK scaled in fp32 at the end.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "b200_internal.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+constexpr int AF_THREADS = 160;
+constexpr int AF_SQ = 0;            // 16 KB
+constexpr int AF_SK = 16384;        // 32 KB
+constexpr int AF_SP = 0;            // 64 KB, aliases Q and K (written only after S = QK^T has retired)
+constexpr int AF_SV = 65536;        // 32 KB
+constexpr int AF_BAR = 98304;
+constexpr int AF_SMEM = AF_BAR + 64 + 1024;
+
+struct AttnParams {
+    int B, T, H, D;   // D = H * 64
+    int tp;           // T rounded up to a multiple of 16
+    float scale;
+    int causal;
+};
+
+__global__ void __launch_bounds__(AF_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + AF_SQ;
+    uint8_t* sK = smem + AF_SK;
+    uint8_t* sP = smem + AF_SP;
+    uint8_t* sV = smem + AF_SV;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AF_BAR);
+    uint64_t* bar_s = bar_load + 1;
+    uint64_t* bar_p = bar_load + 2;
+    uint64_t* bar_o = bar_load + 3;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_load + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_mt = (p.T + 127) / 128;
+    const int mt = blockIdx.x % n_mt;
+    const int bh = blockIdx.x / n_mt;
+    const int h = bh % p.H;
+    const int b = bh / p.H;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmKV);
+            mbar_init(bar_load, 1);
+            mbar_init(bar_s, 1);
+            mbar_init(bar_p, 128);
+            mbar_init(bar_o, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 4) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_load, 16384u + 2u * static_cast<uint32_t>(p.tp) * 128u);
+            tma_load_3d(sQ, &tmQ, bar_load, h * 64, mt * 128, b);
+            tma_load_3d(sK, &tmKV, bar_load, p.D + h * 64, 0, b);
+            tma_load_3d(sV, &tmKV, bar_load, 2 * p.D + h * 64, 0, b);
+            mbar_wait(bar_load, 0);
+            tc_fence_after_sync();
+            const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(p.tp), 0, 0);
+            const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tmem_base, make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
+                          make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), idesc_s, kk > 0 ? 1u : 0u);
+            umma_commit(bar_s);
+            mbar_wait(bar_p, 0);
+            tc_fence_after_sync();
+            const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t p_base = smem_u32(sP), v_base = smem_u32(sV);
+            const int nkk = p.tp / 16;
+            for (int kk = 0; kk < nkk; ++kk)
+                umma_bf16(tmem_base, make_smem_desc(p_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, kSwz128),
+                          make_smem_desc(v_base + kk * 2048, 0, 1024, kSwz128), idesc_o, kk > 0 ? 1u : 0u);
+            umma_commit(bar_o);
+        }
+    } else {
+        const int r = threadIdx.x;  // row inside the query tile == TMEM lane
+        const int i = mt * 128 + r;  // query index
+        const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(warp) * 32u) << 16);
+        const float sl2 = p.scale * kLog2e;
+        int nvalid = p.T;
+        if (p.causal && i + 1 < nvalid) nvalid = i + 1;
+        const int nchunk = p.tp / 16;
+        mbar_wait(bar_s, 0);
+        tc_fence_after_sync();
+        // pass 1: row max
+        float m = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c * 16 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        const float m2 = m * sl2;
+        // pass 2: p = exp2(s*c - m*c), row sum, P -> smem (bf16, K-major 128B swizzle)
+        float sum = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+            tmem_ld_wait();
+            float pv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float e = exp2f(__uint_as_float(v[j]) * sl2 - m2);
+                pv[j] = (c * 16 + j < nvalid) ? e : 0.f;
+                sum += pv[j];
+            }
+            const int col = c * 16;
+            uint8_t* blk = sP + (col >> 6) * 16384 + r * 128;
+            const uint32_t ch = static_cast<uint32_t>((col & 63) >> 3);
+            *reinterpret_cast<uint4*>(blk + (((ch) ^ (r & 7u)) << 4)) =
+                make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+            *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (r & 7u)) << 4)) =
+                make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(bar_p);
+        // O = P V
+        mbar_wait(bar_o, 0);
+        tc_fence_after_sync();
+        const float inv = 1.0f / sum;
+        const bool valid = i < p.T;
+        __nv_bfloat16* orow = out + (static_cast<long long>(b) * p.T + i) * p.D + h * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+            tmem_ld_wait();
+            if (valid) {
+                uint4 o0, o1;
+                o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+                o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+                o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+                o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+                o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+                o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+                o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+                o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+                reinterpret_cast<uint4*>(orow + c * 16)[0] = o0;
+                reinterpret_cast<uint4*>(orow + c * 16)[1] = o1;
+            }
+        }
+        if (valid) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+constexpr int AB_THREADS = 288;
+constexpr int AB_SQ = 0;        // 2 x 16 KB (query tiles 0,1)
+constexpr int AB_SDO = 32768;   // 2 x 16 KB
+constexpr int AB_SK = 65536;    // 16 KB (current key tile)
+constexpr int AB_SV = 81920;    // 16 KB
+constexpr int AB_SP = 98304;    // 32 KB: P  [128 q x 128 keys] as two 64-key blocks
+constexpr int AB_SDS = 131072;  // 32 KB: dS
+constexpr int AB_LSE = 163840;  // 256 floats
+constexpr int AB_DELTA = AB_LSE + 1024;
+constexpr int AB_BAR = AB_DELTA + 1024;
+constexpr int AB_SMEM = AB_BAR + 128 + 1024;
+
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DK = 256, TM_DV = 320, TM_DQ = 384;
+
+__device__ __forceinline__ void store_row64_scaled(__nv_bfloat16* dst, uint32_t taddr, float sc, bool valid) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+        tmem_ld_wait();
+        if (valid) {
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+            o0.y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+            o0.z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+            o0.w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+            o1.x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+            o1.y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+            o1.z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+            o1.w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+            reinterpret_cast<uint4*>(dst + c * 16)[0] = o0;
+            reinterpret_cast<uint4*>(dst + c * 16)[1] = o1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
+                const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + AB_SQ;
+    uint8_t* sDO = smem + AB_SDO;
+    uint8_t* sK = smem + AB_SK;
+    uint8_t* sV = smem + AB_SV;
+    uint8_t* sP = smem + AB_SP;
+    uint8_t* sDS = smem + AB_SDS;
+    float* lse_s = reinterpret_cast<float*>(smem + AB_LSE);
+    float* delta_s = reinterpret_cast<float*>(smem + AB_DELTA);
+    uint64_t* bar_qdo = reinterpret_cast<uint64_t*>(smem + AB_BAR);
+    uint64_t* bar_kvload = bar_qdo + 1;
+    uint64_t* bar_sdp = bar_qdo + 2;
+    uint64_t* bar_pds = bar_qdo + 3;
+    uint64_t* bar_kv = bar_qdo + 4;
+    uint64_t* bar_kvfree = bar_qdo + 5;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_qdo + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_mt = (p.T + 127) / 128;
+    const int n_kt = n_mt;
+    const int h = blockIdx.x % p.H;
+    const int b = blockIdx.x / p.H;
+    const long long D3 = 3ll * p.D;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQKV);
+            tma_prefetch_desc(&tmDO);
+            mbar_init(bar_qdo, 1);
+            mbar_init(bar_kvload, 1);
+            mbar_init(bar_sdp, 1);
+            mbar_init(bar_pds, 256);
+            mbar_init(bar_kv, 1);
+            mbar_init(bar_kvfree, 256);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    } else {
+        // delta_i = sum_d dO[i,d] * O[i,d] (fp32) and lse_i for all (<= 256) query rows of this (b, h)
+        const int i = threadIdx.x;
+        float dl = 0.f, ls = 0.f;
+        if (i < p.T) {
+            const uint4* po = reinterpret_cast<const uint4*>(o_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
+            const uint4* pd = reinterpret_cast<const uint4*>(do_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 a = po[k], g = pd[k];
+                dl += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+                      bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+            }
+            ls = lse_in[(static_cast<long long>(b) * p.H + h) * p.T + i];
+        }
+        lse_s[i] = ls * kLog2e;
+        delta_s[i] = dl;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 8) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_qdo, static_cast<uint32_t>(n_mt) * 2u * 16384u);
+            for (int mt = 0; mt < n_mt; ++mt) {
+                tma_load_3d(sQ + mt * 16384, &tmQKV, bar_qdo, h * 64, mt * 128, b);
+                tma_load_3d(sDO + mt * 16384, &tmDO, bar_qdo, h * 64, mt * 128, b);
+            }
+            const uint32_t idesc_nn = make_idesc_bf16(128, 128, 0, 0);  // S, dP   : A K-major,  B K-major
+            const uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);   // dV, dK  : A MN-major, B MN-major
+            const uint32_t idesc_nt = make_idesc_bf16(128, 64, 0, 1);   // dQ      : A K-major,  B MN-major
+            const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+            uint32_t it = 0;
+            for (int kt = 0; kt < n_kt; ++kt) {
+                if (kt > 0) mbar_wait(bar_kv, static_cast<uint32_t>(kt - 1) & 1u);  // MMAs reading sK / sV retired
+                mbar_expect_tx(bar_kvload, 2u * 16384u);
+                tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, kt * 128, b);
+                tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, kt * 128, b);
+                if (kt == 0) mbar_wait(bar_qdo, 0);
+                mbar_wait(bar_kvload, static_cast<uint32_t>(kt) & 1u);
+                tc_fence_after_sync();
+                for (int mt = 0; mt < n_mt; ++mt, ++it) {
+                    const uint32_t q_base = smem_u32(sQ + mt * 16384), do_base = smem_u32(sDO + mt * 16384);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + TM_S, make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
+                                  make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), idesc_nn, kk > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + TM_DP, make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
+                                  make_smem_desc(v_base + kk * 32, 0, 1024, kSwz128), idesc_nn, kk > 0 ? 1u : 0u);
+                    umma_commit(bar_sdp);
+                    mbar_wait(bar_pds, it & 1u);
+                    tc_fence_after_sync();
+                    if (mt == 0 && kt > 0) {
+                        mbar_wait(bar_kvfree, static_cast<uint32_t>(kt - 1) & 1u);  // dK / dV of the previous key tile read out
+                        tc_fence_after_sync();
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 queries of this tile, 16 per step
+                        const uint64_t a_p = make_smem_desc(p_base + kk * 2048, 16384, 1024, kSwz128);
+                        const uint64_t a_ds = make_smem_desc(ds_base + kk * 2048, 16384, 1024, kSwz128);
+                        const uint64_t b_do = make_smem_desc(do_base + kk * 2048, 0, 1024, kSwz128);
+                        const uint64_t b_q = make_smem_desc(q_base + kk * 2048, 0, 1024, kSwz128);
+                        const uint32_t acc = (mt > 0 || kk > 0) ? 1u : 0u;
+                        umma_bf16(tmem_base + TM_DV, a_p, b_do, idesc_tt, acc);
+                        umma_bf16(tmem_base + TM_DK, a_ds, b_q, idesc_tt, acc);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 keys of this tile
+                        const uint64_t a_ds = make_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, kSwz128);
+                        const uint64_t b_k = make_smem_desc(k_base + kk * 2048, 0, 1024, kSwz128);
+                        umma_bf16(tmem_base + TM_DQ + static_cast<uint32_t>(mt * 64), a_ds, b_k, idesc_nt, (kt > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    if (mt == n_mt - 1) umma_commit(bar_kv);
+                }
+            }
+        }
+    } else {
+        const uint32_t q = static_cast<uint32_t>(warp & 3);
+        const int ch = warp >> 2;                  // which 64-key half of the key tile
+        const int r = static_cast<int>(q) * 32 + lane;  // row in the query tile
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+        const float sl2 = p.scale * kLog2e;
+        uint32_t it = 0;
+        for (int kt = 0; kt < n_kt; ++kt) {
+            for (int mt = 0; mt < n_mt; ++mt, ++it) {
+                const int i = mt * 128 + r;
+                const bool rowvalid = i < p.T;
+                const float lse2 = lse_s[i];
+                const float delta = delta_s[i];
+                mbar_wait(bar_sdp, it & 1u);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col = ch * 64 + c * 16;
+                    const int j0 = kt * 128 + col;
+                    uint32_t sv[16], dv[16];
+                    tmem_ld_32x32b_x16(taddr + TM_S + static_cast<uint32_t>(col), sv);
+                    tmem_ld_32x32b_x16(taddr + TM_DP + static_cast<uint32_t>(col), dv);
+                    tmem_ld_wait();
+                    float pv[16], ds[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int j = j0 + jj;
+                        const bool ok = rowvalid && (j < p.T) && (!p.causal || j <= i);
+                        const float e = exp2f(__uint_as_float(sv[jj]) * sl2 - lse2);
+                        pv[jj] = ok ? e : 0.f;
+                        ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - delta) : 0.f;
+                    }
+                    const uint32_t c16 = static_cast<uint32_t>(c * 2);
+                    const uint32_t off0 = static_cast<uint32_t>(ch) * 16384u + static_cast<uint32_t>(r) * 128u + (((c16) ^ (static_cast<uint32_t>(r) & 7u)) << 4);
+                    const uint32_t off1 = static_cast<uint32_t>(ch) * 16384u + static_cast<uint32_t>(r) * 128u + (((c16 + 1) ^ (static_cast<uint32_t>(r) & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(sP + off0) = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+                    *reinterpret_cast<uint4*>(sP + off1) = make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
+                    *reinterpret_cast<uint4*>(sDS + off0) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+                    *reinterpret_cast<uint4*>(sDS + off1) = make_uint4(pack_bf16x2(ds[8], ds[9]), pack_bf16x2(ds[10], ds[11]), pack_bf16x2(ds[12], ds[13]), pack_bf16x2(ds[14], ds[15]));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                mbar_arrive(bar_pds);
+                if (mt == n_mt - 1) {
+                    // dK / dV of this key tile are complete (and, on the last key tile, so are all dQ)
+                    mbar_wait(bar_kv, static_cast<uint32_t>(kt) & 1u);
+                    tc_fence_after_sync();
+                    const int key = kt * 128 + r;
+                    __nv_bfloat16* drow = dqkv + (static_cast<long long>(b) * p.T + key) * D3 + h * 64;
+                    if (ch == 0) store_row64_scaled(drow + p.D, taddr + TM_DK, p.scale, key < p.T);
+                    else         store_row64_scaled(drow + 2 * p.D, taddr + TM_DV, 1.0f, key < p.T);
+                    tc_fence_before_sync();
+                    mbar_arrive(bar_kvfree);
+                }
+            }
+        }
+        // dQ tiles: warps with ch < n_mt each write query tile `ch`
+        if (ch < n_mt) {
+            const int i = ch * 128 + r;
+            __nv_bfloat16* drow = dqkv + (static_cast<long long>(b) * p.T + i) * D3 + h * 64;
+            store_row64_scaled(drow, taddr + TM_DQ + static_cast<uint32_t>(ch * 64), p.scale, i < p.T);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static int attn_check(int B, int T, int H, int Dh) {
+    if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");
+    if (Dh != 64) return set_error(B200_ERR_ARG, "attention: head dim must be 64");
+    if (T > 256) return set_error(B200_ERR_ARG, "attention: T must be <= 256");
+    return 0;
+}
+
+extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int H, int Dh,
+                                  float scale, int causal, cudaStream_t stream) {
+    int rc = attn_check(B, T, H, Dh);
+    if (rc) return rc;
+    const int D = H * 64;
+    const int tp = (T + 15) / 16 * 16;
+    CUtensorMap tmQ, tmKV;
+    uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(3 * D) * 2 * static_cast<uint64_t>(T)};
+    uint32_t boxq[3] = {64, 128, 1};
+    uint32_t boxkv[3] = {64, static_cast<uint32_t>(tp), 1};
+    if ((rc = make_tmap(&tmQ, qkv_bf16, 2, 3, dims, strides, boxq, 128)) != 0) return rc;
+    if ((rc = make_tmap(&tmKV, qkv_bf16, 2, 3, dims, strides, boxkv, 128)) != 0) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
+        if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
+        configured = true;
+    }
+    AttnParams p;
+    p.B = B; p.T = T; p.H = H; p.D = D; p.tp = tp; p.scale = scale; p.causal = causal;
+    const int n_mt = (T + 127) / 128;
+    attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
+    return check_launch("attention_fwd");
+}
+
+extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                                  void* dqkv_bf16, int B, int T, int H, int Dh, float scale, int causal,
+                                  cudaStream_t stream) {
+    int rc = attn_check(B, T, H, Dh);
+    if (rc) return rc;
+    const int D = H * 64;
+    CUtensorMap tmQKV, tmDO;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+        uint64_t strides[2] = {static_cast<uint64_t>(3 * D) * 2, static_cast<uint64_t>(3 * D) * 2 * static_cast<uint64_t>(T)};
+        uint32_t box[3] = {64, 128, 1};
+        if ((rc = make_tmap(&tmQKV, qkv_bf16, 2, 3, dims, strides, box, 128)) != 0) return rc;
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+        uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(D) * 2 * static_cast<uint64_t>(T)};
+        uint32_t box[3] = {64, 128, 1};
+        if ((rc = make_tmap(&tmDO, dout_bf16, 2, 3, dims, strides, box, 128)) != 0) return rc;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
+        configured = true;
+    }
+    AttnParams p;
+    p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
+    attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+                                                            reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
+                                                            reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), p);
+    return check_launch("attention_bwd");
+}

@@ -1,0 +1,528 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (fp32 accumulate in TMEM)
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages of 48 KB)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma 128x256x16)
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused epilogue -> swizzled smem -> TMA store)
+//
+// The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
+// latter is what the backward GEMMs need (dgrad reads W[N,K] with the reduction over N, wgrad reads dY and X
+// with the reduction over tokens) -- no transposed copies are ever materialised.
+//
+// This one kernel serves every dense layer on the hot path of the reference's transformer block
+// (SURVEY.md section 2b, K1/K4/K8/K10/K11/K12/K14):
+//   F.linear call sites  cflearn/modules/core/customs.py:85-89, attentions.py:214,277, channel_mixers.py:29-33
+//   conv-as-GEMM         cflearn/modules/core/convs/basic.py:155-174 (patch embed, k = s = 16)
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "b200_internal.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int MN_BOX_BYTES = 64 * BK * 2;   // one MN-major TMA box: 64 (MN) x 64 (K) bf16 = 8 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B
+constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
+
+constexpr int SMEM_A_OFF = 0;
+constexpr int SMEM_B_OFF = SMEM_A_OFF + STAGES * A_STAGE_BYTES;
+constexpr int SMEM_EPI_OFF = SMEM_B_OFF + STAGES * B_STAGE_BYTES;
+constexpr int SMEM_BAR_OFF = SMEM_EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int SMEM_BAR_BYTES = 256;
+constexpr int GEMM_SMEM_BYTES = SMEM_BAR_OFF + SMEM_BAR_BYTES + 1024;  // + slack for manual 1 KB alignment
+
+struct GemmParams {
+    int M, N, K;
+    int num_m_tiles, num_n_tiles, splits, num_kb;
+    int a_mn, b_mn;  // 1 = MN-major operand
+    const __nv_bfloat16* bias;  // [N] bf16 or nullptr
+};
+
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_t, int& n_t, int& sp, int& kb0,
+                                            int& kb1) {
+    n_t = u % p.num_n_tiles;
+    int r = u / p.num_n_tiles;
+    sp = r % p.splits;
+    m_t = r / p.splits;
+    kb0 = static_cast<int>((static_cast<long long>(p.num_kb) * sp) / p.splits);
+    kb1 = static_cast<int>((static_cast<long long>(p.num_kb) * (sp + 1)) / p.splits);
+}
+
+// 16-byte row-per-thread accesses into a TMA-swizzled staging tile (bank-conflict free)
+__device__ __forceinline__ uint32_t swz128_off(uint32_t row, uint32_t chunk) {  // 128 B rows, 8 chunks
+    return row * 128u + ((chunk ^ (row & 7u)) << 4);
+}
+__device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {  // 64 B rows, 4 chunks
+    return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
+                 const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem + SMEM_A_OFF;
+    uint8_t* sB = smem + SMEM_B_OFF;
+    uint8_t* sEpi = smem + SMEM_EPI_OFF;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t* aux_bar = tmem_empty_bar + 2;  // [NUM_EPI_WARPS]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + NUM_EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut0);
+        if (EPI == EPI_BIAS_GELU_BF16) tma_prefetch_desc(&tmOut1);
+        if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAux);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);
+        }
+        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+                int m_t, n_t, sp, kb0, kb1;
+                decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+                const int m0 = m_t * BM, n0 = n_t * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+                    uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+                    if (!p.a_mn) {
+                        tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(a_dst + i * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(b_dst + i * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+            int stage = 0;
+            uint32_t phase = 0;
+            int lt = 0;
+            for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lt) {
+                int m_t, n_t, sp, kb0, kb1;
+                decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+                const int as = lt & 1;
+                const uint32_t aph = (lt >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        // K-major  : 8-row groups 1024 B apart (SBO); +32 B per 16-element K step.
+                        // MN-major : 8-k-row groups 1024 B apart (SBO); 64-element MN atoms one TMA box
+                        //            (8 KB) apart (LBO); +2048 B per 16-row K step.
+                        const uint64_t adesc = p.a_mn ? make_smem_desc(a_base + kk * 2048, MN_BOX_BYTES, 1024, kSwz128)
+                                                      : make_smem_desc(a_base + kk * 32, 0, 1024, kSwz128);
+                        const uint64_t bdesc = p.b_mn ? make_smem_desc(b_base + kk * 2048, MN_BOX_BYTES, 1024, kSwz128)
+                                                      : make_smem_desc(b_base + kk * 32, 0, 1024, kSwz128);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================================== epilogue warps ===================================
+        const int e = warp - 2;               // 0..7
+        const uint32_t q = warp & 3;          // TMEM lane quadrant this warp may access
+        const int half = e >> 2;              // which 128-column half of the accumulator
+        uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
+        uint64_t* my_aux_bar = &aux_bar[e];
+        uint32_t aux_phase = 0;
+        int lt = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lt) {
+            int m_t, n_t, sp, kb0, kb1;
+            decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+            const int as = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1u;
+            const int grow0 = m_t * BM + static_cast<int>(q) * 32;
+            mbar_wait(&tmem_full_bar[as], aph);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col = half * 128 + c * 32;
+                const int gcol = n_t * BN + col;
+                const bool active = (gcol < p.N) && (grow0 < p.M);  // warp-uniform
+                // staging buffer must have been drained by the previous TMA store
+                if (lane == 0) tma_store_wait_read0();
+                __syncwarp();
+                if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
+                    if (active && lane == 0) {
+                        mbar_expect_tx(my_aux_bar, EPI == EPI_BIAS_RESID_F32 ? 4096u : 2048u);
+                        tma_load_3d(stg, &tmAux, my_aux_bar, gcol, grow0, 0);
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(col), v);
+                tmem_ld_wait();
+                if (c == 3) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                if (!active) continue;
+
+                // bias for these 32 columns (bf16, broadcast load); N % 8 == 0 is enforced on the host
+                float bv[32];
+                if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4 t = make_uint4(0, 0, 0, 0);
+                        if (p.bias != nullptr && gcol + j8 * 8 < p.N)
+                            t = *reinterpret_cast<const uint4*>(p.bias + gcol + j8 * 8);
+                        bv[j8 * 8 + 0] = bf16lo(t.x); bv[j8 * 8 + 1] = bf16hi(t.x);
+                        bv[j8 * 8 + 2] = bf16lo(t.y); bv[j8 * 8 + 3] = bf16hi(t.y);
+                        bv[j8 * 8 + 4] = bf16lo(t.z); bv[j8 * 8 + 5] = bf16hi(t.z);
+                        bv[j8 * 8 + 6] = bf16lo(t.w); bv[j8 * 8 + 7] = bf16hi(t.w);
+                    }
+                }
+
+                if constexpr (EPI == EPI_BIAS_BF16) {
+                    // out0 = bf16(acc + bias)
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j4 * 8 + 0]) + bv[j4 * 8 + 0], __uint_as_float(v[j4 * 8 + 1]) + bv[j4 * 8 + 1]);
+                        o.y = pack_bf16x2(__uint_as_float(v[j4 * 8 + 2]) + bv[j4 * 8 + 2], __uint_as_float(v[j4 * 8 + 3]) + bv[j4 * 8 + 3]);
+                        o.z = pack_bf16x2(__uint_as_float(v[j4 * 8 + 4]) + bv[j4 * 8 + 4], __uint_as_float(v[j4 * 8 + 5]) + bv[j4 * 8 + 5]);
+                        o.w = pack_bf16x2(__uint_as_float(v[j4 * 8 + 6]) + bv[j4 * 8 + 6], __uint_as_float(v[j4 * 8 + 7]) + bv[j4 * 8 + 7]);
+                        *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
+                        tma_store_commit();
+                    }
+                } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                    // out0 = h = bf16(acc + bias);  out1 = bf16(gelu(h))   (GELU sees the ROUNDED h, like eager)
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint32_t hp[4], gp[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int j = j4 * 8 + t * 2;
+                            hp[t] = pack_bf16x2(__uint_as_float(v[j]) + bv[j], __uint_as_float(v[j + 1]) + bv[j + 1]);
+                            gp[t] = pack_bf16x2(gelu_erf(bf16lo(hp[t])), gelu_erf(bf16hi(hp[t])));
+                        }
+                        *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                        *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
+                        tma_store_3d(&tmOut1, stg + 2048, gcol, grow0, sp);
+                        tma_store_commit();
+                    }
+                } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                    // out0(fp32) = aux(fp32) + float(bf16(acc + bias))     (aux may alias out0)
+                    mbar_wait(my_aux_bar, aux_phase);
+                    aux_phase ^= 1u;
+#pragma unroll
+                    for (int j8 = 0; j8 < 8; ++j8) {
+                        float4* ptr = reinterpret_cast<float4*>(stg + swz128_off(lane, j8));
+                        float4 r = *ptr;
+                        r.x += bf16_round(__uint_as_float(v[j8 * 4 + 0]) + bv[j8 * 4 + 0]);
+                        r.y += bf16_round(__uint_as_float(v[j8 * 4 + 1]) + bv[j8 * 4 + 1]);
+                        r.z += bf16_round(__uint_as_float(v[j8 * 4 + 2]) + bv[j8 * 4 + 2]);
+                        r.w += bf16_round(__uint_as_float(v[j8 * 4 + 3]) + bv[j8 * 4 + 3]);
+                        *ptr = r;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
+                        tma_store_commit();
+                    }
+                } else if constexpr (EPI == EPI_DGELU_BF16) {
+                    // out0 = bf16( float(bf16(acc)) * gelu'(h) ),  h = aux (bf16)
+                    mbar_wait(my_aux_bar, aux_phase);
+                    aux_phase ^= 1u;
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const uint4 h = *reinterpret_cast<const uint4*>(stg + swz64_off(lane, j4));
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                        uint32_t op[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int j = j4 * 8 + t * 2;
+                            const float d0 = bf16_round(__uint_as_float(v[j])) * gelu_erf_grad(bf16lo(hw[t]));
+                            const float d1 = bf16_round(__uint_as_float(v[j + 1])) * gelu_erf_grad(bf16hi(hw[t]));
+                            op[t] = pack_bf16x2(d0, d1);
+                        }
+                        *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(op[0], op[1], op[2], op[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmOut0, stg + 2048, gcol, grow0, sp);
+                        tma_store_commit();
+                    }
+                } else {  // EPI_PARTIAL_F32: out0[sp] = acc (fp32)
+#pragma unroll
+                    for (int j8 = 0; j8 < 8; ++j8) {
+                        *reinterpret_cast<uint4*>(stg + swz128_off(lane, j8)) =
+                            make_uint4(v[j8 * 4 + 0], v[j8 * 4 + 1], v[j8 * 4 + 2], v[j8 * 4 + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all0();
+        __syncwarp();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+// rank-2/3 tiled map; dims/box innermost first; strides in BYTES for dims 1.. (rank-1 entries)
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return set_error(B200_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return set_error(B200_ERR_ALIGN, "tensor base not 16 B aligned");
+    for (int i = 0; i + 1 < rank; ++i)
+        if (gstr[i] % 16 != 0) return set_error(B200_ERR_ALIGN, "tensor stride not a multiple of 16 B");
+    CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu box %u %u)",
+                 static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return set_error(B200_ERR_DRIVER, msg);
+    }
+    return 0;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& o0, const CUtensorMap& o1,
+                       const CUtensorMap& ax, const GemmParams& p, int grid, cudaStream_t stream) {
+    static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
+    cudaError_t e;
+    if (!configured) {
+        e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
+        configured = true;
+    }
+    gemm_bf16_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, o0, o1, ax, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
+    count_launch(1);
+    return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm_pick_splits(int M, int N, int K) {
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int num_kb = (K + BK - 1) / BK;
+    const int sms = 148;
+    int best = 1;
+    double best_score = -1.0;
+    for (int s = 1; s <= 16 && s <= num_kb; ++s) {
+        const int units = tiles * s;
+        const int waves = (units + sms - 1) / sms;
+        double eff = static_cast<double>(units) / (static_cast<double>(waves) * sms);
+        // each split costs a pipeline fill/drain (~ 8 k-blocks worth) and an extra fp32 partial
+        const double kb_per = static_cast<double>(num_kb) / s;
+        eff *= kb_per / (kb_per + 8.0);
+        if (eff > best_score + 1e-9) {
+            best_score = eff;
+            best = s;
+        }
+    }
+    return best;
+}
+
+extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                              int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
+                              void* out1, const void* aux, long long ldo, int splits, int max_ctas,
+                              cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: non-positive dimension");
+    if (N % 8 != 0) return set_error(B200_ERR_ARG, "gemm: N must be a multiple of 8");
+    if (A == nullptr || B == nullptr || out0 == nullptr) return set_error(B200_ERR_ARG, "gemm: null pointer");
+    if (splits < 1) splits = 1;
+    if (epilogue != EPI_PARTIAL_F32 && splits != 1) return set_error(B200_ERR_ARG, "gemm: split-K needs EPI_PARTIAL_F32");
+    const int num_kb = (K + BK - 1) / BK;
+    if (splits > num_kb) splits = num_kb;
+
+    CUtensorMap tmA, tmB, tmO0, tmO1, tmAx;
+    int rc;
+    {
+        // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
+        uint64_t d[2], s[1];
+        uint32_t bx[2];
+        if (!a_mn_major) { d[0] = K; d[1] = M; bx[0] = BK; bx[1] = BM; }
+        else             { d[0] = M; d[1] = K; bx[0] = 64; bx[1] = BK; }
+        s[0] = static_cast<uint64_t>(lda) * 2;
+        if ((rc = make_tmap(&tmA, A, 2, 2, d, s, bx, 128)) != 0) return rc;
+        if (!b_mn_major) { d[0] = K; d[1] = N; bx[0] = BK; bx[1] = BN; }
+        else             { d[0] = N; d[1] = K; bx[0] = 64; bx[1] = BK; }
+        s[0] = static_cast<uint64_t>(ldb) * 2;
+        if ((rc = make_tmap(&tmB, B, 2, 2, d, s, bx, 128)) != 0) return rc;
+    }
+    const bool out_f32 = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_PARTIAL_F32);
+    {
+        const int eb = out_f32 ? 4 : 2;
+        uint64_t d[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), static_cast<uint64_t>(splits)};
+        uint64_t s[2] = {static_cast<uint64_t>(ldo) * eb, static_cast<uint64_t>(ldo) * eb * static_cast<uint64_t>(M)};
+        uint32_t bx[3] = {32, 32, 1};
+        const int swz = out_f32 ? 128 : 64;
+        if ((rc = make_tmap(&tmO0, out0, eb, 3, d, s, bx, swz)) != 0) return rc;
+        tmO1 = tmO0;
+        tmAx = tmO0;
+        if (epilogue == EPI_BIAS_GELU_BF16) {
+            if (out1 == nullptr) return set_error(B200_ERR_ARG, "gemm: GELU epilogue needs out1");
+            if ((rc = make_tmap(&tmO1, out1, eb, 3, d, s, bx, swz)) != 0) return rc;
+        }
+        if (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_DGELU_BF16) {
+            if (aux == nullptr) return set_error(B200_ERR_ARG, "gemm: epilogue needs aux");
+            if ((rc = make_tmap(&tmAx, aux, eb, 3, d, s, bx, swz)) != 0) return rc;
+        }
+    }
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_tiles = (M + BM - 1) / BM;
+    p.num_n_tiles = (N + BN - 1) / BN;
+    p.splits = splits;
+    p.num_kb = num_kb;
+    p.a_mn = a_mn_major ? 1 : 0;
+    p.b_mn = b_mn_major ? 1 : 0;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    const long long units = static_cast<long long>(p.num_m_tiles) * p.num_n_tiles * splits;
+    int grid = num_sms();
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (units < grid) grid = static_cast<int>(units);
+    switch (epilogue) {
+        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
+    }
+}

@@ -1,0 +1,580 @@
+// HBM-bound row kernels of the transformer-block training step: LayerNorm fwd/bwd, column sums (bias / gamma /
+// beta grads), split-K reduction, patch-embed glue, softmax cross-entropy, casts.  All are coalesced 16-byte
+// vector streams with warp-shuffle reductions; none of them re-reads a tensor.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "b200_internal.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// error / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+    return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        return set_error(B200_ERR_LAUNCH, buf);
+    }
+    count_launch(1);
+    return 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row held in registers (dim <= 1024, dim % 4 == 0)
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAX_V4 = 8;  // float4 per lane
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ld_x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int rows, int dim, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + static_cast<long long>(warp) * ld_x;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < dim) {
+            v[i] = *reinterpret_cast<const float4*>(xr + c);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float inv_n = 1.0f / static_cast<float>(dim);
+    const float mean = warp_sum(s) * inv_n;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < dim) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float var = warp_sum(ss) * inv_n;
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+        mean_out[warp] = mean;
+        rstd_out[warp] = rstd;
+    }
+    __nv_bfloat16* yr = y + static_cast<long long>(warp) * dim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < dim) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+            const float4 b = *reinterpret_cast<const float4*>(beta + c);
+            uint2 o;
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            *reinterpret_cast<uint2*>(yr + c) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: warps stride over rows; per-lane dgamma/dbeta partials live in registers and are
+// reduced across the block's warps through shared memory -> part[blockIdx][dim].
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const float* __restrict__ x, long long ld_x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ dres, float* __restrict__ dx_out,
+                                                            long long ld_dx, __nv_bfloat16* __restrict__ dx_bf16,
+                                                            float* __restrict__ dgamma_part,
+                                                            float* __restrict__ dbeta_part, int rows, int dim) {
+    extern __shared__ float sred[];  // [8 warps][2][dim]
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    float4 g[NV], dg[NV], db[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        g[i] = c < dim ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float fn = static_cast<float>(dim);
+    for (int row = blockIdx.x * warps_per_block + wib; row < rows; row += gridDim.x * warps_per_block) {
+        const float mean = mean_in[row];
+        const float rstd = rstd_in[row];
+        const float* xr = x + static_cast<long long>(row) * ld_x;
+        const __nv_bfloat16* dyr = dy + static_cast<long long>(row) * dim;
+        float4 xh[NV], gy[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < dim) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+                const uint2 dv = *reinterpret_cast<const uint2*>(dyr + c);
+                const float d0 = bf16lo(dv.x), d1 = bf16hi(dv.x), d2 = bf16lo(dv.y), d3 = bf16hi(dv.y);
+                xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+                gy[i] = make_float4(d0 * g[i].x, d1 * g[i].y, d2 * g[i].z, d3 * g[i].w);
+                s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+                s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+                dg[i].x += d0 * xh[i].x; dg[i].y += d1 * xh[i].y; dg[i].z += d2 * xh[i].z; dg[i].w += d3 * xh[i].w;
+                db[i].x += d0; db[i].y += d1; db[i].z += d2; db[i].w += d3;
+            }
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        const float term = rstd / fn;
+        float* dxr = dx_out + static_cast<long long>(row) * ld_dx;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < dim) {
+                float4 o;
+                o.x = (fn * gy[i].x - s1 - xh[i].x * s2) * term;
+                o.y = (fn * gy[i].y - s1 - xh[i].y * s2) * term;
+                o.z = (fn * gy[i].z - s1 - xh[i].z * s2) * term;
+                o.w = (fn * gy[i].w - s1 - xh[i].w * s2) * term;
+                if (dres != nullptr) {
+                    const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ld_dx + c);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(dxr + c) = o;
+                if (dx_bf16 != nullptr) {
+                    uint2 p;
+                    p.x = pack_bf16x2(o.x, o.y);
+                    p.y = pack_bf16x2(o.z, o.w);
+                    *reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * dim + c) = p;
+                }
+            }
+        }
+    }
+    // block reduce of dgamma / dbeta partials
+    float* sg = sred + (wib * 2 + 0) * dim;
+    float* sb = sred + (wib * 2 + 1) * dim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < dim) {
+            *reinterpret_cast<float4*>(sg + c) = dg[i];
+            *reinterpret_cast<float4*>(sb + c) = db[i];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < warps_per_block; ++w) {
+            a += sred[(w * 2 + 0) * dim + c];
+            b += sred[(w * 2 + 1) * dim + c];
+        }
+        dgamma_part[static_cast<long long>(blockIdx.x) * dim + c] = a;
+        dbeta_part[static_cast<long long>(blockIdx.x) * dim + c] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 matrix: grid (col chunks of 256, row slices); block (32, 8)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows,
+                                                          int cols, float* __restrict__ part) {
+    __shared__ float sm[8][256 + 8];
+    const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+    const int nslices = gridDim.y;
+    const int r_begin = static_cast<int>((static_cast<long long>(rows) * blockIdx.y) / nslices);
+    const int r_end = static_cast<int>((static_cast<long long>(rows) * (blockIdx.y + 1)) / nslices);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < cols) {
+        int r = r_begin + threadIdx.y;
+        for (; r + 24 < r_end; r += 32) {  // 4 independent loads in flight per thread
+            uint4 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * k) * ld + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[0] += bf16lo(t[k].x); acc[1] += bf16hi(t[k].x); acc[2] += bf16lo(t[k].y); acc[3] += bf16hi(t[k].y);
+                acc[4] += bf16lo(t[k].z); acc[5] += bf16hi(t[k].z); acc[6] += bf16lo(t[k].w); acc[7] += bf16hi(t[k].w);
+            }
+        }
+        for (; r < r_end; r += 8) {
+            const uint4 t = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + c0);
+            acc[0] += bf16lo(t.x); acc[1] += bf16hi(t.x); acc[2] += bf16lo(t.y); acc[3] += bf16hi(t.y);
+            acc[4] += bf16lo(t.z); acc[5] += bf16hi(t.z); acc[6] += bf16lo(t.w); acc[7] += bf16hi(t.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[threadIdx.y][threadIdx.x * 8 + k] = acc[k];
+    __syncthreads();
+    const int t = threadIdx.y * 32 + threadIdx.x;  // 0..255 -> one column each
+    const int c = blockIdx.x * 256 + t;
+    if (c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sm[w][t];
+        part[static_cast<long long>(blockIdx.y) * cols + c] = s;
+    }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out,
+                                     int round_bf16, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[static_cast<long long>(p) * cols + c];
+    if (round_bf16) s = bf16_round(s);
+    out[c] = accumulate ? out[c] + s : s;
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long n4,
+                                     float* __restrict__ out, int round_bf16, int accumulate) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = reinterpret_cast<const float4*>(partial)[i];
+    for (int k = 1; k < splits; ++k) {
+        const float4 t = reinterpret_cast<const float4*>(partial)[static_cast<long long>(k) * n4 + i];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (round_bf16) { s.x = bf16_round(s.x); s.y = bf16_round(s.y); s.z = bf16_round(s.z); s.w = bf16_round(s.w); }
+    if (accumulate) {
+        const float4 o = reinterpret_cast<const float4*>(out)[i];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch-embed glue
+// ------------------------------------------------------------------------------------------------
+// thread = (b, c, y, x16): 16 consecutive pixels of one image row -> 16 consecutive k of one patch row
+__global__ void patch_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int B, int C,
+                                    int img, int P) {
+    const int segs = img / 16;
+    const long long total = static_cast<long long>(B) * C * img * segs;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x16 = static_cast<int>(i % segs);
+    long long r = i / segs;
+    const int y = static_cast<int>(r % img);
+    r /= img;
+    const int c = static_cast<int>(r % C);
+    const int b = static_cast<int>(r / C);
+    const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<long long>(b) * C + c) * img + y) * img + x16 * 16);
+    const float4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+    const int side = img / P;
+    const int py = y / P, ky = y % P;
+    const int px = (x16 * 16) / P, kx0 = (x16 * 16) % P;
+    const long long row = (static_cast<long long>(b) * side + py) * side + px;
+    __nv_bfloat16* dst = cols + row * (static_cast<long long>(C) * P * P) + (static_cast<long long>(c) * P + ky) * P + kx0;
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(a0.x, a0.y); o0.y = pack_bf16x2(a0.z, a0.w); o0.z = pack_bf16x2(a1.x, a1.y); o0.w = pack_bf16x2(a1.z, a1.w);
+    o1.x = pack_bf16x2(a2.x, a2.y); o1.y = pack_bf16x2(a2.z, a2.w); o1.z = pack_bf16x2(a3.x, a3.y); o1.w = pack_bf16x2(a3.z, a3.w);
+    reinterpret_cast<uint4*>(dst)[0] = o0;
+    reinterpret_cast<uint4*>(dst)[1] = o1;
+}
+
+// net[b, t, d..d+7] = (t == 0 ? cls : float(patch[b*np + t-1])) + pos[t]
+__global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ net, int B, int np, int D) {
+    const int d8 = D / 8;
+    const long long total = static_cast<long long>(B) * (np + 1) * d8;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dc = static_cast<int>(i % d8) * 8;
+    const long long bt = i / d8;
+    const int t = static_cast<int>(bt % (np + 1));
+    const int b = static_cast<int>(bt / (np + 1));
+    float v[8];
+    if (t == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(cls + dc);
+        const float4 c = *reinterpret_cast<const float4*>(cls + dc + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+        const uint4 p = *reinterpret_cast<const uint4*>(patch + (static_cast<long long>(b) * np + (t - 1)) * D + dc);
+        v[0] = bf16lo(p.x); v[1] = bf16hi(p.x); v[2] = bf16lo(p.y); v[3] = bf16hi(p.y);
+        v[4] = bf16lo(p.z); v[5] = bf16hi(p.z); v[6] = bf16lo(p.w); v[7] = bf16hi(p.w);
+    }
+    const float4 p0 = *reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D + dc);
+    const float4 p1 = *reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D + dc + 4);
+    float* o = net + bt * D + dc;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0] + p0.x, v[1] + p0.y, v[2] + p0.z, v[3] + p0.w);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
+}
+
+// thread = (t, d4): loops over the batch; dpos[t] = sum_b dnet[b,t]; dpatch = bf16(dnet[:,1:]); dcls = dpos[0]
+__global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dnet, __nv_bfloat16* __restrict__ dpatch,
+                                           float* __restrict__ dpos, float* __restrict__ dcls, int B, int np, int D,
+                                           int accumulate) {
+    const int d4 = D / 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (np + 1) * d4) return;
+    const int dc = (i % d4) * 4;
+    const int t = i / d4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long bstride = static_cast<long long>(np + 1) * D;
+    const float* src = dnet + static_cast<long long>(t) * D + dc;
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(src + b * bstride);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        if (t > 0) {
+            uint2 p;
+            p.x = pack_bf16x2(v.x, v.y);
+            p.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(dpatch + (static_cast<long long>(b) * np + (t - 1)) * D + dc) = p;
+        }
+    }
+    float* pp = dpos + static_cast<long long>(t) * D + dc;
+    if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(pp); *reinterpret_cast<float4*>(pp) = make_float4(o.x + s.x, o.y + s.y, o.z + s.z, o.w + s.w); }
+    else *reinterpret_cast<float4*>(pp) = s;
+    if (t == 0) {
+        float* pc = dcls + dc;
+        if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(pc); *reinterpret_cast<float4*>(pc) = make_float4(o.x + s.x, o.y + s.y, o.z + s.z, o.w + s.w); }
+        else *reinterpret_cast<float4*>(pc) = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax cross entropy: one block per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, long long ldl,
+                                                           const long long* __restrict__ labels,
+                                                           float* __restrict__ loss_rows,
+                                                           __nv_bfloat16* __restrict__ dlogits, int* bad_flag, int B,
+                                                           int C, float gscale) {
+    __shared__ float sred[8];
+    __shared__ float sbc;
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const __nv_bfloat16* lr = logits + static_cast<long long>(row) * ldl;
+    float m = -INFINITY;
+    for (int c = tid; c < C; c += 256) m = fmaxf(m, __bfloat162float(lr[c]));
+    m = warp_max(m);
+    if (lane == 0) sred[wid] = m;
+    __syncthreads();
+    if (tid == 0) { float t = sred[0]; for (int w = 1; w < 8; ++w) t = fmaxf(t, sred[w]); sbc = t; }
+    __syncthreads();
+    m = sbc;
+    float s = 0.f;
+    for (int c = tid; c < C; c += 256) s += expf(__bfloat162float(lr[c]) - m);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) sred[wid] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += sred[w]; sbc = t; }
+    __syncthreads();
+    const float lse = m + logf(sbc);
+    long long lab = labels[row];
+    if (lab < 0 || lab >= C) {  // torch's gather would raise; flag it and clamp so we stay in bounds
+        if (tid == 0) atomicExch(bad_flag, 1);
+        lab = lab < 0 ? 0 : C - 1;
+    }
+    if (tid == 0) loss_rows[row] = lse - __bfloat162float(lr[lab]);
+    if (dlogits != nullptr) {
+        __nv_bfloat16* dr = dlogits + static_cast<long long>(row) * C;
+        const float sc = gscale / static_cast<float>(B);
+        for (int c = tid; c < C; c += 256) {
+            float p = expf(__bfloat162float(lr[c]) - lse);
+            if (c == lab) p -= 1.0f;
+            dr[c] = __float2bfloat16_rn(p * sc);
+        }
+    }
+}
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+    __shared__ float sred[8];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) s += v[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += sred[w]; out[0] = t / static_cast<float>(n); }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+    if (i + 8 <= n) {
+        const float4 a = *reinterpret_cast<const float4*>(src + i);
+        const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+        *reinterpret_cast<uint4*>(dst + i) = o;
+    } else {
+        for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
+    }
+}
+__global__ void fill_f32_kernel(float* __restrict__ dst, float v, long long n) {
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n) *reinterpret_cast<float4*>(dst + i) = make_float4(v, v, v, v);
+    else for (long long k = i; k < n; ++k) dst[k] = v;
+}
+
+template <int NV>
+static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, const float* beta, void* y, float* mean,
+                         float* rstd, int rows, int dim, float eps, cudaStream_t st) {
+    const int blocks = (rows + 7) / 8;
+    layernorm_fwd_kernel<NV><<<blocks, 256, 0, st>>>(x, ld_x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean,
+                                                     rstd, rows, dim, eps);
+    return check_launch("layernorm_fwd");
+}
+template <int NV>
+static int ln_bwd_launch(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
+                         const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
+                         float* dgp, float* dbp, int nparts, int rows, int dim, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(8) * 2 * dim * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    }
+    layernorm_bwd_kernel<NV><<<nparts, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, ld_x, gamma, mean,
+                                                        rstd, dres, dx_out, ld_dx,
+                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgp, dbp, rows, dim);
+    return check_launch("layernorm_bwd");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" long long b200_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const float* beta, void* y_bf16,
+                                  float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t stream) {
+    if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 128 * LN_MAX_V4) return set_error(B200_ERR_ARG, "layernorm_fwd: need 0 < dim <= 1024, dim % 4 == 0");
+    if (ld_x % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_fwd: ld_x % 4 != 0");
+    const int nv = (dim + 127) / 128;
+    if (nv <= 4) return ln_fwd_launch<4>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
+    if (nv <= 6) return ln_fwd_launch<6>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
+    return ln_fwd_launch<8>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma,
+                                  const float* mean, const float* rstd, const float* dres, float* dx_out,
+                                  long long ld_dx, void* dx_bf16, float* dgamma_part, float* dbeta_part, int max_parts,
+                                  int* nparts_out, int rows, int dim, cudaStream_t stream) {
+    if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 128 * LN_MAX_V4) return set_error(B200_ERR_ARG, "layernorm_bwd: need 0 < dim <= 1024, dim % 4 == 0");
+    if (ld_x % 4 != 0 || ld_dx % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_bwd: ld % 4 != 0");
+    if (max_parts < 1) return set_error(B200_ERR_ARG, "layernorm_bwd: max_parts < 1");
+    int nparts = num_sms() * 4;
+    const int need = (rows + 7) / 8;
+    if (nparts > need) nparts = need;
+    if (nparts > max_parts) nparts = max_parts;
+    if (nparts_out) *nparts_out = nparts;
+    const int nv = (dim + 127) / 128;
+    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
+    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
+    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
+}
+
+extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
+                                int* nparts_out, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || cols % 8 != 0 || ld % 8 != 0) return set_error(B200_ERR_ARG, "colsum: cols and ld must be multiples of 8");
+    if (max_parts < 1) return set_error(B200_ERR_ARG, "colsum: max_parts < 1");
+    const int chunks = (cols + 255) / 256;
+    int slices = (num_sms() * 4) / chunks;
+    if (slices < 1) slices = 1;
+    if (slices > (rows + 7) / 8) slices = (rows + 7) / 8;
+    if (slices > max_parts) slices = max_parts;
+    if (nparts_out) *nparts_out = slices;
+    colsum_bf16_kernel<<<dim3(chunks, slices), dim3(32, 8), 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, cols, part);
+    return check_launch("colsum_bf16");
+}
+
+extern "C" int b200_colsum_finish(const float* part, int nparts, int cols, float* out, int round_bf16, int accumulate,
+                                  cudaStream_t stream) {
+    if (nparts <= 0 || cols <= 0) return set_error(B200_ERR_ARG, "colsum_finish: bad size");
+    colsum_finish_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(part, nparts, cols, out, round_bf16, accumulate);
+    return check_launch("colsum_finish");
+}
+
+extern "C" int b200_splitk_reduce(const float* partial, int splits, long long n, float* out, int round_bf16,
+                                  int accumulate, cudaStream_t stream) {
+    if (splits < 1 || n <= 0 || n % 4 != 0) return set_error(B200_ERR_ARG, "splitk_reduce: n must be a positive multiple of 4");
+    const long long n4 = n / 4;
+    splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(partial, splits, n4, out, round_bf16, accumulate);
+    return check_launch("splitk_reduce");
+}
+
+extern "C" int b200_patch_im2col(const float* x, void* cols_bf16, int B, int C, int img, int patch, cudaStream_t stream) {
+    if (B <= 0 || C <= 0 || img <= 0 || patch <= 0 || patch % 16 != 0 || img % patch != 0) return set_error(B200_ERR_ARG, "patch_im2col: need patch % 16 == 0 and img % patch == 0");
+    const long long total = static_cast<long long>(B) * C * img * (img / 16);
+    patch_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(cols_bf16), B, C, img, patch);
+    return check_launch("patch_im2col");
+}
+
+extern "C" int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,
+                                    int D, cudaStream_t stream) {
+    if (B <= 0 || np <= 0 || D <= 0 || D % 8 != 0) return set_error(B200_ERR_ARG, "assemble_tokens: D % 8 != 0");
+    const long long total = static_cast<long long>(B) * (np + 1) * (D / 8);
+    assemble_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(patch_bf16), cls, pos, net, B, np, D);
+    return check_launch("assemble_tokens");
+}
+
+extern "C" int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, float* dcls, int B, int np,
+                                        int D, int accumulate, cudaStream_t stream) {
+    if (B <= 0 || np <= 0 || D <= 0 || D % 4 != 0) return set_error(B200_ERR_ARG, "assemble_tokens_bwd: D % 4 != 0");
+    const int total = (np + 1) * (D / 4);
+    assemble_tokens_bwd_kernel<<<(total + 127) / 128, 128, 0, stream>>>(dnet, reinterpret_cast<__nv_bfloat16*>(dpatch_bf16), dpos, dcls, B, np, D, accumulate);
+    return check_launch("assemble_tokens_bwd");
+}
+
+extern "C" int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels,
+                                         float* loss_rows, float* loss_mean, void* dlogits_bf16, int* bad_label_flag,
+                                         int B, int C, float grad_scale, cudaStream_t stream) {
+    if (B <= 0 || C <= 0) return set_error(B200_ERR_ARG, "softmax_xent: bad size");
+    if (bad_label_flag == nullptr || loss_rows == nullptr) return set_error(B200_ERR_ARG, "softmax_xent: null output");
+    softmax_xent_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ldl, labels, loss_rows,
+                                               reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), bad_label_flag, B, C, grad_scale);
+    int rc = check_launch("softmax_xent");
+    if (rc) return rc;
+    if (loss_mean != nullptr) {
+        mean_kernel<<<1, 256, 0, stream>>>(loss_rows, B, loss_mean);
+        rc = check_launch("loss_mean");
+    }
+    return rc;
+}
+
+extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream) {
+    if (n <= 0) return set_error(B200_ERR_ARG, "cast: n <= 0");
+    const long long thr = (n + 7) / 8;
+    cast_f32_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+    return check_launch("cast_f32_bf16");
+}
+extern "C" int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream) {
+    if (n <= 0) return set_error(B200_ERR_ARG, "fill: n <= 0");
+    const long long thr = (n + 3) / 4;
+    fill_f32_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, stream>>>(dst, value, n);
+    return check_launch("fill_f32");
+}

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C-ABI: PyTorch supplies device memory and the current stream, nothing else.
+
+Every function launches hand-written sm_100a kernels from ``libb200_cflearn.so`` on the *current* CUDA stream
+(autograd's backward thread included) and raises ``B200Error`` on any failure.  No function here has a CPU or
+ATen fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import B200Error, call
+
+EPI_BIAS_BF16 = 0
+EPI_BIAS_GELU_BF16 = 1
+EPI_BIAS_RESID_F32 = 2
+EPI_DGELU_BF16 = 3
+EPI_PARTIAL_F32 = 4
+
+_MAX_PARTS = 1024
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise B200Error("b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+class Workspace:
+    """Per-device scratch for split-K partials and column-sum partials (grown on demand, never freed)."""
+
+    def __init__(self) -> None:
+        self._bufs = {}
+
+    def get(self, device: torch.device, nfloats: int, tag: str = "ws") -> Tensor:
+        key = (device.index, tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nfloats:
+            buf = torch.empty(max(nfloats, 1 << 20), dtype=torch.float32, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+WORKSPACE = Workspace()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------------------------
+def gemm(
+    a: Tensor,
+    b: Tensor,
+    *,
+    a_mn_major: bool = False,
+    b_mn_major: bool = False,
+    epilogue: int = EPI_BIAS_BF16,
+    bias: Optional[Tensor] = None,
+    out0: Optional[Tensor] = None,
+    out1: Optional[Tensor] = None,
+    aux: Optional[Tensor] = None,
+    splits: int = 1,
+    max_ctas: int = 0,
+) -> Tensor:
+    """C[M,N] = A . B^T on tcgen05.  ``a``: [M,K] (or [K,M] if a_mn_major); ``b``: [N,K] (or [K,N])."""
+    _need_cuda(a, b, bias, out0, out1, aux)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise B200Error("gemm operands must be bf16")
+    if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise B200Error("gemm operands must be 2-D with unit inner stride")
+    if a_mn_major:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn_major:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    if K != Kb:
+        raise B200Error(f"gemm reduction mismatch: {K} vs {Kb}")
+    f32_out = epilogue in (EPI_BIAS_RESID_F32, EPI_PARTIAL_F32)
+    if out0 is None:
+        shape = (splits, M, N) if epilogue == EPI_PARTIAL_F32 else (M, N)
+        out0 = torch.empty(shape, dtype=torch.float32 if f32_out else torch.bfloat16, device=a.device)
+    if out0.dtype != (torch.float32 if f32_out else torch.bfloat16):
+        raise B200Error("gemm: out0 dtype does not match the epilogue")
+    ldo = out0.stride(-2)
+    call(
+        "b200_gemm_bf16",
+        a.data_ptr(), a.stride(0), int(a_mn_major),
+        b.data_ptr(), b.stride(0), int(b_mn_major),
+        M, N, K, epilogue, _ptr(bias), out0.data_ptr(), _ptr(out1), _ptr(aux), ldo, splits, max_ctas, _stream(),
+    )
+    return out0
+
+
+def pick_splits(M: int, N: int, K: int) -> int:
+    return int(_cabi.lib().b200_gemm_pick_splits(M, N, K))
+
+
+def wgrad(dy: Tensor, x: Tensor, out: Tensor, *, round_bf16: bool = True, accumulate: bool = False) -> Tensor:
+    """out[N_out, K_in] (fp32) (+)= dy[M, N_out]^T . x[M, K_in]   (split-K over the M tokens, then reduce)."""
+    M, n_out = dy.shape
+    k_in = x.shape[1]
+    splits = pick_splits(n_out, k_in, M)
+    part = WORKSPACE.get(dy.device, splits * n_out * k_in, "splitk")[: splits * n_out * k_in].view(splits, n_out, k_in)
+    gemm(dy, x, a_mn_major=True, b_mn_major=True, epilogue=EPI_PARTIAL_F32, out0=part, splits=splits)
+    call("b200_splitk_reduce", part.data_ptr(), splits, n_out * k_in, out.data_ptr(), int(round_bf16), int(accumulate), _stream())
+    return out
+
+
+def colsum(x: Tensor, out: Tensor, *, round_bf16: bool = True, accumulate: bool = False) -> Tensor:
+    """out[cols] (fp32) (+)= sum over rows of x[rows, cols] (bf16): bias gradients."""
+    _need_cuda(x, out)
+    rows, cols = x.shape
+    part = WORKSPACE.get(x.device, _MAX_PARTS * cols, "colsum")
+    nparts = ctypes.c_int(0)
+    call("b200_colsum_bf16", x.data_ptr(), x.stride(0), rows, cols, part.data_ptr(), _MAX_PARTS, ctypes.byref(nparts), _stream())
+    call("b200_colsum_finish", part.data_ptr(), nparts.value, cols, out.data_ptr(), int(round_bf16), int(accumulate), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ----------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, rows: int, dim: int, ld_x: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(x, gamma, beta)
+    y = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    call("b200_layernorm_fwd", x.data_ptr(), ld_x, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(
+    dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, *, rows: int, dim: int, ld_x: int,
+    dres: Optional[Tensor], dx_out: Tensor, ld_dx: int, dx_bf16: Optional[Tensor],
+    dgamma: Tensor, dbeta: Tensor, accumulate: bool = False,
+) -> None:
+    part = WORKSPACE.get(x.device, 2 * _MAX_PARTS * dim, "lnbwd")
+    pg = part[: _MAX_PARTS * dim]
+    pb = part[_MAX_PARTS * dim : 2 * _MAX_PARTS * dim]
+    nparts = ctypes.c_int(0)
+    call(
+        "b200_layernorm_bwd", dy.data_ptr(), x.data_ptr(), ld_x, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+        _ptr(dres), dx_out.data_ptr(), ld_dx, _ptr(dx_bf16), pg.data_ptr(), pb.data_ptr(), _MAX_PARTS,
+        ctypes.byref(nparts), rows, dim, _stream(),
+    )
+    call("b200_colsum_finish", pg.data_ptr(), nparts.value, dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
+    call("b200_colsum_finish", pb.data_ptr(), nparts.value, dim, dbeta.data_ptr(), 0, int(accumulate), _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def attention_fwd(qkv: Tensor, B: int, T: int, H: int, *, scale: Optional[float] = None, causal: bool = False) -> Tuple[Tensor, Tensor]:
+    _need_cuda(qkv)
+    D = H * 64
+    if qkv.dtype != torch.bfloat16 or qkv.numel() != B * T * 3 * D or not qkv.is_contiguous():
+        raise B200Error("attention_fwd: qkv must be contiguous bf16 [B, T, 3*H*64]")
+    out = torch.empty((B * T, D), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+    sc = float(scale) if scale is not None else 0.125
+    call("b200_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, H, 64, sc, int(causal), _stream())
+    return out, lse
+
+
+def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, B: int, T: int, H: int, *, scale: Optional[float] = None, causal: bool = False, dqkv: Optional[Tensor] = None) -> Tensor:
+    _need_cuda(qkv, out, dout, lse)
+    D = H * 64
+    if dqkv is None:
+        dqkv = torch.empty((B * T, 3 * D), dtype=torch.bfloat16, device=qkv.device)
+    sc = float(scale) if scale is not None else 0.125
+    call("b200_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, 64, sc, int(causal), _stream())
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# patch embedding glue, loss, casts
+# ----------------------------------------------------------------------------------------------------------------
+def patch_im2col(x: Tensor, patch: int) -> Tensor:
+    _need_cuda(x)
+    B, C, Hh, Ww = x.shape
+    if Hh != Ww or x.dtype != torch.float32 or not x.is_contiguous():
+        raise B200Error("patch_im2col: need contiguous fp32 [B, C, S, S]")
+    side = Hh // patch
+    cols = torch.empty((B * side * side, C * patch * patch), dtype=torch.bfloat16, device=x.device)
+    call("b200_patch_im2col", x.data_ptr(), cols.data_ptr(), B, C, Hh, patch, _stream())
+    return cols
+
+
+def assemble_tokens(patch: Tensor, cls: Tensor, pos: Tensor, B: int, np_: int, D: int) -> Tensor:
+    net = torch.empty((B, np_ + 1, D), dtype=torch.float32, device=patch.device)
+    call("b200_assemble_tokens", patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), net.data_ptr(), B, np_, D, _stream())
+    return net
+
+
+def assemble_tokens_bwd(dnet: Tensor, dpos: Tensor, dcls: Tensor, B: int, np_: int, D: int, accumulate: bool = False) -> Tensor:
+    dpatch = torch.empty((B * np_, D), dtype=torch.bfloat16, device=dnet.device)
+    call("b200_assemble_tokens_bwd", dnet.data_ptr(), dpatch.data_ptr(), dpos.data_ptr(), dcls.data_ptr(), B, np_, D, int(accumulate), _stream())
+    return dpatch
+
+
+def softmax_xent(logits: Tensor, labels: Tensor, *, grad_scale: float = 1.0, need_grad: bool = True) -> Tuple[Tensor, Tensor, Optional[Tensor], Tensor]:
+    """Returns (loss_mean[1], loss_rows[B], dlogits bf16 [B,C] or None, bad_label_flag int32[1])."""
+    _need_cuda(logits, labels)
+    Bn, C = logits.shape
+    if logits.dtype != torch.bfloat16 or logits.stride(1) != 1:
+        raise B200Error("softmax_xent: logits must be bf16 with unit inner stride")
+    if labels.dtype != torch.int64 or labels.numel() != Bn or not labels.is_contiguous():
+        raise B200Error("softmax_xent: labels must be contiguous int64 with one entry per row")
+    loss_rows = torch.empty(Bn, dtype=torch.float32, device=logits.device)
+    loss_mean = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty((Bn, C), dtype=torch.bfloat16, device=logits.device) if need_grad else None
+    bad = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    call(
+        "b200_softmax_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), loss_rows.data_ptr(),
+        loss_mean.data_ptr(), _ptr(dlogits), bad.data_ptr(), Bn, C, float(grad_scale), _stream(),
+    )
+    return loss_mean, loss_rows, dlogits, bad
+
+
+def cast_bf16(src: Tensor, dst: Optional[Tensor] = None) -> Tensor:
+    _need_cuda(src)
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        raise B200Error("cast_bf16: need contiguous fp32")
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    call("b200_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    return dst
+
+
+def fill_f32(dst: Tensor, value: float) -> Tensor:
+    call("b200_fill_f32", dst.data_ptr(), float(value), dst.numel(), _stream())
+    return dst

@@ -1,0 +1,143 @@
+/* b200_cflearn.h -- C-ABI of the B200-native transformer-block training-step kernels.
+ *
+ * The reference (carefree-learn @ ca5ced1) has NO native code and no FFI: its plug-in surface is a Python
+ * registry of nn.Module classes (cflearn/modules/common.py:30-53) whose forward()s call torch.nn.functional.
+ * This header is therefore the boundary a maintainer would bind from Python (ctypes stub in INTEGRATION.md);
+ * each entry point names the reference call site (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise, caller-owned,
+ *     16-byte aligned, dense row-major with the documented leading dimension;
+ *   - asynchronous on `stream`; never allocates, never synchronises, never falls back to the CPU;
+ *   - returns 0 on success or a negative B200_ERR_* code; b200_last_error() describes the last failure
+ *     on the calling thread;
+ *   - bf16 = IEEE bfloat16 (round-to-nearest-even), f32 = IEEE binary32.
+ */
+#ifndef B200_CFLEARN_H_
+#define B200_CFLEARN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum {
+    B200_OK = 0,
+    B200_ERR_ARG = -1,    /* invalid argument (shape, null pointer, unsupported combination) */
+    B200_ERR_ALIGN = -2,  /* pointer / stride alignment requirement violated */
+    B200_ERR_DRIVER = -3, /* CUDA driver entry point missing or tensor-map encode failed */
+    B200_ERR_LAUNCH = -4, /* kernel launch failed (cudaGetLastError) */
+    B200_ERR_NO_DEVICE = -5
+};
+
+/* GEMM epilogues (b200_gemm_bf16) */
+enum {
+    B200_EPI_BIAS_BF16 = 0,      /* out0[bf16] = bf16(acc + bias)                                               */
+    B200_EPI_BIAS_GELU_BF16 = 1, /* out0 = h = bf16(acc + bias); out1 = bf16(gelu_erf(h))                        */
+    B200_EPI_BIAS_RESID_F32 = 2, /* out0[f32] = aux[f32] + float(bf16(acc + bias))   (aux may alias out0)         */
+    B200_EPI_DGELU_BF16 = 3,     /* out0[bf16] = bf16(float(bf16(acc)) * gelu_erf'(aux[bf16]))                   */
+    B200_EPI_PARTIAL_F32 = 4     /* out0[f32][split, M, N] = partial accumulators (split-K)                      */
+};
+
+int b200_abi_version(void);
+const char* b200_last_error(void);
+/* number of kernels this library has launched on the calling process so far (bench.py's gpu_launches) */
+long long b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense layers: C[M,N] = A[M,K] . B[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+ *   a_mn_major = 0: A is row-major [M, lda] (K contiguous);  1: A is row-major [K, lda] (M contiguous).
+ *   b_mn_major = 0: B is row-major [N, ldb] (K contiguous);  1: B is row-major [K, ldb] (N contiguous).
+ *   bias: bf16 [N] or NULL.  ldo: leading dimension (elements) of out0/out1/aux.  N % 8 == 0.
+ *   splits > 1 only with B200_EPI_PARTIAL_F32 (out0 is f32 [splits, M, ldo]).  max_ctas <= 0: all SMs.
+ * Replaces F.linear at cflearn/modules/core/customs.py:85-89 (Linear.forward), the packed-QKV projection at
+ * cflearn/modules/core/attentions.py:214, FeedForward's Linear->GELU->Linear at
+ * cflearn/modules/core/mixed_stacks/channel_mixers.py:29-36, the k=s=16 patch-embed F.conv2d at
+ * cflearn/modules/core/convs/basic.py:155-174, and autograd's dgrad/wgrad of all of them.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                   int M, int N, int K, int epilogue, const void* bias, void* out0, void* out1, const void* aux,
+                   long long ldo, int splits, int max_ctas, cudaStream_t stream);
+/* split count that fills the 148 SMs best for an [M,N] output with reduction length K */
+int b200_gemm_pick_splits(int M, int N, int K);
+/* out[f32][n] (+)= round( sum_s partial[s][n] ); round_bf16 mirrors autocast (the weight grad of a bf16 matmul
+ * is produced in bf16, cf. cflearn/schema.py:1266-1276 autocast + :980 backward). accumulate: 0 overwrite. */
+int b200_splitk_reduce(const float* partial, int splits, long long n, float* out, int round_bf16, int accumulate,
+                       cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (fp32 statistics), replaces nn.LayerNorm built by NormFactory("layer")
+ * (cflearn/modules/core/norms.py:88-89,118-124; used at mixed_stacks/api.py:141,155,397-402).
+ *   x: f32 [rows, ld_x] (first `dim` columns are normalised; ld_x lets the head LN read only token 0 of each
+ *   image -- api.py:365).  y: bf16 [rows, dim] (the value autocast hands to the next F.linear).
+ *   mean, rstd: f32 [rows], saved for backward.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const float* beta, void* y_bf16,
+                       float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t stream);
+/* dx_out[f32] = (dres ? dres : 0) + LN'(dy); dx_out row stride ld_dx (so the head LN can scatter into token 0).
+ * dy: bf16 [rows, dim].  dx_bf16 (optional) receives bf16(dx_out) -- the gradient the preceding bf16 matmul
+ * output sees under autocast.  dgamma_part/dbeta_part: f32 [nparts, dim] workspace, reduced by
+ * b200_colsum_finish.  Returns nparts through *nparts_out (host int). */
+int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma, const float* mean,
+                       const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
+                       float* dgamma_part, float* dbeta_part, int max_parts, int* nparts_out, int rows, int dim,
+                       cudaStream_t stream);
+
+/* column sums: part[p][c] = sum over a slice of rows of x[r][c]  (x bf16 or f32), then finish() reduces the
+ * parts.  Bias gradients of every Linear (autograd of customs.py:89) and LN gamma/beta gradients. */
+int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
+                     int* nparts_out, cudaStream_t stream);
+int b200_colsum_finish(const float* part, int nparts, int cols, float* out, int round_bf16, int accumulate,
+                       cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention on the PACKED qkv tensor, replaces the split/permute/contiguous copies at
+ * cflearn/modules/core/attentions.py:216,180-185,245,270 and F.scaled_dot_product_attention reached through
+ * cflearn/toolkit.py:911-974 (sdp_attn).  qkv: bf16 [B, T, 3*H*Dh] laid out [q | k | v], heads contiguous
+ * inside each third (chunk(3, dim=-1) then view(B,T,H,Dh)).  out: bf16 [B, T, H*Dh].  lse: f32 [B, H, T]
+ * (natural-log sum-exp of the scaled scores), saved for backward.  causal != 0 applies the lower-triangular
+ * mask of cflearn/modules/nlp/encoder/transformer.py:42-48.  Dh must be 64, T <= 256.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int H, int Dh, float scale,
+                       int causal, cudaStream_t stream);
+int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                       void* dqkv_bf16, int B, int T, int H, int Dh, float scale, int causal, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Patch embedding glue (cflearn/modules/core/high_level.py:143-149,181-188, mixed_stacks/api.py:419-438):
+ *   im2col : x f32 [B, C, IMG, IMG] (NCHW) -> cols bf16 [B*(IMG/P)^2, C*P*P]  (k index = (c, ky, kx))
+ *   assemble: net f32 [B, 1+np, D] = cat(cls, float(patch bf16 [B*np, D])) + pos[1+np, D]
+ *   assemble_bwd: dpatch bf16 [B*np, D] = bf16(dnet[:,1:,:]); dpos f32 [1+np, D] = sum_b dnet; dcls f32 [D]
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_patch_im2col(const float* x, void* cols_bf16, int B, int C, int img, int patch, cudaStream_t stream);
+int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,
+                         int D, cudaStream_t stream);
+int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, float* dcls, int B, int np, int D,
+                             int accumulate, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Cross entropy with integer labels (cflearn/losses/basic.py:137-141: -log_softmax(logits,1).gather(1,labels),
+ * mean over the batch via ILoss._reduce, cflearn/schema.py:767-810).  logits bf16 [B, C] (ld = ldl),
+ * labels int64 [B].  loss_rows f32 [B], loss_mean f32 [1].  dlogits bf16 [B, C] = bf16((softmax - onehot) *
+ * grad_scale / B).  The label gather is integer-exact; out-of-range labels set *bad_label_flag (device int).
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels, float* loss_rows,
+                              float* loss_mean, void* dlogits_bf16, int* bad_label_flag, int B, int C,
+                              float grad_scale, cudaStream_t stream);
+
+/* element-wise helpers */
+int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream);
+int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_CFLEARN_H_ */

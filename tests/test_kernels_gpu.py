@@ -1,0 +1,325 @@
+"""GPU parity tests of every C-ABI kernel against plain PyTorch references of the same op (fp32 math,
+bf16 rounding at the same points the reference's autocast path rounds).  Run on the B200 box: pytest -m gpu."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cflearn_b200  # noqa: F401  (registers the package)
+from cflearn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand_bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def _relerr(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _assert_bf16_close(got, ref_f32, what, max_ulps=1.01):
+    """`got` (bf16) must equal bf16(ref) up to one bf16 ulp at a tiny fraction of positions."""
+    ref = ref_f32.to(torch.bfloat16)
+    rel = _relerr(got, ref)
+    assert rel < 2e-3, f"{what}: relative L2 error {rel}"
+    diff = (got.float() - ref.float()).abs()
+    tol = ref.float().abs() * (2.0 ** -7) * max_ulps + 1e-3 * ref.float().abs().max()
+    frac_bad = (diff > tol).float().mean().item()
+    assert frac_bad == 0.0, f"{what}: {frac_bad:.3e} of the elements differ by more than {max_ulps} bf16 ulp"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------------------
+def test_cast_and_fill():
+    x = torch.randn(1000003, device=DEV)
+    y = ops.cast_bf16(x)
+    assert torch.equal(y, x.to(torch.bfloat16))
+    z = torch.empty(12345, device=DEV)
+    ops.fill_f32(z, 2.5)
+    assert torch.equal(z, torch.full_like(z, 2.5))
+
+
+@pytest.mark.parametrize("rows,dim", [(50432 // 8, 768), (1000, 512), (77, 1024), (5, 256)])
+def test_layernorm_fwd(rows, dim):
+    torch.manual_seed(0)
+    x = torch.randn(rows, dim, device=DEV) * 2 + 0.5
+    g = torch.randn(dim, device=DEV)
+    b = torch.randn(dim, device=DEV)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6, rows=rows, dim=dim, ld_x=dim)
+    ref = F.layer_norm(x, (dim,), g, b, 1e-6)
+    _assert_bf16_close(y, ref, "layernorm_fwd")
+    assert torch.allclose(mean, x.mean(-1), atol=1e-5)
+    assert torch.allclose(rstd, (x.var(-1, unbiased=False) + 1e-6).rsqrt(), rtol=1e-4)
+
+
+def test_layernorm_fwd_strided_head():
+    # head LN reads only token 0 of every image (row stride = T * D)
+    B, T, D = 16, 197, 768
+    net = torch.randn(B, T, D, device=DEV)
+    g = torch.randn(D, device=DEV)
+    b = torch.randn(D, device=DEV)
+    y, _, _ = ops.layernorm_fwd(net, g, b, 1e-6, rows=B, dim=D, ld_x=T * D)
+    _assert_bf16_close(y, F.layer_norm(net[:, 0], (D,), g, b, 1e-6), "layernorm_fwd strided")
+
+
+@pytest.mark.parametrize("rows,dim,with_res", [(4096, 768, True), (333, 512, False), (50, 1024, True)])
+def test_layernorm_bwd(rows, dim, with_res):
+    torch.manual_seed(1)
+    x = (torch.randn(rows, dim, device=DEV) * 1.5 + 0.3).requires_grad_(True)
+    g = torch.randn(dim, device=DEV, requires_grad=True)
+    b = torch.randn(dim, device=DEV, requires_grad=True)
+    dy = torch.randn(rows, dim, device=DEV).to(torch.bfloat16)
+    dres = torch.randn(rows, dim, device=DEV) if with_res else None
+    y = F.layer_norm(x, (dim,), g, b, 1e-6)
+    y.backward(dy.float())
+    _, mean, rstd = ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-6, rows=rows, dim=dim, ld_x=dim)
+    dx = torch.empty(rows, dim, device=DEV)
+    dxb = torch.empty(rows, dim, device=DEV, dtype=torch.bfloat16)
+    dg = torch.empty(dim, device=DEV)
+    db = torch.empty(dim, device=DEV)
+    ops.layernorm_bwd(dy, x.detach(), g.detach(), mean, rstd, rows=rows, dim=dim, ld_x=dim, dres=dres, dx_out=dx,
+                      ld_dx=dim, dx_bf16=dxb, dgamma=dg, dbeta=db)
+    ref_dx = x.grad + (dres if with_res else 0)
+    assert _relerr(dx, ref_dx) < 1e-5
+    assert torch.equal(dxb, dx.to(torch.bfloat16))
+    assert _relerr(dg, g.grad) < 1e-5
+    assert _relerr(db, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols", [(50432 // 4, 2304), (1000, 768), (256, 1000), (7, 3072)])
+def test_colsum(rows, cols):
+    x = _rand_bf16(rows, cols, seed=3)
+    out = torch.empty(cols, device=DEV)
+    ops.colsum(x, out, round_bf16=False)
+    assert _relerr(out, x.float().sum(0)) < 1e-5
+    ops.colsum(x, out, round_bf16=True, accumulate=True)
+    ref = x.float().sum(0) + x.float().sum(0).to(torch.bfloat16).float()
+    assert _relerr(out, ref) < 1e-3
+
+
+def test_patch_glue():
+    B, C, S, P, D = 4, 3, 224, 16, 768
+    torch.manual_seed(0)
+    x = torch.randn(B, C, S, S, device=DEV)
+    cols = ops.patch_im2col(x, P)
+    ref = F.unfold(x, kernel_size=P, stride=P).transpose(1, 2).reshape(B * 196, C * P * P)
+    assert torch.equal(cols, ref.to(torch.bfloat16))
+    patch = _rand_bf16(B * 196, D, seed=4)
+    cls = torch.randn(1, 1, D, device=DEV)
+    pos = torch.randn(1, 197, D, device=DEV)
+    net = ops.assemble_tokens(patch, cls, pos, B, 196, D)
+    ref_net = torch.cat([cls.expand(B, 1, D), patch.view(B, 196, D).float()], 1) + pos
+    assert torch.equal(net, ref_net)
+    dnet = torch.randn(B, 197, D, device=DEV)
+    dpos = torch.empty(197, D, device=DEV)
+    dcls = torch.empty(D, device=DEV)
+    dpatch = ops.assemble_tokens_bwd(dnet, dpos, dcls, B, 196, D)
+    assert torch.equal(dpatch, dnet[:, 1:].reshape(B * 196, D).to(torch.bfloat16))
+    assert _relerr(dpos, dnet.sum(0)) < 1e-6
+    assert _relerr(dcls, dnet[:, 0].sum(0)) < 1e-6
+
+
+def test_patch_im2col_p32():
+    x = torch.randn(2, 3, 224, 224, device=DEV)
+    cols = ops.patch_im2col(x, 32)
+    ref = F.unfold(x, kernel_size=32, stride=32).transpose(1, 2).reshape(2 * 49, 3 * 32 * 32)
+    assert torch.equal(cols, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,C", [(256, 1000), (32, 10), (3, 50000)])
+def test_softmax_xent(B, C):
+    torch.manual_seed(2)
+    logits = (torch.randn(B, C, device=DEV) * 3).to(torch.bfloat16)
+    labels = torch.randint(0, C, (B,), device=DEV)
+    loss_mean, loss_rows, dlogits, bad = ops.softmax_xent(logits, labels)
+    lf = logits.float().requires_grad_(True)
+    ref_rows = -F.log_softmax(lf, dim=1).gather(1, labels[:, None])[:, 0]
+    ref_rows.mean().backward()
+    assert bad.item() == 0
+    assert torch.allclose(loss_rows, ref_rows, rtol=1e-5, atol=1e-5)
+    assert abs(loss_mean.item() - ref_rows.mean().item()) < 1e-5 * max(1.0, abs(ref_rows.mean().item()))
+    _assert_bf16_close(dlogits, lf.grad, "dlogits")
+    # integer label path is exact: the gathered logit equals logits[row, label] bit for bit
+    picked = logits.gather(1, labels[:, None])[:, 0].float()
+    lse = torch.logsumexp(logits.float(), 1)
+    assert torch.allclose(loss_rows, lse - picked, rtol=1e-5, atol=1e-5)
+
+
+def test_softmax_xent_bad_label_is_flagged():
+    logits = torch.zeros(4, 8, device=DEV, dtype=torch.bfloat16)
+    labels = torch.tensor([0, 9, 2, -1], device=DEV)
+    _, _, _, bad = ops.softmax_xent(logits, labels)
+    assert bad.item() == 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ------------------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(128, 256, 64), (256, 256, 128), (384, 512, 192), (300, 264, 200), (2048, 768, 768), (256, 1000, 768)]
+
+
+def _operands(M, N, K, a_mn, b_mn, seed=0):
+    a = _rand_bf16(M, K, seed=seed)
+    b = _rand_bf16(N, K, scale=0.5, seed=seed + 1)
+    a_arg = a.t().contiguous() if a_mn else a
+    b_arg = b.t().contiguous() if b_mn else b
+    return a, b, a_arg, b_arg
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_kmajor_bias(M, N, K):
+    a, b, a_arg, b_arg = _operands(M, N, K, False, False)
+    bias = _rand_bf16(N, seed=7)
+    out = ops.gemm(a_arg, b_arg, bias=bias)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias.float()
+    _assert_bf16_close(out, ref, f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 512, 192), (328, 264, 200), (768, 768, 4096)])
+def test_gemm_mn_major(M, N, K, a_mn, b_mn):
+    a, b, a_arg, b_arg = _operands(M, N, K, a_mn, b_mn, seed=11)
+    out = ops.gemm(a_arg, b_arg, a_mn_major=a_mn, b_mn_major=b_mn)
+    torch.cuda.synchronize()
+    _assert_bf16_close(out, a.float() @ b.float().t(), f"gemm mn-major a={a_mn} b={b_mn} {M}x{N}x{K}")
+
+
+def test_gemm_persistent_many_tiles():
+    # 8192 x 2304 x 768: 576 tiles over 148 CTAs -> several tiles per CTA, smem ring and TMEM phases wrap
+    M, N, K = 8192, 2304, 768
+    a, b, a_arg, b_arg = _operands(M, N, K, False, False, seed=21)
+    bias = _rand_bf16(N, seed=22)
+    out = ops.gemm(a_arg, b_arg, bias=bias)
+    torch.cuda.synchronize()
+    _assert_bf16_close(out, a.float() @ b.float().t() + bias.float(), "gemm persistent")
+    out2 = ops.gemm(a_arg, b_arg, bias=bias, max_ctas=5)
+    assert torch.equal(out, out2), "result must not depend on the number of CTAs"
+
+
+def test_gemm_gelu_epilogue():
+    M, N, K = 1024, 3072, 768
+    a, b, a_arg, b_arg = _operands(M, N, K, False, False, seed=31)
+    bias = _rand_bf16(N, seed=32)
+    g = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a_arg, b_arg, bias=bias, epilogue=ops.EPI_BIAS_GELU_BF16, out1=g)
+    torch.cuda.synchronize()
+    ref_h = (a.float() @ b.float().t() + bias.float())
+    _assert_bf16_close(h, ref_h, "gelu epilogue: h")
+    ref_g = F.gelu(h.float())  # GELU of the ROUNDED pre-activation, evaluated in fp32, like ATen on bf16
+    _assert_bf16_close(g, ref_g, "gelu epilogue: gelu(h)")
+
+
+@pytest.mark.parametrize("inplace", [True, False])
+def test_gemm_residual_epilogue(inplace):
+    M, N, K = 1024, 768, 3072
+    a, b, a_arg, b_arg = _operands(M, N, K, False, False, seed=41)
+    bias = _rand_bf16(N, seed=42)
+    res = torch.randn(M, N, device=DEV)
+    ref = res + (a.float() @ b.float().t() + bias.float()).to(torch.bfloat16).float()
+    if inplace:
+        out = res.clone()
+        ops.gemm(a_arg, b_arg, bias=bias, epilogue=ops.EPI_BIAS_RESID_F32, out0=out, aux=out)
+    else:
+        out = ops.gemm(a_arg, b_arg, bias=bias, epilogue=ops.EPI_BIAS_RESID_F32, aux=res)
+    torch.cuda.synchronize()
+    err = (out - ref).abs()
+    # identical up to bf16 rounding flips of the matmul term
+    assert (err > 0.02 * ref.abs().clamp_min(1.0)).float().mean().item() == 0.0
+    assert _relerr(out, ref) < 1e-3
+
+
+def test_gemm_dgelu_epilogue():
+    M, N, K = 512, 3072, 768  # dG[M, 3072] = dY[M, 768] . W2[768, 3072] ; W2 is MN-major B
+    dy = _rand_bf16(M, K, seed=51)
+    w2 = _rand_bf16(K, N, scale=0.05, seed=52)  # [768, 3072] row-major == reference layout [out=768, in=3072]
+    h = _rand_bf16(M, N, seed=53)
+    out = ops.gemm(dy, w2, b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=h)
+    torch.cuda.synchronize()
+    dg = (dy.float() @ w2.float()).to(torch.bfloat16)
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).backward(dg.float())
+    _assert_bf16_close(out, hf.grad, "dgelu epilogue", max_ulps=2.01)
+
+
+@pytest.mark.parametrize("n_out,k_in,M", [(768, 768, 4096), (2304, 768, 2048), (1000, 768, 256), (768, 3072, 1024)])
+def test_wgrad_splitk(n_out, k_in, M):
+    dy = _rand_bf16(M, n_out, seed=61)
+    x = _rand_bf16(M, k_in, seed=62)
+    out = torch.empty(n_out, k_in, device=DEV)
+    ops.wgrad(dy, x, out, round_bf16=False)
+    torch.cuda.synchronize()
+    ref = dy.float().t() @ x.float()
+    assert _relerr(out, ref) < 1e-5
+    ops.wgrad(dy, x, out, round_bf16=True)
+    assert torch.equal(out, ops_ref_round(ref, out))
+
+
+def ops_ref_round(ref, got):
+    # bf16 rounding of two fp32 sums that differ in the last bits may flip; accept either neighbour
+    r = ref.to(torch.bfloat16).float()
+    flips = (r != got)
+    if flips.any():
+        assert flips.float().mean().item() < 1e-3
+        assert ((got - ref).abs()[flips] <= ref.abs()[flips] * 2.0 ** -7 + 1e-6).all()
+        r = torch.where(flips, got, r)
+    return r
+
+
+# ------------------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, B, T, H, causal):
+    D = H * 64
+    q, k, v = qkv.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4).float()  # [B,H,T,64]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, device=s.device, dtype=torch.bool).triu(1), float("-inf"))
+    p = torch.softmax(s, -1)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(B * T, D), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False), (2, 128, 1, True)])
+def test_attention_fwd(B, T, H, causal):
+    qkv = _rand_bf16(B * T, 3 * H * 64, seed=71)
+    out, lse = ops.attention_fwd(qkv, B, T, H, causal=causal)
+    torch.cuda.synchronize()
+    ref_o, ref_lse = _attn_ref(qkv, B, T, H, causal)
+    assert _relerr(out, ref_o) < 5e-3, _relerr(out, ref_o)
+    assert torch.allclose(lse, ref_lse, rtol=1e-4, atol=1e-4)
+    # and against the kernel the reference itself dispatches to (toolkit.py:959-963)
+    q, k, v = qkv.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sdpa = F.scaled_dot_product_attention(q, k, v, is_causal=causal).permute(0, 2, 1, 3).reshape(B * T, H * 64)
+    assert _relerr(out, sdpa) < 5e-3
+
+
+@pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False)])
+def test_attention_bwd(B, T, H, causal):
+    D = H * 64
+    qkv = _rand_bf16(B * T, 3 * D, seed=81)
+    dout = _rand_bf16(B * T, D, seed=82)
+    out, lse = ops.attention_fwd(qkv, B, T, H, causal=causal)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, T, H, causal=causal)
+    torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    ref_o, _ = _attn_ref(qf, B, T, H, causal)
+    ref_o.backward(dout.float())
+    ref = qf.grad
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e = _relerr(dqkv[:, sl], ref[:, sl])
+        assert e < 1e-2, f"{name}: {e}"
+    # eager bf16 SDPA backward as a second opinion
+    q2 = qkv.clone().requires_grad_(True)
+    q, k, v = q2.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    o2 = F.scaled_dot_product_attention(q, k, v, is_causal=causal).permute(0, 2, 1, 3).reshape(B * T, D)
+    o2.backward(dout)
+    assert _relerr(dqkv, q2.grad) < 1.5e-2
