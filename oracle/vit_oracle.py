@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE ONLY -- a plain-PyTorch restatement of the reference's ViT classifier training step.
+
+This is the ORACLE for the B200 kernels: it restates, op by op and in the reference's order, what
+``cflearn.modules`` computes on the hot path named by BASELINE.json.  It is never imported by the product package
+(``carefree-learn_b200/``); only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may use it.
+
+Pinning: ``oracle/make_golden.py`` (run in the build container, where /root/reference exists) checks this file
+bit-for-bit against the reference's own ``ViTEncoder`` / ``Linear`` / ``CrossEntropyLoss`` code imported through
+``oracle/load_reference.py`` and writes the golden fixtures in ``tests/golden/`` that ``tests/test_oracle.py``
+re-checks on every run.  The reference ships no golden vectors of its own for this path.
+
+Every function cites the reference lines it follows (paths relative to /root/reference/cflearn/).
+Run it under ``torch.autocast(device, dtype=torch.bfloat16)`` to get the reference's mixed-precision path
+(accelerate's ``mixed_precision="bf16"`` wraps the same ops, schema.py:1260-1276); without autocast it is the fp32 path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+StateDict = Dict[str, Tensor]
+
+
+def vit_config(name: str = "vit_b16") -> Dict[str, int]:
+    """Shapes of the named configurations (BASELINE.json configs[1] is ``vit_b16``)."""
+    table = {
+        # modules/cv/encoder/transformer.py:19-43 defaults with latent_dim=768 -> 12 heads (:61), FF ratio 4 (:34)
+        "vit_b16": dict(img_size=224, patch_size=16, in_channels=3, latent_dim=768, num_layers=12, num_classes=1000),
+        "vit_tiny": dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, num_layers=2, num_classes=10),
+        "vit_small": dict(img_size=64, patch_size=16, in_channels=3, latent_dim=256, num_layers=3, num_classes=24),
+    }
+    return dict(table[name])
+
+
+def state_dict_spec(cfg: Dict[str, int]) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(key, shape) of ``cv_clf``-style parameters: ViTEncoder keys + ``head.linear.*``."""
+    d, p, c = cfg["latent_dim"], cfg["patch_size"], cfg["in_channels"]
+    n_tok = (cfg["img_size"] // p) ** 2 + 1
+    ff = 4 * d
+    spec: List[Tuple[str, Tuple[int, ...]]] = [
+        ("to_patches.projection.weight", (d, c, p, p)),
+        ("to_patches.projection.bias", (d,)),
+        ("encoder.head_token", (1, 1, d)),
+        ("encoder.pos_encoding.pos_encoding", (1, n_tok, d)),
+    ]
+    for i in range(cfg["num_layers"]):
+        b = f"encoder.mixing_blocks.{i}."
+        spec += [
+            (b + "token_norm.weight", (d,)), (b + "token_norm.bias", (d,)),
+            (b + "token_mixing.net.in_w", (3 * d, d)), (b + "token_mixing.net.qkv_bias", (3 * d,)),
+            (b + "token_mixing.net.out_linear.linear.weight", (d, d)), (b + "token_mixing.net.out_linear.linear.bias", (d,)),
+            (b + "channel_norm.weight", (d,)), (b + "channel_norm.bias", (d,)),
+            (b + "channel_mixing.net.0.linear.weight", (ff, d)), (b + "channel_mixing.net.0.linear.bias", (ff,)),
+            (b + "channel_mixing.net.3.linear.weight", (d, ff)), (b + "channel_mixing.net.3.linear.bias", (d,)),
+        ]
+    spec += [("encoder.head.norms.0.weight", (d,)), ("encoder.head.norms.0.bias", (d,))]
+    spec += [("head.linear.weight", (cfg["num_classes"], d)), ("head.linear.bias", (cfg["num_classes"],))]
+    return spec
+
+
+def init_state_dict(cfg: Dict[str, int], seed: int = 0, *, perturb: bool = True) -> StateDict:
+    """Synthetic weights with the reference's initialisation statistics (mixed_stacks/api.py:405-417,205;
+    convs/basic.py:94-97).  ``perturb`` moves biases / LayerNorm affine parameters off their 0 / 1 initial values so
+    that every term of every kernel is exercised.  Parity is always checked with IDENTICAL injected weights."""
+    g = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for key, shape in state_dict_spec(cfg):
+        if key.endswith("norm.weight") or key.endswith("norms.0.weight"):
+            t = torch.ones(shape) + (0.1 * torch.randn(shape, generator=g) if perturb else 0)
+        elif key.endswith("bias"):
+            t = 0.02 * torch.randn(shape, generator=g) if perturb else torch.zeros(shape)
+        elif key == "to_patches.projection.weight":
+            fan_in = shape[1] * shape[2] * shape[3]
+            fan_out = shape[0] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * (2.0 / (fan_in + fan_out)) ** 0.5  # xavier_normal
+        else:
+            t = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)
+        sd[key] = t.float()
+    return sd
+
+
+def synthetic_batch(cfg: Dict[str, int], batch: int, seed: int = 0) -> Tuple[Tensor, Tensor]:
+    """images ~ N(0,1) fp32, labels uniform int64 [B, 1]."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, cfg["in_channels"], cfg["img_size"], cfg["img_size"], generator=g)
+    y = torch.randint(0, cfg["num_classes"], (batch, 1), generator=g)
+    return x, y
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# forward, op by op
+# -----------------------------------------------------------------------------------------------------------------
+def patch_embed(sd: StateDict, x: Tensor) -> Tensor:
+    """VanillaPatchEmbed.forward (modules/core/high_level.py:181-188): Conv2d k = s = patch, pad 0
+    (convs/basic.py:155-174), then _flatten (high_level.py:143-149): [B,C,h,w] -> [B, h*w, C] contiguous."""
+    w = sd["to_patches.projection.weight"]
+    p = w.shape[-1]
+    net = F.conv2d(x, w, sd["to_patches.projection.bias"], stride=p, padding=0)
+    b, c, h, ww = net.shape
+    return net.view(b, c, h * ww).transpose(1, 2).contiguous()
+
+
+def pre_process(sd: StateDict, patches: Tensor) -> Tensor:
+    """MixedStackedEncoder.pre_process (mixed_stacks/api.py:419-438): cat head token, add learned positional
+    encoding (PositionalEncoding.forward early-return path, api.py:209-228,244-245).  Dropout(0) is the identity."""
+    n = patches.shape[0]
+    head_tokens = sd["encoder.head_token"].repeat([n, 1, 1])
+    net = torch.cat([head_tokens, patches], dim=1)
+    return net + sd["encoder.pos_encoding.pos_encoding"]
+
+
+def attention(sd: StateDict, prefix: str, net: Tensor, num_heads: int, causal: bool = False) -> Tensor:
+    """Attention.forward, qkv_same branch (modules/core/attentions.py:213-277): packed projection, chunk(3),
+    _to_heads (:180-185), sdp_attn -> F.scaled_dot_product_attention(q,k,v,mask,0.0) (toolkit.py:953-963),
+    transpose+contiguous+view (:270-275), out_linear (:277; Linear.forward customs.py:85-89)."""
+    b, t, d = net.shape
+    qkv = F.linear(net, sd[prefix + "in_w"], sd[prefix + "qkv_bias"])
+    q, k, v = qkv.chunk(3, dim=-1)
+    q, k, v = (z.view(b, t, num_heads, d // num_heads).permute(0, 2, 1, 3).contiguous() for z in (q, k, v))
+    mask = None
+    if causal:  # nlp/encoder/transformer.py:42-48 builds the upper-triangular "zeroed" mask; attentions.py:251-253 inverts it
+        mask = ~torch.ones(t, t, dtype=torch.bool, device=net.device).triu(1)
+    out = F.scaled_dot_product_attention(q, k, v, mask, 0.0)
+    out = out.transpose(1, 2).contiguous().view(-1, t, d)
+    return F.linear(out, sd[prefix + "out_linear.linear.weight"], sd[prefix + "out_linear.linear.bias"])
+
+
+def feed_forward(sd: StateDict, prefix: str, net: Tensor) -> Tensor:
+    """FeedForward (mixed_stacks/channel_mixers.py:29-36): Linear -> nn.GELU() (exact erf) -> Dropout(0) -> Linear."""
+    h = F.linear(net, sd[prefix + "0.linear.weight"], sd[prefix + "0.linear.bias"])
+    return F.linear(F.gelu(h), sd[prefix + "3.linear.weight"], sd[prefix + "3.linear.bias"])
+
+
+def mixing_block(sd: StateDict, i: int, net: Tensor, num_heads: int, eps: float) -> Tensor:
+    """MixingBlock._pre_norm_forward (mixed_stacks/api.py:130-158); DropPath / Dropout are identities at rate 0."""
+    b = f"encoder.mixing_blocks.{i}."
+    d = net.shape[-1]
+    t = F.layer_norm(net, (d,), sd[b + "token_norm.weight"], sd[b + "token_norm.bias"], eps)
+    net = net + attention(sd, b + "token_mixing.net.", t, num_heads)
+    c = F.layer_norm(net, (d,), sd[b + "channel_norm.weight"], sd[b + "channel_norm.bias"], eps)
+    return net + feed_forward(sd, b + "channel_mixing.net.", c)
+
+
+def encoder_forward(sd: StateDict, x: Tensor, cfg: Dict[str, int], taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """ViTEncoder.forward (modules/cv/encoder/transformer.py:88-100) -> [B, latent_dim]."""
+    d = cfg["latent_dim"]
+    heads = d // 64  # transformer.py:61
+    eps = 1e-6  # norms.py:118-119
+    net = pre_process(sd, patch_embed(sd, x))
+    if taps is not None:
+        taps["tokens"] = net
+    for i in range(cfg["num_layers"]):
+        net = mixing_block(sd, i, net, heads, eps)
+        if taps is not None:
+            taps[f"block{i}"] = net
+    # head = PreNorm(LayerNorm, Lambda(x[:, 0])) (api.py:365,397-402; high_level.py:42-45): normalise ALL tokens, take token 0
+    net = F.layer_norm(net, (d,), sd["encoder.head.norms.0.weight"], sd["encoder.head.norms.0.bias"], eps)[:, 0]
+    if taps is not None:
+        taps["encoded"] = net
+    return net
+
+
+def classifier_forward(sd: StateDict, x: Tensor, cfg: Dict[str, int], taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """VanillaClassifier.forward (modules/cv/classifier/vanilla.py:57-61) with the ViT encoder (SURVEY finding 4:
+    ``encoder.encode`` is what it would call) and head = Linear(latent_dim, num_classes) (vanilla.py:43)."""
+    enc = encoder_forward(sd, x, cfg, taps)
+    logits = F.linear(enc, sd["head.linear.weight"], sd["head.linear.bias"])
+    if taps is not None:
+        taps["logits"] = logits
+    return logits
+
+
+def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
+    """CrossEntropyLoss._get_stat + ILoss._reduce('mean') (losses/basic.py:137-141; schema.py:767-775).
+    labels: int64 [B, 1]; the gather is an integer index op."""
+    log_prob = F.log_softmax(logits, dim=1)
+    return (-log_prob.gather(dim=1, index=labels)).mean()
+
+
+def train_step(sd: StateDict, x: Tensor, labels: Tensor, cfg: Dict[str, int], *, autocast_bf16: bool,
+               want_taps: bool = False) -> Tuple[Tensor, StateDict, Dict[str, Tensor]]:
+    """One fwd + loss + bwd (IDLModel.train, schema.py:1266-1276 forward/loss under autocast; :980 backward).
+    Returns (loss, grads keyed like the state_dict, taps)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    taps: Dict[str, Tensor] = {}
+    dev = x.device.type
+    with torch.autocast(dev, dtype=torch.bfloat16, enabled=autocast_bf16):
+        logits = classifier_forward(params, x, cfg, taps if want_taps else None)
+        loss = cross_entropy(logits, labels)
+    loss.backward()
+    grads = {k: v.grad for k, v in params.items()}
+    return loss.detach(), grads, {k: v.detach() for k, v in taps.items()}

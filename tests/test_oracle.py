@@ -1,0 +1,64 @@
+"""CPU tests: the oracle restatement (oracle/vit_oracle.py) against the golden vectors generated from the REAL
+reference (oracle/make_golden.py), plus -- when /root/reference is present (build container only) -- a live re-pin."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import vit_oracle as vo  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def fixture():
+    return torch.load(os.path.join(GOLDEN, "vit_tiny_reference.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_oracle_matches_reference_golden(fixture, mode):
+    cfg = vo.vit_config(fixture["config_name"])
+    sd = vo.init_state_dict(cfg, seed=fixture["weights_seed"])
+    x, y = vo.synthetic_batch(cfg, fixture["batch"], seed=fixture["data_seed"])
+    assert torch.equal(x, fixture["x"]) and torch.equal(y, fixture["labels"])
+    loss, grads, taps = vo.train_step(sd, x, y, cfg, autocast_bf16=(mode == "bf16"), want_taps=True)
+    ref = fixture["reference"][mode]
+    # same torch build -> bit-identical; a different CPU / torch build may reorder fp32 sums, so allow a few ulps
+    tol = dict(rtol=1e-5, atol=1e-6) if mode == "fp32" else dict(rtol=2e-2, atol=2e-3)
+    assert torch.allclose(taps["encoded"].float(), ref["encoded"].float(), **tol)
+    assert torch.allclose(taps["logits"].float(), ref["logits"].float(), **tol)
+    assert torch.allclose(loss.float(), ref["loss"].float(), **tol)
+    assert set(grads) == set(ref["grads"])
+    for k, g in ref["grads"].items():
+        err = (grads[k] - g).norm() / g.norm().clamp_min(1e-20)
+        assert err < (1e-4 if mode == "fp32" else 2e-2), (k, err.item())
+
+
+def test_state_dict_contract_matches_reference_vit_b16():
+    with open(os.path.join(GOLDEN, "vit_b16_state_dict_keys.json")) as f:
+        golden = json.load(f)
+    cfg = vo.vit_config("vit_b16")
+    spec = {k: list(s) for k, s in vo.state_dict_spec(cfg) if not k.startswith("head.linear")}
+    assert spec == golden["keys"]
+    assert golden["num_params"] == 85798656  # SURVEY.md finding 5
+
+
+def test_loss_known_answer():
+    # CrossEntropyLoss semantics (losses/basic.py:137-141): uniform logits -> log(C)
+    logits = torch.zeros(5, 7)
+    labels = torch.arange(5)[:, None]
+    assert abs(vo.cross_entropy(logits, labels).item() - torch.log(torch.tensor(7.0)).item()) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_live_pin_against_reference():
+    import make_golden
+
+    make_golden.known_answer_attention()
+    make_golden.pin("vit_tiny", 2, False)
+    make_golden.pin("vit_tiny", 2, True)
