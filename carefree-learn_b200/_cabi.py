@@ -32,7 +32,7 @@ SIGNATURES: Dict[str, Any] = {
     ),
     "b200_gemm_pick_splits": (c_int, [c_int, c_int, c_int]),
     "b200_splitk_reduce": (c_int, [_P, c_int, _LL, _P, c_int, c_int, _P]),
-    "b200_layernorm_fwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "b200_layernorm_fwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "b200_layernorm_bwd": (
         c_int,
         [_P, _P, _LL, _P, _P, _P, _P, _P, _LL, _P, _P, _P, c_int, POINTER(c_int), c_int, c_int, _P],
@@ -44,7 +44,8 @@ SIGNATURES: Dict[str, Any] = {
     "b200_patch_im2col": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
+    "b200_adam_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     "b200_cast_f32_to_bf16": (c_int, [_P, _P, _LL, _P]),
     "b200_fill_f32": (c_int, [_P, c_float, _LL, _P]),
 }

@@ -57,8 +57,9 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ld_x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
-                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                                                            float* __restrict__ rstd_out, int rows, int dim, float eps) {
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int rows, int dim, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -99,10 +100,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
         if (c < dim) {
             const float4 g = *reinterpret_cast<const float4*>(gamma + c);
             const float4 b = *reinterpret_cast<const float4*>(beta + c);
+            const float4 r = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                         (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
             uint2 o;
-            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            o.x = pack_bf16x2(r.x, r.y);
+            o.y = pack_bf16x2(r.z, r.w);
             *reinterpret_cast<uint2*>(yr + c) = o;
+            if (y32 != nullptr) *reinterpret_cast<float4*>(y32 + static_cast<long long>(warp) * dim + c) = r;
         }
     }
 }
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const __nv_bfloat16* 
                                                            const long long* __restrict__ labels,
                                                            float* __restrict__ loss_rows,
                                                            __nv_bfloat16* __restrict__ dlogits, int* bad_flag, int B,
-                                                           int C, float gscale) {
+                                                           int C, float gscale, const float* __restrict__ gscale_dev) {
     __shared__ float sred[8];
     __shared__ float sbc;
     const int row = blockIdx.x;
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const __nv_bfloat16* 
     if (tid == 0) loss_rows[row] = lse - __bfloat162float(lr[lab]);
     if (dlogits != nullptr) {
         __nv_bfloat16* dr = dlogits + static_cast<long long>(row) * C;
-        const float sc = gscale / static_cast<float>(B);
+        const float sc = gscale * (gscale_dev != nullptr ? gscale_dev[0] : 1.0f) / static_cast<float>(B);
         for (int c = tid; c < C; c += 256) {
             float p = expf(__bfloat162float(lr[c]) - lse);
             if (c == lab) p -= 1.0f;
@@ -440,12 +444,39 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, float v, long long n) {
     else for (long long k = i; k < n; ++k) dst[k] = v;
 }
 
+// Adam over the flat parameter arena (torch.optim.Adam semantics, no amsgrad; L2 weight decay added to the grad)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n4, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float step = lr / bc1;
+    auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+        gw += wd * pw;
+        mw += (gw - mw) * (1.0f - b1);
+        vw = vw * b2 + (1.0f - b2) * gw * gw;
+        const float denom = sqrtf(vw) / bc2_sqrt + eps;
+        pw -= step * (mw / denom);
+    };
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+}
+
 template <int NV>
-static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, const float* beta, void* y, float* mean,
-                         float* rstd, int rows, int dim, float eps, cudaStream_t st) {
+static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, const float* beta, void* y, float* y32,
+                         float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t st) {
     const int blocks = (rows + 7) / 8;
-    layernorm_fwd_kernel<NV><<<blocks, 256, 0, st>>>(x, ld_x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean,
-                                                     rstd, rows, dim, eps);
+    layernorm_fwd_kernel<NV><<<blocks, 256, 0, st>>>(x, ld_x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), y32,
+                                                     mean, rstd, rows, dim, eps);
     return check_launch("layernorm_fwd");
 }
 template <int NV>
@@ -471,13 +502,14 @@ extern "C" const char* b200_last_error(void) { return g_err; }
 extern "C" long long b200_launch_count(void) { return g_launches.load(); }
 
 extern "C" int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const float* beta, void* y_bf16,
-                                  float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t stream) {
+                                  float* y_f32, float* mean, float* rstd, int rows, int dim, float eps,
+                                  cudaStream_t stream) {
     if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 128 * LN_MAX_V4) return set_error(B200_ERR_ARG, "layernorm_fwd: need 0 < dim <= 1024, dim % 4 == 0");
     if (ld_x % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_fwd: ld_x % 4 != 0");
     const int nv = (dim + 127) / 128;
-    if (nv <= 4) return ln_fwd_launch<4>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
-    if (nv <= 6) return ln_fwd_launch<6>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
-    return ln_fwd_launch<8>(x, ld_x, gamma, beta, y_bf16, mean, rstd, rows, dim, eps, stream);
+    if (nv <= 4) return ln_fwd_launch<4>(x, ld_x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, stream);
+    if (nv <= 6) return ln_fwd_launch<6>(x, ld_x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, stream);
+    return ln_fwd_launch<8>(x, ld_x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, stream);
 }
 
 extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma,
@@ -552,11 +584,12 @@ extern "C" int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, fl
 
 extern "C" int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels,
                                          float* loss_rows, float* loss_mean, void* dlogits_bf16, int* bad_label_flag,
-                                         int B, int C, float grad_scale, cudaStream_t stream) {
+                                         int B, int C, float grad_scale, const float* grad_scale_dev,
+                                         cudaStream_t stream) {
     if (B <= 0 || C <= 0) return set_error(B200_ERR_ARG, "softmax_xent: bad size");
     if (bad_label_flag == nullptr || loss_rows == nullptr) return set_error(B200_ERR_ARG, "softmax_xent: null output");
     softmax_xent_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits_bf16), ldl, labels, loss_rows,
-                                               reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), bad_label_flag, B, C, grad_scale);
+                                               reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), bad_label_flag, B, C, grad_scale, grad_scale_dev);
     int rc = check_launch("softmax_xent");
     if (rc) return rc;
     if (loss_mean != nullptr) {
@@ -571,6 +604,17 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long
     const long long thr = (n + 7) / 8;
     cast_f32_bf16_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
     return check_launch("cast_f32_bf16");
+}
+extern "C" int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              cudaStream_t stream) {
+    if (n <= 0 || n % 4 != 0 || step < 1) return set_error(B200_ERR_ARG, "adam_step: n must be a positive multiple of 4, step >= 1");
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+    const long long n4 = n / 4;
+    adam_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n4, lr, beta1,
+                                                                          beta2, eps, weight_decay, bc1, bc2_sqrt);
+    return check_launch("adam_step");
 }
 extern "C" int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream) {
     if (n <= 0) return set_error(B200_ERR_ARG, "fill: n <= 0");

@@ -134,12 +134,14 @@ def colsum(x: Tensor, out: Tensor, *, round_bf16: bool = True, accumulate: bool 
 # ----------------------------------------------------------------------------------------------------------------
 # LayerNorm
 # ----------------------------------------------------------------------------------------------------------------
-def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, rows: int, dim: int, ld_x: int) -> Tuple[Tensor, Tensor, Tensor]:
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, rows: int, dim: int, ld_x: int,
+                  y_f32: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda(x, gamma, beta)
     y = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    call("b200_layernorm_fwd", x.data_ptr(), ld_x, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _stream())
+    call("b200_layernorm_fwd", x.data_ptr(), ld_x, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(y_f32),
+         mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _stream())
     return y, mean, rstd
 
 
@@ -212,7 +214,8 @@ def assemble_tokens_bwd(dnet: Tensor, dpos: Tensor, dcls: Tensor, B: int, np_: i
     return dpatch
 
 
-def softmax_xent(logits: Tensor, labels: Tensor, *, grad_scale: float = 1.0, need_grad: bool = True) -> Tuple[Tensor, Tensor, Optional[Tensor], Tensor]:
+def softmax_xent(logits: Tensor, labels: Tensor, *, grad_scale: float = 1.0, need_grad: bool = True,
+                 grad_scale_dev: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Optional[Tensor], Tensor]:
     """Returns (loss_mean[1], loss_rows[B], dlogits bf16 [B,C] or None, bad_label_flag int32[1])."""
     _need_cuda(logits, labels)
     Bn, C = logits.shape
@@ -226,7 +229,7 @@ def softmax_xent(logits: Tensor, labels: Tensor, *, grad_scale: float = 1.0, nee
     bad = torch.zeros(1, dtype=torch.int32, device=logits.device)
     call(
         "b200_softmax_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), loss_rows.data_ptr(),
-        loss_mean.data_ptr(), _ptr(dlogits), bad.data_ptr(), Bn, C, float(grad_scale), _stream(),
+        loss_mean.data_ptr(), _ptr(dlogits), bad.data_ptr(), Bn, C, float(grad_scale), _ptr(grad_scale_dev), _stream(),
     )
     return loss_mean, loss_rows, dlogits, bad
 

@@ -1,0 +1,522 @@
+"""B200-native drop-in for the reference's ViT encoder / classifier training step.
+
+``ViTEncoderB200`` mirrors ``cflearn.modules.cv.encoder.transformer.ViTEncoder`` (transformer.py:17-100): same
+constructor keywords, same ``state_dict`` keys and shapes, same forward signature, plus the
+``.encode`` method ``cv_clf`` expects (cv/classifier/vanilla.py:57; SURVEY finding 4).  ``VanillaClassifierB200``
+mirrors ``VanillaClassifier`` (vanilla.py:16-66) with the ViT encoder and returns ``{"predictions": logits}``.
+
+Everything between the input image and the logits -- and its whole backward -- runs in hand-written sm_100a kernels
+through the C-ABI (``ops``); autograd sees ONE ``torch.autograd.Function`` per module.  Numerics follow the
+reference under ``torch.autocast(bf16)``: fp32 residual stream / LayerNorm / softmax / loss, bf16 GEMM operands with
+fp32 accumulation, bf16 rounding at exactly the points eager rounds (see DESIGN.md "rounding points").
+
+Parameters live in ONE flat fp32 arena (each ``nn.Parameter`` is a view), shadowed by a bf16 arena refreshed once
+per step and a flat fp32 gradient arena that the data-parallel reducer (``dp.py``) all-reduces in buckets while
+backward is still running.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from ._cabi import B200Error
+
+PREDICTIONS_KEY = "predictions"  # cflearn/constants.py:6
+LATENT_KEY = "latent"
+
+_ALIGN = 64  # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 arena
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# parameter arena
+# -----------------------------------------------------------------------------------------------------------------
+class ParamArena:
+    """Flat fp32 parameters + bf16 shadow + flat fp32 gradients, addressed by reference ``state_dict`` key."""
+
+    def __init__(self, spec: List[Tuple[str, Tuple[int, ...]]]):
+        self.spec = list(spec)
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for key, shape in self.spec:
+            self.offsets[key] = off
+            off += (math.prod(shape) + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.shapes = dict(self.spec)
+        self.flat: Optional[Tensor] = None
+        self.flat_bf16: Optional[Tensor] = None
+        self.grad: Optional[Tensor] = None
+        self.grad_scratch: Optional[Tensor] = None
+        self.params: Dict[str, nn.Parameter] = {}
+        self._bf16_version = -1
+
+    def view(self, flat: Tensor, key: str) -> Tensor:
+        off = self.offsets[key]
+        shape = self.shapes[key]
+        return flat[off : off + math.prod(shape)].view(shape)
+
+    def attach(self, params: Dict[str, nn.Parameter]) -> None:
+        self.params = params
+        self.rebuild()
+
+    def rebuild(self) -> None:
+        """(Re)create the arenas on the parameters' current device and re-point every parameter into them."""
+        first = next(iter(self.params.values()))
+        dev = first.device
+        flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for key, p in self.params.items():
+                v = self.view(flat, key)
+                v.copy_(p.data.to(torch.float32))
+                p.data = v
+        self.flat = flat
+        self.flat_bf16 = torch.zeros(self.total, dtype=torch.bfloat16, device=dev) if dev.type == "cuda" else None
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.grad_scratch = None
+        self._bf16_version = -1
+
+    def ensure(self) -> None:
+        """Cheap aliasing check: ``module.to(device)`` / ``load_state_dict(assign=True)`` break the views."""
+        assert self.flat is not None
+        base = self.flat.data_ptr()
+        ok = True
+        for key, p in self.params.items():
+            if p.data_ptr() != base + 4 * self.offsets[key] or p.device != self.flat.device:
+                ok = False
+                break
+        if not ok:
+            self.rebuild()
+
+    def refresh_bf16(self) -> None:
+        """fp32 -> bf16 shadow of ALL parameters in one launch (what autocast's per-op weight casts amount to)."""
+        assert self.flat is not None and self.flat_bf16 is not None
+        ops.cast_bf16(self.flat, self.flat_bf16)
+
+    def w(self, key: str) -> Tensor:  # bf16 view
+        return self.view(self.flat_bf16, key)
+
+    def p(self, key: str) -> Tensor:  # fp32 view
+        return self.view(self.flat, key)
+
+    def g(self, key: str, arena: Optional[Tensor] = None) -> Tensor:  # fp32 grad view
+        return self.view(self.grad if arena is None else arena, key)
+
+
+def _register_dotted(root: nn.Module, key: str, param: nn.Parameter) -> None:
+    parts = key.split(".")
+    mod = root
+    for name in parts[:-1]:
+        child = mod._modules.get(name)
+        if child is None:
+            child = nn.Module()
+            mod.add_module(name, child)
+        mod = child
+    mod.register_parameter(parts[-1], param)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# geometry / spec
+# -----------------------------------------------------------------------------------------------------------------
+class ViTGeometry:
+    def __init__(self, *, img_size: int, patch_size: int, in_channels: int, latent_dim: int, num_layers: int,
+                 ff_ratio: float, eps: float, num_classes: Optional[int]):
+        if latent_dim % 64 != 0:
+            raise NotImplementedError("latent_dim must be a multiple of 64 (head dim 64, transformer.py:61)")
+        if patch_size % 16 != 0 or img_size % patch_size != 0:
+            raise NotImplementedError("patch_size must be a multiple of 16 dividing img_size")
+        self.img, self.patch, self.cin, self.D, self.L = img_size, patch_size, in_channels, latent_dim, num_layers
+        self.H = latent_dim // 64
+        self.FF = int(round(latent_dim * ff_ratio))
+        self.np = (img_size // patch_size) ** 2
+        self.T = self.np + 1
+        self.eps = eps
+        self.C = num_classes
+        if self.T > 256:
+            raise NotImplementedError("sequence length > 256 tokens is not supported by the fused attention yet")
+
+    def spec(self, with_head: bool) -> List[Tuple[str, Tuple[int, ...]]]:
+        d, p, c, ff = self.D, self.patch, self.cin, self.FF
+        out: List[Tuple[str, Tuple[int, ...]]] = [
+            ("to_patches.projection.weight", (d, c, p, p)), ("to_patches.projection.bias", (d,)),
+            ("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, self.T, d)),
+        ]
+        for i in range(self.L):
+            b = f"encoder.mixing_blocks.{i}."
+            out += [
+                (b + "token_norm.weight", (d,)), (b + "token_norm.bias", (d,)),
+                (b + "token_mixing.net.in_w", (3 * d, d)), (b + "token_mixing.net.qkv_bias", (3 * d,)),
+                (b + "token_mixing.net.out_linear.linear.weight", (d, d)), (b + "token_mixing.net.out_linear.linear.bias", (d,)),
+                (b + "channel_norm.weight", (d,)), (b + "channel_norm.bias", (d,)),
+                (b + "channel_mixing.net.0.linear.weight", (ff, d)), (b + "channel_mixing.net.0.linear.bias", (ff,)),
+                (b + "channel_mixing.net.3.linear.weight", (d, ff)), (b + "channel_mixing.net.3.linear.bias", (d,)),
+            ]
+        out += [("encoder.head.norms.0.weight", (d,)), ("encoder.head.norms.0.bias", (d,))]
+        if with_head:
+            out += [("head.linear.weight", (self.C, d)), ("head.linear.bias", (self.C,))]
+        return out
+
+
+def _init_param(key: str, shape: Tuple[int, ...]) -> Tensor:
+    """Reference initialisation: trunc_normal(0.02) for Linear / in_w / cls / pos (mixed_stacks/api.py:205,405-417;
+    attentions.py:108-110), zero biases, LayerNorm 1/0, xavier_normal(gain/sqrt 2) conv (convs/basic.py:94-97)."""
+    if key.endswith("norm.weight") or key.endswith("norms.0.weight"):
+        return torch.ones(shape)
+    if key.endswith("bias"):
+        return torch.zeros(shape)
+    if key == "to_patches.projection.weight":
+        t = torch.empty(shape)
+        nn.init.xavier_normal_(t, 1.0 / math.sqrt(2.0))
+        return t
+    return nn.init.trunc_normal_(torch.empty(shape), std=0.02)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# the engine: forward / backward of the whole stack on raw buffers
+# -----------------------------------------------------------------------------------------------------------------
+class _Saved:
+    __slots__ = ("B", "cols", "blocks", "net_last", "head_mean", "head_rstd", "enc_bf16")
+
+
+class ViTEngine:
+    def __init__(self, geo: ViTGeometry, arena: ParamArena):
+        self.geo = geo
+        self.arena = arena
+        self.reducer = None  # set by dp.attach_reducer
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def encoder_forward(self, x: Tensor, want_f32: bool) -> Tuple[Tensor, Optional[Tensor], _Saved]:
+        g, A = self.geo, self.arena
+        if not x.is_cuda:
+            raise B200Error("ViTEncoderB200 runs on CUDA only: there is no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != g.cin or x.shape[2] != g.img or x.shape[3] != g.img:
+            raise ValueError(f"expected input [B, {g.cin}, {g.img}, {g.img}], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        A.refresh_bf16()
+        B, T, D, M = x.shape[0], g.T, g.D, x.shape[0] * g.T
+        sv = _Saved()
+        sv.B = B
+        cols = ops.patch_im2col(x, g.patch)
+        patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1), bias=A.w("to_patches.projection.bias"))
+        net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(M, D)
+        sv.cols = cols
+        sv.blocks = []
+        for i in range(g.L):
+            b = f"encoder.mixing_blocks.{i}."
+            ln1, mean1, rstd1 = ops.layernorm_fwd(net, A.p(b + "token_norm.weight"), A.p(b + "token_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+            qkv = ops.gemm(ln1, A.w(b + "token_mixing.net.in_w"), bias=A.w(b + "token_mixing.net.qkv_bias"))
+            attn, lse = ops.attention_fwd(qkv, B, T, g.H)
+            mid = ops.gemm(attn, A.w(b + "token_mixing.net.out_linear.linear.weight"), bias=A.w(b + "token_mixing.net.out_linear.linear.bias"),
+                           epilogue=ops.EPI_BIAS_RESID_F32, aux=net)
+            ln2, mean2, rstd2 = ops.layernorm_fwd(mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+            act = torch.empty((M, g.FF), dtype=torch.bfloat16, device=x.device)
+            h = ops.gemm(ln2, A.w(b + "channel_mixing.net.0.linear.weight"), bias=A.w(b + "channel_mixing.net.0.linear.bias"),
+                         epilogue=ops.EPI_BIAS_GELU_BF16, out1=act)
+            out = ops.gemm(act, A.w(b + "channel_mixing.net.3.linear.weight"), bias=A.w(b + "channel_mixing.net.3.linear.bias"),
+                           epilogue=ops.EPI_BIAS_RESID_F32, aux=mid)
+            sv.blocks.append((net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act))
+            net = out
+        enc_f32 = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_f32 else None
+        # head = LayerNorm over all tokens then token 0 (api.py:365,397-402): only row 0 of each image is needed
+        enc_bf16, hm, hr = ops.layernorm_fwd(net, A.p("encoder.head.norms.0.weight"), A.p("encoder.head.norms.0.bias"), g.eps,
+                                             rows=B, dim=D, ld_x=T * D, y_f32=enc_f32)
+        sv.net_last, sv.head_mean, sv.head_rstd, sv.enc_bf16 = net, hm, hr, enc_bf16
+        return enc_bf16, enc_f32, sv
+
+    def head_forward(self, enc_bf16: Tensor) -> Tensor:
+        A = self.arena
+        return ops.gemm(enc_bf16, A.w("head.linear.weight"), bias=A.w("head.linear.bias"))
+
+    # ---- backward -----------------------------------------------------------------------------------------
+    def head_backward(self, sv: _Saved, dlogits: Tensor, G: Tensor) -> Tensor:
+        A = self.arena
+        d_enc = ops.gemm(dlogits, A.w("head.linear.weight"), b_mn_major=True)  # [B, D] bf16
+        ops.wgrad(dlogits, sv.enc_bf16, A.g("head.linear.weight", G))
+        ops.colsum(dlogits, A.g("head.linear.bias", G))
+        return d_enc
+
+    def encoder_backward(self, sv: _Saved, d_enc_bf16: Tensor, G: Tensor) -> None:
+        """Writes every encoder parameter gradient into the flat arena ``G`` (overwrite semantics)."""
+        g, A = self.geo, self.arena
+        B, T, D, M = sv.B, g.T, g.D, sv.B * g.T
+        dev = d_enc_bf16.device
+        red = self.reducer
+        dnet = torch.empty((M, D), dtype=torch.float32, device=dev)
+        ops.fill_f32(dnet, 0.0)
+        ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p("encoder.head.norms.0.weight"), sv.head_mean, sv.head_rstd,
+                          rows=B, dim=D, ld_x=T * D, dres=None, dx_out=dnet, ld_dx=T * D, dx_bf16=None,
+                          dgamma=A.g("encoder.head.norms.0.weight", G), dbeta=A.g("encoder.head.norms.0.bias", G))
+        dnet_bf = ops.cast_bf16(dnet)
+        if red is not None:
+            red.ready("tail", G)
+        for i in reversed(range(g.L)):
+            b = f"encoder.mixing_blocks.{i}."
+            net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act = sv.blocks[i]
+            # FeedForward: net_out = mid + W2 gelu(W1 ln2 + b1) + b2
+            dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=h)
+            ops.wgrad(dnet_bf, act, A.g(b + "channel_mixing.net.3.linear.weight", G))
+            ops.colsum(dnet_bf, A.g(b + "channel_mixing.net.3.linear.bias", G))
+            dln2 = ops.gemm(dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
+            ops.wgrad(dh, ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
+            ops.colsum(dh, A.g(b + "channel_mixing.net.0.linear.bias", G))
+            dmid = torch.empty((M, D), dtype=torch.float32, device=dev)
+            dmid_bf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.layernorm_bwd(dln2, mid, A.p(b + "channel_norm.weight"), mean2, rstd2, rows=M, dim=D, ld_x=D, dres=dnet,
+                              dx_out=dmid, ld_dx=D, dx_bf16=dmid_bf,
+                              dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G))
+            # attention: mid = net + Wo attn + bo
+            dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
+            ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
+            ops.colsum(dmid_bf, A.g(b + "token_mixing.net.out_linear.linear.bias", G))
+            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H)
+            dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
+            ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
+            ops.colsum(dqkv, A.g(b + "token_mixing.net.qkv_bias", G))
+            ops.layernorm_bwd(dln1, net, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D, dres=dmid,
+                              dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,
+                              dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G))
+            sv.blocks[i] = None  # release this block's activations
+            if red is not None:
+                red.ready(i, G)
+        # tokens = cat(cls, patches) + pos ; patches = conv(x)
+        dpatch = ops.assemble_tokens_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), A.g("encoder.head_token", G), B, g.np, D)
+        ops.wgrad(dpatch, sv.cols, A.g("to_patches.projection.weight", G).view(D, -1))
+        ops.colsum(dpatch, A.g("to_patches.projection.bias", G))
+        if red is not None:
+            red.ready("stem", G)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# autograd glue
+# -----------------------------------------------------------------------------------------------------------------
+def _publish_grads(arena: ParamArena, G: Tensor, keys: List[str]) -> None:
+    """Make ``p.grad`` views of the gradient arena (no copies).  Called at the end of backward."""
+    with torch.no_grad():
+        for key in keys:
+            p = arena.params[key]
+            v = arena.view(arena.grad, key)
+            if G is arena.grad:
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v
+            else:  # accumulation step: G is the scratch arena
+                if p.grad is None:
+                    v.copy_(arena.view(G, key))
+                    p.grad = v
+                else:
+                    p.grad.add_(arena.view(G, key))
+
+
+def _pick_grad_arena(arena: ParamArena, keys: List[str]) -> Tensor:
+    """Overwrite the main arena unless some parameter already holds a gradient (gradient accumulation)."""
+    accumulating = any(arena.params[k].grad is not None for k in keys)
+    if not accumulating:
+        return arena.grad
+    if arena.grad_scratch is None:
+        arena.grad_scratch = torch.zeros_like(arena.grad)
+    return arena.grad_scratch
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, module: "ViTEncoderB200", x: Tensor, *params: Tensor) -> Tensor:
+        enc_bf16, enc_f32, sv = module.engine.encoder_forward(x, want_f32=True)
+        ctx.module, ctx.sv = module, sv
+        return enc_f32
+
+    @staticmethod
+    def backward(ctx: Any, d_enc: Tensor) -> Tuple[Any, ...]:
+        module, sv = ctx.module, ctx.sv
+        arena, eng = module.arena, module.engine
+        keys = module.encoder_keys
+        G = _pick_grad_arena(arena, keys)
+        # under autocast the encoder output feeds a bf16 matmul, so its gradient is bf16-representable
+        d_bf = ops.cast_bf16(d_enc.contiguous().float())
+        eng.encoder_backward(sv, d_bf, G)
+        if eng.reducer is not None:
+            eng.reducer.finish()
+        _publish_grads(arena, G, keys)
+        ctx.sv = None
+        return (None, None) + (None,) * len(keys)
+
+
+class _ClassifierFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, module: "VanillaClassifierB200", x: Tensor, *params: Tensor) -> Tensor:
+        eng = module.engine
+        enc_bf16, _, sv = eng.encoder_forward(x, want_f32=False)
+        logits = eng.head_forward(enc_bf16)
+        ctx.module, ctx.sv = module, sv
+        return logits
+
+    @staticmethod
+    def backward(ctx: Any, dlogits: Tensor) -> Tuple[Any, ...]:
+        module, sv = ctx.module, ctx.sv
+        arena, eng = module.arena, module.engine
+        keys = module.all_keys
+        G = _pick_grad_arena(arena, keys)
+        if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
+            raise B200Error("classifier backward expects a contiguous bf16 gradient for the bf16 logits")
+        d_enc = eng.head_backward(sv, dlogits, G)
+        eng.encoder_backward(sv, d_enc, G)
+        if eng.reducer is not None:
+            eng.reducer.finish()
+        _publish_grads(arena, G, keys)
+        ctx.sv = None
+        return (None, None) + (None,) * len(keys)
+
+
+class _SoftmaxXentFn(torch.autograd.Function):
+    """CrossEntropyLoss (losses/basic.py:137-141) + mean reduction (schema.py:767-775) on bf16 logits."""
+
+    @staticmethod
+    def forward(ctx: Any, logits: Tensor, labels: Tensor) -> Tensor:
+        lab = labels.reshape(-1).contiguous()
+        loss_mean, _, _, bad = ops.softmax_xent(logits, lab, need_grad=False)
+        ctx.save_for_backward(logits, lab)
+        ctx.bad = bad
+        return loss_mean.reshape(())
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: Tensor) -> Tuple[Any, ...]:
+        logits, lab = ctx.saved_tensors
+        go = grad_out.reshape(1).contiguous().float()
+        _, _, dlogits, _ = ops.softmax_xent(logits, lab, need_grad=True, grad_scale_dev=go)
+        return dlogits, None
+
+
+def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
+    """Mean softmax cross-entropy of bf16 ``logits`` [B, C] against int64 ``labels`` [B] or [B, 1]."""
+    if logits.dtype != torch.bfloat16:
+        raise B200Error("cross_entropy expects the bf16 logits produced by VanillaClassifierB200")
+    return _SoftmaxXentFn.apply(logits.contiguous(), labels)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# modules (the plug-in surface)
+# -----------------------------------------------------------------------------------------------------------------
+def _check_supported(**kw: Any) -> None:
+    expected = dict(to_patches_type="vanilla", dropout=0.0, drop_path_rate=0.0, norm_type="layer", embedding_norm=None,
+                    residual_after_norm=False, use_head_token=True, use_positional_encoding=True, norm_after_head=False,
+                    output_dim=None, feedforward_kwargs=None)
+    for k, v in expected.items():
+        if k in kw and kw[k] != v and not (kw[k] is None and v is None):
+            raise NotImplementedError(
+                f"ViTEncoderB200: {k}={kw[k]!r} is outside the fused B200 path (supported: {v!r}); "
+                f"use the reference module for this configuration"
+            )
+
+
+class ViTEncoderB200(nn.Module):
+    """Drop-in for ``ViTEncoder`` (registered as ``encoders.vit`` in the reference, transformer.py:16-17)."""
+
+    def __init__(
+        self,
+        *,
+        img_size: int,
+        patch_size: int,
+        in_channels: int,
+        latent_dim: int = 384,
+        to_patches_type: str = "vanilla",
+        to_patches_config: Optional[Dict[str, Any]] = None,
+        num_layers: int = 12,
+        dropout: float = 0.0,
+        drop_path_rate: float = 0.0,
+        norm_type: Optional[str] = "layer",
+        norm_kwargs: Optional[Dict[str, Any]] = None,
+        embedding_norm: Optional[nn.Module] = None,
+        residual_after_norm: bool = False,
+        feedforward_dim_ratio: float = 4.0,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+        feedforward_kwargs: Optional[Dict[str, Any]] = None,
+        use_head_token: bool = True,
+        head_pooler: Optional[str] = "mean",
+        use_positional_encoding: bool = True,
+        norm_after_head: bool = False,
+        output_dim: Optional[int] = None,
+        _num_classes: Optional[int] = None,
+    ):
+        super().__init__()
+        _check_supported(to_patches_type=to_patches_type, dropout=dropout, drop_path_rate=drop_path_rate, norm_type=norm_type,
+                         embedding_norm=embedding_norm, residual_after_norm=residual_after_norm, use_head_token=use_head_token,
+                         use_positional_encoding=use_positional_encoding, norm_after_head=norm_after_head, output_dim=output_dim,
+                         feedforward_kwargs=feedforward_kwargs)
+        ak = dict(attention_kwargs or {})
+        if ak.get("num_heads", latent_dim // 64) != latent_dim // 64 or not ak.get("bias", True):
+            raise NotImplementedError("ViTEncoderB200 supports the default attention_kwargs only (bias=True, head dim 64)")
+        if set(ak) - {"num_heads", "bias"}:
+            raise NotImplementedError(f"unsupported attention_kwargs: {sorted(set(ak) - {'num_heads', 'bias'})}")
+        if to_patches_config:
+            raise NotImplementedError("to_patches_config extras are outside the fused path")
+        eps = float((norm_kwargs or {}).get("eps", 1e-6))  # norms.py:118-119 default, clip.py:128 overrides to 1e-5
+        self.geo = ViTGeometry(img_size=img_size, patch_size=patch_size, in_channels=in_channels, latent_dim=latent_dim,
+                               num_layers=num_layers, ff_ratio=feedforward_dim_ratio, eps=eps, num_classes=_num_classes)
+        spec = self.geo.spec(with_head=_num_classes is not None)
+        self.arena = ParamArena(spec)
+        params: Dict[str, nn.Parameter] = {}
+        for key, shape in spec:
+            p = nn.Parameter(_init_param(key, shape))
+            params[key] = p
+            _register_dotted(self, key, p)
+        self.arena.attach(params)
+        self.engine = ViTEngine(self.geo, self.arena)
+        self.all_keys = [k for k, _ in spec]
+        self.encoder_keys = [k for k in self.all_keys if not k.startswith("head.linear")]
+        self.latent_dim = latent_dim
+
+    def _param_list(self, keys: List[str]) -> List[nn.Parameter]:
+        return [self.arena.params[k] for k in keys]
+
+    def forward(self, net: Tensor, *, hw: Any = None, hwp: Any = None, deterministic: bool = False) -> Tensor:
+        if hwp is not None:
+            raise NotImplementedError("positional-encoding interpolation (hwp) is outside the fused path")
+        self.arena.ensure()
+        return _EncoderFn.apply(self, net, *self._param_list(self.encoder_keys))
+
+    def encode(self, net: Tensor) -> Tensor:  # IEncoder.encode, cv/common.py:42-50
+        return self.forward(net)
+
+
+class VanillaClassifierB200(ViTEncoderB200):
+    """Drop-in for ``cv_clf`` with ``encoder="vit"`` (cv/classifier/vanilla.py:16-66): ``{"predictions": logits}``.
+
+    ``state_dict`` keys: the encoder's keys under their reference names plus ``head.linear.{weight,bias}``; use
+    ``load_reference_state_dict`` for checkpoints saved from the reference ``cv_clf`` (keys prefixed ``encoder.``)."""
+
+    def __init__(self, in_channels: int, num_classes: int, img_size: Optional[int] = None, latent_dim: int = 128,
+                 aux_num_classes: Optional[Dict[str, int]] = None, *, encoder: str = "vit",
+                 encoder_config: Optional[Dict[str, Any]] = None):
+        if aux_num_classes is not None:
+            raise NotImplementedError("aux heads are outside the fused path")
+        if encoder not in ("vit", "vit_b200"):
+            raise NotImplementedError(f"VanillaClassifierB200 only fuses the ViT encoder, got encoder={encoder!r}")
+        if num_classes % 8 != 0:
+            raise NotImplementedError("num_classes must be a multiple of 8 (16-byte rows for TMA)")
+        cfg = dict(encoder_config or {})
+        cfg.setdefault("img_size", img_size)
+        cfg.setdefault("in_channels", in_channels)
+        cfg.setdefault("latent_dim", latent_dim)
+        super().__init__(**cfg, _num_classes=num_classes)
+        self.num_classes = num_classes
+
+    def forward(self, net: Tensor, *, return_latent: bool = False) -> Dict[str, Tensor]:  # type: ignore[override]
+        self.arena.ensure()
+        if return_latent:
+            return {LATENT_KEY: _EncoderFn.apply(self, net, *self._param_list(self.encoder_keys))}
+        logits = _ClassifierFn.apply(self, net, *self._param_list(self.all_keys))
+        return {PREDICTIONS_KEY: logits}
+
+    def train_step(self, net: Tensor, labels: Tensor) -> Tensor:
+        """forward + CrossEntropyLoss + backward (IDLModel.train, schema.py:1266-1276,:980); returns the loss."""
+        loss = cross_entropy(self.forward(net)[PREDICTIONS_KEY], labels)
+        loss.backward()
+        return loss.detach()
+
+    def load_reference_state_dict(self, sd: Dict[str, Tensor]) -> None:
+        """Accepts a reference ``cv_clf`` checkpoint (``encoder.<ViTEncoder keys>`` + ``head.linear.*``)."""
+        mapped = {}
+        for k, v in sd.items():
+            mapped[k[len("encoder."):] if k.startswith("encoder.to_patches") or k.startswith("encoder.encoder.") else k] = v
+        self.load_state_dict(mapped, strict=True)

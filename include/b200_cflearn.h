@@ -81,7 +81,8 @@ int b200_splitk_reduce(const float* partial, int splits, long long n, float* out
  *   mean, rstd: f32 [rows], saved for backward.
  * --------------------------------------------------------------------------------------------------------- */
 int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const float* beta, void* y_bf16,
-                       float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t stream);
+                       float* y_f32 /* optional [rows, dim]: the un-rounded fp32 result */, float* mean, float* rstd,
+                       int rows, int dim, float eps, cudaStream_t stream);
 /* dx_out[f32] = (dres ? dres : 0) + LN'(dy); dx_out row stride ld_dx (so the head LN can scatter into token 0).
  * dy: bf16 [rows, dim].  dx_bf16 (optional) receives bf16(dx_out) -- the gradient the preceding bf16 matmul
  * output sees under autocast.  dgamma_part/dbeta_part: f32 [nparts, dim] workspace, reduced by
@@ -127,11 +128,20 @@ int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, 
  * Cross entropy with integer labels (cflearn/losses/basic.py:137-141: -log_softmax(logits,1).gather(1,labels),
  * mean over the batch via ILoss._reduce, cflearn/schema.py:767-810).  logits bf16 [B, C] (ld = ldl),
  * labels int64 [B].  loss_rows f32 [B], loss_mean f32 [1].  dlogits bf16 [B, C] = bf16((softmax - onehot) *
- * grad_scale / B).  The label gather is integer-exact; out-of-range labels set *bad_label_flag (device int).
+ * grad_scale * (grad_scale_dev ? *grad_scale_dev : 1) / B) -- grad_scale_dev is the upstream gradient of the mean
+ * loss living on the device (autograd's grad_output), so backward needs no host synchronisation.
+ * The label gather is integer-exact; out-of-range labels set *bad_label_flag (device int).
  * --------------------------------------------------------------------------------------------------------- */
 int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels, float* loss_rows,
                               float* loss_mean, void* dlogits_bf16, int* bad_label_flag, int B, int C,
-                              float grad_scale, cudaStream_t stream);
+                              float grad_scale, const float* grad_scale_dev, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimizer step on the flat fp32 arenas (torch.optim.Adam semantics without amsgrad; the reference's default
+ * optimizer "adam", cflearn/optimizers.py:29-32, stepped at cflearn/schema.py:983).  n % 4 == 0; step >= 1.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t stream);
 
 /* element-wise helpers */
 int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream);

@@ -1,0 +1,169 @@
+"""End-to-end parity of the B200 ViT classifier training step against the oracle (oracle/vit_oracle.py, pinned to the
+reference), on the GPU.  Three comparisons per configuration:
+
+  (1) vs the oracle run EAGERLY ON THE SAME GPU under bf16 autocast -- "the reference's own PyTorch-eager path":
+      relative L2 error of logits / loss / every parameter gradient within the tolerances below;
+  (2) vs the fp32 oracle: our bf16 path must be as close to the exact answer as eager bf16 is (<= 1.5x its error);
+  (3) vs the golden vectors generated from the real reference on CPU (tests/golden/vit_tiny_reference.pt).
+
+Tolerances (relative L2, stated per BASELINE.json's 1e-3 target and what bf16 permits): forward tensors 2e-3; bf16
+gradients are compared both ways because two correct bf16 pipelines differ by accumulated 2^-9 roundings.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import vit_oracle as vo  # noqa: E402
+
+import cflearn_b200  # noqa: F401,E402
+from cflearn_b200 import registry, vit  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+FWD_TOL = 2e-3
+GRAD_TOL_VS_EAGER = 2e-2
+GRAD_TOL_VS_FP32_FACTOR = 1.5
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def build(cfg, sd):
+    m = registry.build_module(
+        "cv_clf", config=dict(in_channels=cfg["in_channels"], num_classes=cfg["num_classes"], img_size=cfg["img_size"],
+                              latent_dim=cfg["latent_dim"], encoder="vit",
+                              encoder_config=dict(patch_size=cfg["patch_size"], num_layers=cfg["num_layers"])))
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+def run_ours(cfg, sd, x, y):
+    m = build(cfg, sd)
+    logits = m(x)[vit.PREDICTIONS_KEY]
+    loss = vit.cross_entropy(logits, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    return logits.detach(), loss.detach(), grads, m
+
+
+def oracle_on_gpu(cfg, sd, x, y, autocast):
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    loss, grads, taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=autocast, want_taps=True)
+    return taps["logits"], loss, grads
+
+
+@pytest.mark.parametrize("name,batch", [("vit_tiny", 4), ("vit_small", 6), ("vit_b16", 8)])
+def test_train_step_parity(name, batch):
+    cfg = vo.vit_config(name)
+    sd = vo.init_state_dict(cfg, seed=0)
+    x, y = vo.synthetic_batch(cfg, batch, seed=1)
+    x, y = x.to(DEV), y.to(DEV)
+    logits, loss, grads, _ = run_ours(cfg, sd, x, y)
+    e_logits, e_loss, e_grads = oracle_on_gpu(cfg, sd, x, y, True)   # eager bf16 autocast: the parity target
+    f_logits, f_loss, f_grads = oracle_on_gpu(cfg, sd, x, y, False)  # fp32: the exact answer
+    assert set(grads) == set(e_grads)
+    assert logits.dtype == torch.bfloat16 and e_logits.dtype == torch.bfloat16
+    err_logits = rel(logits, e_logits)
+    assert err_logits < FWD_TOL * 3, f"logits vs eager: {err_logits}"
+    assert rel(logits, f_logits) < max(GRAD_TOL_VS_FP32_FACTOR * rel(e_logits, f_logits), 1e-3)
+    assert abs(loss.item() - e_loss.item()) < 2e-3 * max(1.0, abs(e_loss.item()))
+    worst = 0.0
+    for k in sorted(grads):
+        ours_vs_eager = rel(grads[k], e_grads[k])
+        ours_vs_fp32 = rel(grads[k], f_grads[k])
+        eager_vs_fp32 = rel(e_grads[k], f_grads[k])
+        worst = max(worst, ours_vs_eager)
+        assert ours_vs_eager < GRAD_TOL_VS_EAGER, f"{k}: ours vs eager {ours_vs_eager}"
+        assert ours_vs_fp32 < max(GRAD_TOL_VS_FP32_FACTOR * eager_vs_fp32, 2e-3), (k, ours_vs_fp32, eager_vs_fp32)
+    print(f"{name}: logits vs eager {err_logits:.2e}; worst grad vs eager {worst:.2e}")
+
+
+def test_against_reference_golden_vectors():
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "vit_tiny_reference.pt"), weights_only=False)
+    cfg = vo.vit_config(fx["config_name"])
+    sd = vo.init_state_dict(cfg, seed=fx["weights_seed"])
+    x, y = fx["x"].to(DEV), fx["labels"].to(DEV)
+    logits, loss, grads, _ = run_ours(cfg, sd, x, y)
+    ref_bf16, ref_fp32 = fx["reference"]["bf16"], fx["reference"]["fp32"]
+    assert rel(logits.cpu(), ref_fp32["logits"]) < 1e-2
+    assert abs(loss.item() - ref_fp32["loss"].item()) < 1e-2
+    for k, g in ref_fp32["grads"].items():
+        ours = rel(grads[k].cpu(), g)
+        theirs = rel(ref_bf16["grads"][k], g)  # how far the reference's own bf16 (CPU autocast) path is from its fp32 path
+        assert ours < max(2.0 * theirs, 5e-3), (k, ours, theirs)
+
+
+def test_label_path_is_integer_exact():
+    cfg = vo.vit_config("vit_tiny")
+    sd = vo.init_state_dict(cfg, seed=0)
+    x, y = vo.synthetic_batch(cfg, 4, seed=1)
+    m = build(cfg, sd)
+    logits = m(x.to(DEV))[vit.PREDICTIONS_KEY].detach()
+    from cflearn_b200 import ops
+
+    _, rows, _, bad = ops.softmax_xent(logits, y.to(DEV).reshape(-1), need_grad=False)
+    ref = -torch.log_softmax(logits.float(), 1).gather(1, y.to(DEV))[:, 0]
+    assert bad.item() == 0
+    assert torch.allclose(rows, ref, rtol=1e-6, atol=1e-6)
+    # permuting labels permutes exactly which logit is picked: loss difference equals the logit difference
+    y2 = (y + 1) % cfg["num_classes"]
+    _, rows2, _, _ = ops.softmax_xent(logits, y2.to(DEV).reshape(-1), need_grad=False)
+    picked = logits.float().gather(1, y.to(DEV))[:, 0] - logits.float().gather(1, y2.to(DEV))[:, 0]
+    assert torch.allclose(rows2 - rows, picked, rtol=1e-5, atol=1e-5)
+
+
+def test_encoder_module_and_registry_surface():
+    cfg = vo.vit_config("vit_small")
+    enc = registry.build_encoder("vit", config=dict(img_size=cfg["img_size"], patch_size=cfg["patch_size"], in_channels=3,
+                                                    latent_dim=cfg["latent_dim"], num_layers=cfg["num_layers"], unknown_key=1))
+    sd = {k: v for k, v in vo.init_state_dict(cfg, seed=3).items() if not k.startswith("head.linear")}
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV)
+    x, _ = vo.synthetic_batch(cfg, 5, seed=2)
+    out = enc.encode(x.to(DEV))
+    assert out.dtype == torch.float32 and out.shape == (5, cfg["latent_dim"])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = vo.encoder_forward({k: v.to(DEV) for k, v in sd.items()}, x.to(DEV), cfg)
+    assert rel(out, ref) < FWD_TOL * 3
+    out.sum().backward()
+    assert all(p.grad is not None for p in enc.parameters())
+    with pytest.raises(NotImplementedError):
+        registry.build_encoder("vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, dropout=0.1))
+
+
+def test_gradient_accumulation_and_adam_step():
+    from cflearn_b200.optim import ArenaAdam
+
+    cfg = vo.vit_config("vit_tiny")
+    sd = vo.init_state_dict(cfg, seed=0)
+    x, y = vo.synthetic_batch(cfg, 4, seed=1)
+    x, y = x.to(DEV), y.to(DEV)
+    m = build(cfg, sd)
+    m.train_step(x, y)
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.train_step(x, y)  # p.grad still set -> accumulates
+    for k, p in m.named_parameters():
+        assert rel(p.grad, 2 * g1[k]) < 1e-6, k
+    # Adam: compare one step with torch.optim.Adam on the same gradients
+    ref_params = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    for rp, p in zip(ref_params, m.parameters()):
+        rp.grad = p.grad.clone()
+    torch.optim.Adam(ref_params, lr=1e-3).step()
+    opt = ArenaAdam(m, lr=1e-3)
+    opt.step()
+    torch.cuda.synchronize()
+    for rp, p in zip(ref_params, m.parameters()):
+        assert torch.allclose(p, rp, rtol=1e-5, atol=1e-7)
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    m.train_step(x, y)
+    assert all(p.grad is not None for p in m.parameters())
