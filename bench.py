@@ -119,11 +119,12 @@ def cpu_reference_samples_per_sec(steps: int, warmup: int, budget_s: float):
         return loss
 
     # calibrate the bounded sample (micro-batch) so that (steps + warmup) steps fit the time budget
-    x, y = vo.synthetic_batch(cfg, 2, seed=0)
+    x, y = vo.synthetic_batch(cfg, 4, seed=0)
+    step(x, y)  # cold step (thread pool spin-up, allocator): not representative
     t0 = time.perf_counter()
     step(x, y)
-    per_img = (time.perf_counter() - t0) / 2
-    mb = int(max(2, min(32, budget_s / max(1e-6, per_img * (steps + warmup)))))
+    per_img = (time.perf_counter() - t0) / 4
+    mb = int(max(4, min(32, budget_s / max(1e-6, per_img * (steps + warmup)))))
     x, y = vo.synthetic_batch(cfg, mb, seed=1)
     for _ in range(warmup):
         step(x, y)

@@ -226,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (!active) continue;
 
-                // bias for these 32 columns (bf16, broadcast load); N % 8 == 0 is enforced on the host
+                // bias for these 32 columns (bf16, broadcast 16-byte loads; must be readable up to roundup(N, 8))
                 float bv[32];
                 if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll
@@ -463,7 +463,8 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
                               void* out1, const void* aux, long long ldo, int splits, int max_ctas,
                               cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: non-positive dimension");
-    if (N % 8 != 0) return set_error(B200_ERR_ARG, "gemm: N must be a multiple of 8");
+    // N need not be a multiple of 8: the bias is read in 16-byte groups (readable up to roundup(N, 8) elements) and the
+    // TMA store clips columns >= N; the leading dimension must keep rows 16-byte aligned (checked in make_tmap).
     if (A == nullptr || B == nullptr || out0 == nullptr) return set_error(B200_ERR_ARG, "gemm: null pointer");
     if (splits < 1) splits = 1;
     if (epilogue != EPI_PARTIAL_F32 && splits != 1) return set_error(B200_ERR_ARG, "gemm: split-K needs EPI_PARTIAL_F32");

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const __nv_bfloat16* 
     }
     if (tid == 0) loss_rows[row] = lse - __bfloat162float(lr[lab]);
     if (dlogits != nullptr) {
-        __nv_bfloat16* dr = dlogits + static_cast<long long>(row) * C;
+        __nv_bfloat16* dr = dlogits + static_cast<long long>(row) * ldl;  // same row stride as the logits
         const float sc = gscale * (gscale_dev != nullptr ? gscale_dev[0] : 1.0f) / static_cast<float>(B);
         for (int c = tid; c < C; c += 256) {
             float p = expf(__bfloat162float(lr[c]) - lse);
@@ -532,7 +532,7 @@ extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long
 
 extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
                                 int* nparts_out, cudaStream_t stream) {
-    if (rows <= 0 || cols <= 0 || cols % 8 != 0 || ld % 8 != 0) return set_error(B200_ERR_ARG, "colsum: cols and ld must be multiples of 8");
+    if (rows <= 0 || cols <= 0 || ld % 8 != 0 || ld < (cols + 7) / 8 * 8) return set_error(B200_ERR_ARG, "colsum: ld must be a multiple of 8 and >= roundup(cols, 8)");
     if (max_parts < 1) return set_error(B200_ERR_ARG, "colsum: max_parts < 1");
     const int chunks = (cols + 255) / 256;
     int slices = (num_sms() * 4) / chunks;

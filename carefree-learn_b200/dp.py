@@ -73,24 +73,30 @@ class GradBucketReducer:
         lo, hi = self.buckets[key]
         if grad is None:
             grad = self.arena.grad
+        if not grad.is_cuda:  # gloo path (host-side logic tests): same protocol, SUM then divide in finish()
+            work = dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((work, grad[lo:hi], True))
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         cs = self._stream()
         cs.wait_event(ev)
         with torch.cuda.stream(cs):
-            if grad.is_cuda:
-                work = dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-            else:  # gloo (CPU tests): no AVG
-                work = dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((work, lo, hi))
+            work = dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._pending.append((work, None, False))
 
     def finish(self) -> None:
         if self.world == 1:
             return
-        for work, lo, hi in self._pending:
+        on_host = False
+        for work, view, host in self._pending:
             work.wait()  # on CUDA this only orders streams, it does not block the host
+            if host:
+                view.div_(self.world)
+                on_host = True
         self._pending.clear()
-        torch.cuda.current_stream().wait_stream(self._stream())
+        if not on_host:
+            torch.cuda.current_stream().wait_stream(self._stream())
 
 
 def allreduce_flat_cpu(grad: torch.Tensor, buckets: List[Tuple[int, int]], group=None) -> None:

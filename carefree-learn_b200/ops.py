@@ -91,8 +91,11 @@ def gemm(
         raise B200Error(f"gemm reduction mismatch: {K} vs {Kb}")
     f32_out = epilogue in (EPI_BIAS_RESID_F32, EPI_PARTIAL_F32)
     if out0 is None:
-        shape = (splits, M, N) if epilogue == EPI_PARTIAL_F32 else (M, N)
-        out0 = torch.empty(shape, dtype=torch.float32 if f32_out else torch.bfloat16, device=a.device)
+        if epilogue == EPI_PARTIAL_F32:
+            out0 = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
+        else:  # rows stay 16-byte aligned for TMA: pad the leading dimension, hand back the [M, N] view
+            npad = (N + 7) // 8 * 8
+            out0 = torch.empty((M, npad), dtype=torch.float32 if f32_out else torch.bfloat16, device=a.device)[:, :N]
     if out0.dtype != (torch.float32 if f32_out else torch.bfloat16):
         raise B200Error("gemm: out0 dtype does not match the epilogue")
     ldo = out0.stride(-2)
@@ -225,7 +228,8 @@ def softmax_xent(logits: Tensor, labels: Tensor, *, grad_scale: float = 1.0, nee
         raise B200Error("softmax_xent: labels must be contiguous int64 with one entry per row")
     loss_rows = torch.empty(Bn, dtype=torch.float32, device=logits.device)
     loss_mean = torch.empty(1, dtype=torch.float32, device=logits.device)
-    dlogits = torch.empty((Bn, C), dtype=torch.bfloat16, device=logits.device) if need_grad else None
+    # dlogits shares the logits' row stride (a multiple of 8 elements so the head dgrad / wgrad can TMA it)
+    dlogits = torch.empty_strided((Bn, C), (logits.stride(0), 1), dtype=torch.bfloat16, device=logits.device) if need_grad else None
     bad = torch.zeros(1, dtype=torch.int32, device=logits.device)
     call(
         "b200_softmax_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), loss_rows.data_ptr(),

@@ -357,8 +357,12 @@ class _ClassifierFn(torch.autograd.Function):
         arena, eng = module.arena, module.engine
         keys = module.all_keys
         G = _pick_grad_arena(arena, keys)
-        if dlogits.dtype != torch.bfloat16 or not dlogits.is_contiguous():
-            raise B200Error("classifier backward expects a contiguous bf16 gradient for the bf16 logits")
+        if dlogits.dtype != torch.bfloat16:
+            raise B200Error("classifier backward expects a bf16 gradient for the bf16 logits")
+        if dlogits.stride(1) != 1 or dlogits.stride(0) % 8 != 0:  # e.g. produced by a foreign loss: re-pad the rows
+            padded = torch.zeros((dlogits.shape[0], (dlogits.shape[1] + 7) // 8 * 8), dtype=torch.bfloat16, device=dlogits.device)
+            padded[:, : dlogits.shape[1]].copy_(dlogits)
+            dlogits = padded[:, : dlogits.shape[1]]
         d_enc = eng.head_backward(sv, dlogits, G)
         eng.encoder_backward(sv, d_enc, G)
         if eng.reducer is not None:
@@ -391,7 +395,7 @@ def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
     """Mean softmax cross-entropy of bf16 ``logits`` [B, C] against int64 ``labels`` [B] or [B, 1]."""
     if logits.dtype != torch.bfloat16:
         raise B200Error("cross_entropy expects the bf16 logits produced by VanillaClassifierB200")
-    return _SoftmaxXentFn.apply(logits.contiguous(), labels)
+    return _SoftmaxXentFn.apply(logits, labels)  # keeps the logits' padded row stride (see ops.gemm)
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -492,8 +496,6 @@ class VanillaClassifierB200(ViTEncoderB200):
             raise NotImplementedError("aux heads are outside the fused path")
         if encoder not in ("vit", "vit_b200"):
             raise NotImplementedError(f"VanillaClassifierB200 only fuses the ViT encoder, got encoder={encoder!r}")
-        if num_classes % 8 != 0:
-            raise NotImplementedError("num_classes must be a multiple of 8 (16-byte rows for TMA)")
         cfg = dict(encoder_config or {})
         cfg.setdefault("img_size", img_size)
         cfg.setdefault("in_channels", in_channels)
