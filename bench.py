@@ -198,6 +198,7 @@ def run_b200(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def step_resident(i):
+        opt.zero_grad()  # schema.py:984 (backward then overwrites the gradient arena instead of accumulating)
         loss = model.train_step(dev_x[i % n_host], dev_y[i % n_host])
         opt.step()
         return loss
@@ -260,6 +261,7 @@ def run_b200(args):
             if i + 1 < n:
                 prefetch(i + 1)
             torch.cuda.current_stream().wait_event(ready[s])
+            opt.zero_grad()
             ls = model.train_step(stage_x[s], stage_y[s])
             opt.step()
             consumed[s].record(torch.cuda.current_stream())

@@ -112,51 +112,61 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm backward: warps stride over rows; per-lane dgamma/dbeta partials live in registers and are
-// reduced across the block's warps through shared memory -> part[blockIdx][dim].
+// LayerNorm backward: warps stride over rows.  Everything a row needs (x, dy, upstream residual grad) is requested
+// up front -- 18 independent 8/16-byte loads per lane -- and the kernel is held to 128 registers so two 256-thread
+// blocks fit per SM; the first version (148 registers, dres loaded after the reductions) sat at 2 TB/s.
+// Per-lane dgamma/dbeta partials live in registers and are reduced across the block's warps through shared memory
+// -> part[blockIdx][0:dim] (dgamma) and part[blockIdx][dim:2*dim] (dbeta).
 // ------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const float* __restrict__ x, long long ld_x,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in,
-                                                            const float* __restrict__ dres, float* __restrict__ dx_out,
-                                                            long long ld_dx, __nv_bfloat16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dgamma_part,
-                                                            float* __restrict__ dbeta_part, int rows, int dim) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const float* __restrict__ x, long long ld_x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in,
+                                                               const float* __restrict__ dres, float* __restrict__ dx_out,
+                                                               long long ld_dx, __nv_bfloat16* __restrict__ dx_bf16,
+                                                               float* __restrict__ part, int rows, int dim) {
     extern __shared__ float sred[];  // [8 warps][2][dim]
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    float4 g[NV], dg[NV], db[NV];
+    float4 dg[NV], db[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        g[i] = c < dim ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float fn = static_cast<float>(dim);
     for (int row = blockIdx.x * warps_per_block + wib; row < rows; row += gridDim.x * warps_per_block) {
-        const float mean = mean_in[row];
-        const float rstd = rstd_in[row];
         const float* xr = x + static_cast<long long>(row) * ld_x;
         const __nv_bfloat16* dyr = dy + static_cast<long long>(row) * dim;
-        float4 xh[NV], gy[NV];
+        const float* rr = dres != nullptr ? dres + static_cast<long long>(row) * ld_dx : nullptr;
+        float4 xv[NV], rv[NV];
+        uint2 dv[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {  // issue every load of this row before touching any of them
+            const int c = (lane + 32 * i) * 4;
+            if (c < dim) {
+                xv[i] = *reinterpret_cast<const float4*>(xr + c);
+                dv[i] = *reinterpret_cast<const uint2*>(dyr + c);
+                rv[i] = rr != nullptr ? *reinterpret_cast<const float4*>(rr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float mean = mean_in[row];
+        const float rstd = rstd_in[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (lane + 32 * i) * 4;
             if (c < dim) {
-                const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-                const uint2 dv = *reinterpret_cast<const uint2*>(dyr + c);
-                const float d0 = bf16lo(dv.x), d1 = bf16hi(dv.x), d2 = bf16lo(dv.y), d3 = bf16hi(dv.y);
-                xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-                gy[i] = make_float4(d0 * g[i].x, d1 * g[i].y, d2 * g[i].z, d3 * g[i].w);
-                s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
-                s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
-                dg[i].x += d0 * xh[i].x; dg[i].y += d1 * xh[i].y; dg[i].z += d2 * xh[i].z; dg[i].w += d3 * xh[i].w;
+                const float4 g = *reinterpret_cast<const float4*>(gamma + c);  // L1-resident
+                const float d0 = bf16lo(dv[i].x), d1 = bf16hi(dv[i].x), d2 = bf16lo(dv[i].y), d3 = bf16hi(dv[i].y);
+                xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd);
+                const float g0 = d0 * g.x, g1 = d1 * g.y, g2 = d2 * g.z, g3 = d3 * g.w;
+                s1 += (g0 + g1) + (g2 + g3);
+                s2 += (g0 * xv[i].x + g1 * xv[i].y) + (g2 * xv[i].z + g3 * xv[i].w);
+                dg[i].x += d0 * xv[i].x; dg[i].y += d1 * xv[i].y; dg[i].z += d2 * xv[i].z; dg[i].w += d3 * xv[i].w;
                 db[i].x += d0; db[i].y += d1; db[i].z += d2; db[i].w += d3;
             }
         }
@@ -168,15 +178,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         for (int i = 0; i < NV; ++i) {
             const int c = (lane + 32 * i) * 4;
             if (c < dim) {
+                const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+                const float d0 = bf16lo(dv[i].x), d1 = bf16hi(dv[i].x), d2 = bf16lo(dv[i].y), d3 = bf16hi(dv[i].y);
                 float4 o;
-                o.x = (fn * gy[i].x - s1 - xh[i].x * s2) * term;
-                o.y = (fn * gy[i].y - s1 - xh[i].y * s2) * term;
-                o.z = (fn * gy[i].z - s1 - xh[i].z * s2) * term;
-                o.w = (fn * gy[i].w - s1 - xh[i].w * s2) * term;
-                if (dres != nullptr) {
-                    const float4 r = *reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ld_dx + c);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
+                o.x = (fn * (d0 * g.x) - s1 - xv[i].x * s2) * term + rv[i].x;
+                o.y = (fn * (d1 * g.y) - s1 - xv[i].y * s2) * term + rv[i].y;
+                o.z = (fn * (d2 * g.z) - s1 - xv[i].z * s2) * term + rv[i].z;
+                o.w = (fn * (d3 * g.w) - s1 - xv[i].w * s2) * term + rv[i].w;
                 *reinterpret_cast<float4*>(dxr + c) = o;
                 if (dx_bf16 != nullptr) {
                     uint2 p;
@@ -205,8 +213,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
             a += sred[(w * 2 + 0) * dim + c];
             b += sred[(w * 2 + 1) * dim + c];
         }
-        dgamma_part[static_cast<long long>(blockIdx.x) * dim + c] = a;
-        dbeta_part[static_cast<long long>(blockIdx.x) * dim + c] = b;
+        part[static_cast<long long>(blockIdx.x) * 2 * dim + c] = a;
+        part[static_cast<long long>(blockIdx.x) * 2 * dim + dim + c] = b;
     }
 }
 
@@ -252,14 +260,25 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     }
 }
 
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out,
-                                     int round_bf16, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] (+)= sum_p part[p * part_ld + c]: block = 32 columns x 8 part lanes (the first version looped over up to 592
+// parts serially per thread: 25 us per call, 100 calls per step)
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ part, long long part_ld, int nparts,
+                                                            int cols, float* __restrict__ out, int round_bf16,
+                                                            int accumulate) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[static_cast<long long>(p) * cols + c];
-    if (round_bf16) s = bf16_round(s);
-    out[c] = accumulate ? out[c] + s : s;
+    if (c < cols)
+        for (int p = threadIdx.y; p < nparts; p += 8) s += part[static_cast<long long>(p) * part_ld + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        if (round_bf16) t = bf16_round(t);
+        out[c] = accumulate ? out[c] + t : t;
+    }
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long n4,
@@ -482,14 +501,14 @@ static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, con
 template <int NV>
 static int ln_bwd_launch(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
-                         float* dgp, float* dbp, int nparts, int rows, int dim, cudaStream_t st) {
+                         float* part, int nparts, int rows, int dim, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(8) * 2 * dim * sizeof(float);
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     }
     layernorm_bwd_kernel<NV><<<nparts, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, ld_x, gamma, mean,
                                                         rstd, dres, dx_out, ld_dx,
-                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgp, dbp, rows, dim);
+                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), part, rows, dim);
     return check_launch("layernorm_bwd");
 }
 
@@ -514,20 +533,20 @@ extern "C" int b200_layernorm_fwd(const float* x, long long ld_x, const float* g
 
 extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma,
                                   const float* mean, const float* rstd, const float* dres, float* dx_out,
-                                  long long ld_dx, void* dx_bf16, float* dgamma_part, float* dbeta_part, int max_parts,
-                                  int* nparts_out, int rows, int dim, cudaStream_t stream) {
+                                  long long ld_dx, void* dx_bf16, float* dgb_part, int max_parts, int* nparts_out,
+                                  int rows, int dim, cudaStream_t stream) {
     if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 128 * LN_MAX_V4) return set_error(B200_ERR_ARG, "layernorm_bwd: need 0 < dim <= 1024, dim % 4 == 0");
     if (ld_x % 4 != 0 || ld_dx % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_bwd: ld % 4 != 0");
     if (max_parts < 1) return set_error(B200_ERR_ARG, "layernorm_bwd: max_parts < 1");
-    int nparts = num_sms() * 4;
+    int nparts = num_sms() * 2  /* two resident 256-thread blocks per SM: one wave */;
     const int need = (rows + 7) / 8;
     if (nparts > need) nparts = need;
     if (nparts > max_parts) nparts = max_parts;
     if (nparts_out) *nparts_out = nparts;
     const int nv = (dim + 127) / 128;
-    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
-    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
-    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgamma_part, dbeta_part, nparts, rows, dim, stream);
+    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
+    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
+    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
 }
 
 extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
@@ -544,10 +563,10 @@ extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int 
     return check_launch("colsum_bf16");
 }
 
-extern "C" int b200_colsum_finish(const float* part, int nparts, int cols, float* out, int round_bf16, int accumulate,
-                                  cudaStream_t stream) {
-    if (nparts <= 0 || cols <= 0) return set_error(B200_ERR_ARG, "colsum_finish: bad size");
-    colsum_finish_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(part, nparts, cols, out, round_bf16, accumulate);
+extern "C" int b200_colsum_finish(const float* part, long long part_ld, int nparts, int cols, float* out, int round_bf16,
+                                  int accumulate, cudaStream_t stream) {
+    if (nparts <= 0 || cols <= 0 || part_ld < cols) return set_error(B200_ERR_ARG, "colsum_finish: bad size");
+    colsum_finish_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, stream>>>(part, part_ld, nparts, cols, out, round_bf16, accumulate);
     return check_launch("colsum_finish");
 }
 

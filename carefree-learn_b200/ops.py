@@ -130,7 +130,7 @@ def colsum(x: Tensor, out: Tensor, *, round_bf16: bool = True, accumulate: bool 
     part = WORKSPACE.get(x.device, _MAX_PARTS * cols, "colsum")
     nparts = ctypes.c_int(0)
     call("b200_colsum_bf16", x.data_ptr(), x.stride(0), rows, cols, part.data_ptr(), _MAX_PARTS, ctypes.byref(nparts), _stream())
-    call("b200_colsum_finish", part.data_ptr(), nparts.value, cols, out.data_ptr(), int(round_bf16), int(accumulate), _stream())
+    call("b200_colsum_finish", part.data_ptr(), cols, nparts.value, cols, out.data_ptr(), int(round_bf16), int(accumulate), _stream())
     return out
 
 
@@ -154,16 +154,17 @@ def layernorm_bwd(
     dgamma: Tensor, dbeta: Tensor, accumulate: bool = False,
 ) -> None:
     part = WORKSPACE.get(x.device, 2 * _MAX_PARTS * dim, "lnbwd")
-    pg = part[: _MAX_PARTS * dim]
-    pb = part[_MAX_PARTS * dim : 2 * _MAX_PARTS * dim]
     nparts = ctypes.c_int(0)
     call(
         "b200_layernorm_bwd", dy.data_ptr(), x.data_ptr(), ld_x, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-        _ptr(dres), dx_out.data_ptr(), ld_dx, _ptr(dx_bf16), pg.data_ptr(), pb.data_ptr(), _MAX_PARTS,
+        _ptr(dres), dx_out.data_ptr(), ld_dx, _ptr(dx_bf16), part.data_ptr(), _MAX_PARTS,
         ctypes.byref(nparts), rows, dim, _stream(),
     )
-    call("b200_colsum_finish", pg.data_ptr(), nparts.value, dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
-    call("b200_colsum_finish", pb.data_ptr(), nparts.value, dim, dbeta.data_ptr(), 0, int(accumulate), _stream())
+    if dbeta.data_ptr() == dgamma.data_ptr() + 4 * dim:  # adjacent in the gradient arena: one reduction for both
+        call("b200_colsum_finish", part.data_ptr(), 2 * dim, nparts.value, 2 * dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
+    else:
+        call("b200_colsum_finish", part.data_ptr(), 2 * dim, nparts.value, dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
+        call("b200_colsum_finish", part.data_ptr() + 4 * dim, 2 * dim, nparts.value, dim, dbeta.data_ptr(), 0, int(accumulate), _stream())
 
 
 # ----------------------------------------------------------------------------------------------------------------

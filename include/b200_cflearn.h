@@ -85,19 +85,18 @@ int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const
                        int rows, int dim, float eps, cudaStream_t stream);
 /* dx_out[f32] = (dres ? dres : 0) + LN'(dy); dx_out row stride ld_dx (so the head LN can scatter into token 0).
  * dy: bf16 [rows, dim].  dx_bf16 (optional) receives bf16(dx_out) -- the gradient the preceding bf16 matmul
- * output sees under autocast.  dgamma_part/dbeta_part: f32 [nparts, dim] workspace, reduced by
- * b200_colsum_finish.  Returns nparts through *nparts_out (host int). */
+ * output sees under autocast.  dgb_part: f32 [nparts, 2*dim] workspace ([.., 0:dim] dgamma partials, [.., dim:2dim]
+ * dbeta partials), reduced by b200_colsum_finish.  Returns nparts through *nparts_out (host int). */
 int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
-                       float* dgamma_part, float* dbeta_part, int max_parts, int* nparts_out, int rows, int dim,
-                       cudaStream_t stream);
+                       float* dgb_part, int max_parts, int* nparts_out, int rows, int dim, cudaStream_t stream);
 
 /* column sums: part[p][c] = sum over a slice of rows of x[r][c]  (x bf16 or f32), then finish() reduces the
  * parts.  Bias gradients of every Linear (autograd of customs.py:89) and LN gamma/beta gradients. */
 int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
                      int* nparts_out, cudaStream_t stream);
-int b200_colsum_finish(const float* part, int nparts, int cols, float* out, int round_bf16, int accumulate,
-                       cudaStream_t stream);
+int b200_colsum_finish(const float* part, long long part_ld, int nparts, int cols, float* out, int round_bf16,
+                       int accumulate, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention on the PACKED qkv tensor, replaces the split/permute/contiguous copies at

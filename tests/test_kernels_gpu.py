@@ -28,7 +28,11 @@ def _assert_bf16_close(got, ref_f32, what, max_ulps=1.01):
     """`got` (bf16) must equal bf16(ref) up to one bf16 ulp at a tiny fraction of positions."""
     ref = ref_f32.to(torch.bfloat16)
     rel = _relerr(got, ref)
-    assert rel < 2e-3, f"{what}: relative L2 error {rel}"
+    # same inputs + same rounding point => only rare 1-ulp flips where the fp32 sums differ in their last bits:
+    # well inside the 1e-3 relative target of BASELINE.json for a single op
+    assert rel < 3e-4, f"{what}: relative L2 error {rel}"
+    flips = (got != ref).float().mean().item()
+    assert flips < 2e-2, f"{what}: {flips:.3e} of the elements are not bit-identical to bf16(reference)"
     diff = (got.float() - ref.float()).abs()
     tol = ref.float().abs() * (2.0 ** -7) * max_ulps + 1e-3 * ref.float().abs().max()
     frac_bad = (diff > tol).float().mean().item()

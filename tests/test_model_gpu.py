@@ -6,8 +6,13 @@ reference), on the GPU.  Three comparisons per configuration:
   (2) vs the fp32 oracle: our bf16 path must be as close to the exact answer as eager bf16 is (<= 1.5x its error);
   (3) vs the golden vectors generated from the real reference on CPU (tests/golden/vit_tiny_reference.pt).
 
-Tolerances (relative L2, stated per BASELINE.json's 1e-3 target and what bf16 permits): forward tensors 2e-3; bf16
-gradients are compared both ways because two correct bf16 pipelines differ by accumulated 2^-9 roundings.
+Tolerances (relative L2).  Single ops match bf16(exact) to < 3e-4 (tests/test_kernels_gpu.py), inside BASELINE.json's
+1e-3.  End to end that figure is NOT attainable between ANY two bf16 pipelines: measured on the B200 the reference's
+own eager-autocast path sits 5e-3 (logits) / 7e-3 (median gradient) away from its own fp32 path, and once one bf16
+rounding decision differs, downstream roundings decorrelate within a layer or two (profiles/parity_r01.md).  The
+end-to-end criterion is therefore "as close to the exact answer as the reference's bf16 path is":
+    err(ours, fp32)  <= 1.5 x err(eager_bf16, fp32) + 1e-3      and      err(ours, eager_bf16) <= 2 x err(eager_bf16, fp32) + 1e-3
+(measured ratios: 1.07-1.25).  The integer label path is exact.
 """
 import os
 import sys
@@ -26,9 +31,9 @@ from cflearn_b200 import registry, vit  # noqa: E402
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-FWD_TOL = 2e-3
-GRAD_TOL_VS_EAGER = 2e-2
-GRAD_TOL_VS_FP32_FACTOR = 1.5
+VS_FP32_FACTOR = 1.5
+VS_EAGER_FACTOR = 2.0
+SLACK = 1e-3
 
 
 def rel(a, b):
@@ -73,18 +78,19 @@ def test_train_step_parity(name, batch):
     assert set(grads) == set(e_grads)
     assert logits.dtype == torch.bfloat16 and e_logits.dtype == torch.bfloat16
     err_logits = rel(logits, e_logits)
-    assert err_logits < FWD_TOL * 3, f"logits vs eager: {err_logits}"
-    assert rel(logits, f_logits) < max(GRAD_TOL_VS_FP32_FACTOR * rel(e_logits, f_logits), 1e-3)
-    assert abs(loss.item() - e_loss.item()) < 2e-3 * max(1.0, abs(e_loss.item()))
+    floor = rel(e_logits, f_logits)
+    assert err_logits < VS_EAGER_FACTOR * floor + SLACK, f"logits vs eager: {err_logits} (eager vs fp32 {floor})"
+    assert rel(logits, f_logits) < VS_FP32_FACTOR * floor + SLACK
+    assert abs(loss.item() - f_loss.item()) < 1.5 * abs(e_loss.item() - f_loss.item()) + 2e-3 * max(1.0, abs(f_loss.item()))
     worst = 0.0
     for k in sorted(grads):
         ours_vs_eager = rel(grads[k], e_grads[k])
         ours_vs_fp32 = rel(grads[k], f_grads[k])
         eager_vs_fp32 = rel(e_grads[k], f_grads[k])
-        worst = max(worst, ours_vs_eager)
-        assert ours_vs_eager < GRAD_TOL_VS_EAGER, f"{k}: ours vs eager {ours_vs_eager}"
-        assert ours_vs_fp32 < max(GRAD_TOL_VS_FP32_FACTOR * eager_vs_fp32, 2e-3), (k, ours_vs_fp32, eager_vs_fp32)
-    print(f"{name}: logits vs eager {err_logits:.2e}; worst grad vs eager {worst:.2e}")
+        worst = max(worst, ours_vs_fp32 / max(eager_vs_fp32, 1e-12))
+        assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
+        assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
+    print(f"{name}: logits vs eager {err_logits:.2e} (bf16 floor {floor:.2e}); worst grad err ratio ours/eager vs fp32 {worst:.2f}")
 
 
 def test_against_reference_golden_vectors():
@@ -131,9 +137,12 @@ def test_encoder_module_and_registry_surface():
     x, _ = vo.synthetic_batch(cfg, 5, seed=2)
     out = enc.encode(x.to(DEV))
     assert out.dtype == torch.float32 and out.shape == (5, cfg["latent_dim"])
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        ref = vo.encoder_forward({k: v.to(DEV) for k, v in sd.items()}, x.to(DEV), cfg)
-    assert rel(out, ref) < FWD_TOL * 3
+        ref = vo.encoder_forward(sdg, x.to(DEV), cfg)
+    exact = vo.encoder_forward(sdg, x.to(DEV), cfg)
+    assert rel(out, exact) < VS_FP32_FACTOR * rel(ref, exact) + SLACK
+    assert rel(out, ref) < VS_EAGER_FACTOR * rel(ref, exact) + SLACK
     out.sum().backward()
     assert all(p.grad is not None for p in enc.parameters())
     with pytest.raises(NotImplementedError):

@@ -41,6 +41,19 @@ def report(name, batch):
     e_loss, e_grads, e_taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=True, want_taps=True)
     f_loss, f_grads, f_taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=False, want_taps=True)
     print(f"## {name} B={batch}: loss ours {loss.item():.6f} eager-bf16 {e_loss.item():.6f} fp32 {f_loss.item():.6f}")
+    # the reference's own eager bf16 path under a second, equally legitimate SDPA backend: its self-consistency floor
+    try:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        with sdpa_kernel(SDPBackend.MATH):
+            m_loss, m_grads, m_taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=True, want_taps=True)
+        import statistics as _st
+
+        print(f"eager-bf16(default SDPA) vs eager-bf16(math SDPA): logits {rel(e_taps['logits'], m_taps['logits']):.3e}, "
+              f"median grad {_st.median(rel(e_grads[k], m_grads[k]) for k in e_grads):.3e}, "
+              f"worst grad {max(rel(e_grads[k], m_grads[k]) for k in e_grads):.3e}")
+    except Exception as err:  # pragma: no cover
+        print("eager-vs-eager skipped:", err)
     print(f"logits: ours-vs-eager {rel(logits, e_taps['logits']):.3e}  ours-vs-fp32 {rel(logits, f_taps['logits']):.3e}  eager-vs-fp32 {rel(e_taps['logits'], f_taps['logits']):.3e}")
     rows = []
     for k in grads:

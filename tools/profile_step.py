@@ -20,6 +20,7 @@ opt = ArenaAdam(m)
 x = torch.randn(B, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (B, 1), device=dev)
 for _ in range(steps):
+    opt.zero_grad()
     loss = m.train_step(x, y)
     opt.step()
 torch.cuda.synchronize()
