@@ -119,12 +119,13 @@ def cpu_reference_samples_per_sec(steps: int, warmup: int, budget_s: float):
         return loss
 
     # calibrate the bounded sample (micro-batch) so that (steps + warmup) steps fit the time budget
-    x, y = vo.synthetic_batch(cfg, 4, seed=0)
+    x, y = vo.synthetic_batch(cfg, 16, seed=0)
     step(x, y)  # cold step (thread pool spin-up, allocator): not representative
     t0 = time.perf_counter()
     step(x, y)
-    per_img = (time.perf_counter() - t0) / 4
-    mb = int(max(4, min(32, budget_s / max(1e-6, per_img * (steps + warmup)))))
+    per_img = (time.perf_counter() - t0) / 16
+    # many-core hosts need a reasonably large micro-batch to use their threads; keep it within the time budget
+    mb = int(max(8, min(64, budget_s / max(1e-6, per_img * (steps + warmup)))))
     x, y = vo.synthetic_batch(cfg, mb, seed=1)
     for _ in range(warmup):
         step(x, y)
@@ -187,7 +188,8 @@ def run_b200(args):
     if world > 1:
         dp.broadcast_parameters(model)
         dp.attach_reducer(model)
-    opt = ArenaAdam(model, lr=1e-3)
+    use_graph = (world == 1 and not args.no_graph) or args.graph_dp
+    opt = ArenaAdam(model, lr=1e-3, capturable=use_graph)
     B = PER_GPU_BATCH
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)  # rank r uses its own data seed
     n_host = 2
@@ -197,11 +199,23 @@ def run_b200(args):
     dev_y = [h.to(dev) for h in host_y]
     loss_host = torch.zeros(1).pin_memory()
 
-    def step_resident(i):
+    gstep = None
+    if use_graph:  # the whole step (zero_grad, fwd, CE, bwd, all-reduce, Adam) as ONE CUDA graph
+        from cflearn_b200.optim import GraphedTrainStep
+
+        model.arena.ensure()
+        gstep = GraphedTrainStep(model, opt, B)
+
+    def do_step(x, y):
+        if gstep is not None:
+            return gstep.step(x, y)
         opt.zero_grad()  # schema.py:984 (backward then overwrites the gradient arena instead of accumulating)
-        loss = model.train_step(dev_x[i % n_host], dev_y[i % n_host])
+        loss = model.train_step(x, y)
         opt.step()
         return loss
+
+    def step_resident(i):
+        return do_step(dev_x[i % n_host], dev_y[i % n_host])
 
     def barrier():
         if world > 1:
@@ -229,6 +243,8 @@ def run_b200(args):
     e1.record()
     barrier()
     launches = _cabi.launch_count() - launches0
+    if gstep is not None:  # graph replays launch the captured kernels without going through the host-side counter
+        launches = gstep.launches_per_replay * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
@@ -261,9 +277,7 @@ def run_b200(args):
             if i + 1 < n:
                 prefetch(i + 1)
             torch.cuda.current_stream().wait_event(ready[s])
-            opt.zero_grad()
-            ls = model.train_step(stage_x[s], stage_y[s])
-            opt.step()
+            ls = do_step(stage_x[s], stage_y[s])
             consumed[s].record(torch.cuda.current_stream())
             loss_host.copy_(ls.reshape(1), non_blocking=False)  # device->host read of the loss, every step (like .item())
 
@@ -325,6 +339,7 @@ def run_b200(args):
             "config": {"workload": "ViT-B/16 classifier 224x224, 1000 classes, batch 256 per GPU (BASELINE.json configs[1]/[2])",
                        "global_batch": world * B, "seq_len": 197, "parallelism": f"dp{world}",
                        "optimizer": "adam (fused arena kernel, inside the timed region)",
+                       "cuda_graph": bool(use_graph),
                        "l2": "per-step working set (> 15 GB of activations) exceeds the 126 MB L2; no explicit flush needed"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -343,6 +358,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--graph-dp", action="store_true", help="also capture the N > 1 step (NCCL all-reduce inside the graph)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

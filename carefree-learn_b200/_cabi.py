@@ -31,6 +31,7 @@ SIGNATURES: Dict[str, Any] = {
         [_P, _LL, c_int, _P, _LL, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _LL, c_int, c_int, _P],
     ),
     "b200_gemm_pick_splits": (c_int, [c_int, c_int, c_int]),
+    "b200_set_gemm_multicast": (c_int, [c_int]),
     "b200_splitk_reduce": (c_int, [_P, c_int, _LL, _P, c_int, c_int, _P]),
     "b200_layernorm_fwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "b200_layernorm_bwd": (
@@ -45,7 +46,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
-    "b200_adam_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
+    "b200_adam_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P, _P]),
     "b200_cast_f32_to_bf16": (c_int, [_P, _P, _LL, _P]),
     "b200_fill_f32": (c_int, [_P, c_float, _LL, _P]),
 }
@@ -70,6 +71,8 @@ def _load() -> None:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("B200_GEMM_MULTICAST", "1") == "0":  # A/B switch for profiling; results are identical
+            lib.b200_set_gemm_multicast(0)
         _lib = lib
     except (OSError, AttributeError) as err:  # pragma: no cover - depends on the build
         _load_error = f"failed to load {LIB_PATH}: {err}"

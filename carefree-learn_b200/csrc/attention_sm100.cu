@@ -136,9 +136,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
             tmem_ld_wait();
+            if (!p.causal && c * 16 + 16 <= p.T) {  // warp-uniform: whole chunk valid, no per-element masking
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (c * 16 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+                for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c * 16 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
+            }
         }
         const float m2 = m * sl2;
         // pass 2: p = exp2(s*c - m*c), row sum, P -> smem (bf16, K-major 128B swizzle)
@@ -148,11 +153,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
             tmem_ld_wait();
             float pv[16];
+            if (!p.causal && c * 16 + 16 <= p.T) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float e = exp2f(__uint_as_float(v[j]) * sl2 - m2);
-                pv[j] = (c * 16 + j < nvalid) ? e : 0.f;
-                sum += pv[j];
+                for (int j = 0; j < 16; ++j) {
+                    pv[j] = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m2));
+                    sum += pv[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float e = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m2));
+                    pv[j] = (c * 16 + j < nvalid) ? e : 0.f;
+                    sum += pv[j];
+                }
             }
             const int col = c * 16;
             uint8_t* blk = sP + (col >> 6) * 16384 + r * 128;
@@ -299,7 +312,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
             ls = lse_in[(static_cast<long long>(b) * p.H + h) * p.T + i];
         }
-        lse_s[i] = ls * kLog2e;
+        lse_s[i] = i < p.T ? ls * kLog2e : INFINITY;  // padded query rows: exp2(s - inf) = 0 -> P = dS = 0 for free
         delta_s[i] = dl;
     }
     tc_fence_before_sync();
@@ -374,7 +387,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int kt = 0; kt < n_kt; ++kt) {
             for (int mt = 0; mt < n_mt; ++mt, ++it) {
                 const int i = mt * 128 + r;
-                const bool rowvalid = i < p.T;
                 const float lse2 = lse_s[i];
                 const float delta = delta_s[i];
                 mbar_wait(bar_sdp, it & 1u);
@@ -388,13 +400,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     tmem_ld_32x32b_x16(taddr + TM_DP + static_cast<uint32_t>(col), dv);
                     tmem_ld_wait();
                     float pv[16], ds[16];
+                    if (!p.causal && j0 + 16 <= p.T) {  // warp-uniform fast path: every key of the chunk is valid
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + jj;
-                        const bool ok = rowvalid && (j < p.T) && (!p.causal || j <= i);
-                        const float e = exp2f(__uint_as_float(sv[jj]) * sl2 - lse2);
-                        pv[jj] = ok ? e : 0.f;
-                        ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - delta) : 0.f;
+                        for (int jj = 0; jj < 16; ++jj) {
+                            pv[jj] = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -lse2));
+                            ds[jj] = pv[jj] * (__uint_as_float(dv[jj]) - delta);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int j = j0 + jj;
+                            const bool ok = (j < p.T) && (!p.causal || j <= i);
+                            const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -lse2));
+                            pv[jj] = ok ? e : 0.f;
+                            ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - delta) : 0.f;
+                        }
                     }
                     const uint32_t c16 = static_cast<uint32_t>(c * 2);
                     const uint32_t off0 = static_cast<uint32_t>(ch) * 16384u + static_cast<uint32_t>(r) * 128u + (((c16) ^ (static_cast<uint32_t>(r) & 7u)) << 4);

@@ -47,15 +47,18 @@ struct GemmParams {
     int M, N, K;
     int num_m_tiles, num_n_tiles, splits, num_kb;
     int a_mn, b_mn;  // 1 = MN-major operand
+    int cluster;     // 1, or 2: CTA pairs work on vertically adjacent tiles and multicast the shared B tile
     const __nv_bfloat16* bias;  // [N] bf16 or nullptr
 };
 
-__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& m_t, int& n_t, int& sp, int& kb0,
-                                            int& kb1) {
+// Work unit u (per cluster) -> (m tile of THIS CTA, n tile, split, k-block range).  With cluster == 2 the two CTAs of
+// a cluster take m tiles 2g and 2g+1 of the same (n tile, split): identical k loop, shared B tile.
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, uint32_t cta_rank, int& m_t, int& n_t, int& sp,
+                                            int& kb0, int& kb1) {
     n_t = u % p.num_n_tiles;
     int r = u / p.num_n_tiles;
     sp = r % p.splits;
-    m_t = r / p.splits;
+    m_t = (r / p.splits) * p.cluster + static_cast<int>(cta_rank);
     kb0 = static_cast<int>((static_cast<long long>(p.num_kb) * sp) / p.splits);
     kb1 = static_cast<int>((static_cast<long long>(p.num_kb) * (sp + 1)) / p.splits);
 }
@@ -71,7 +74,7 @@ __device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {  /
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
                  const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +90,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+    // clusters (of 1 or 2 CTAs) stride over the work units; both CTAs of a pair run the same unit sequence
+    const uint32_t cta_rank = p.cluster > 1 ? cluster_ctarank() : 0u;
+    const int total_units = ((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * p.splits;
+    const int unit0 = static_cast<int>(blockIdx.x) / p.cluster;
+    const int unit_stride = static_cast<int>(gridDim.x) / p.cluster;
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -97,7 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], static_cast<uint32_t>(p.cluster));  // released by the MMA warp of EVERY CTA in the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -111,7 +119,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_relinquish();
     }
     tc_fence_before_sync();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();  // the peer's barriers must be initialised before we multicast into them
+    else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -120,9 +129,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+            for (int u = unit0; u < total_units; u += unit_stride) {
                 int m_t, n_t, sp, kb0, kb1;
-                decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+                decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
                 const int m0 = m_t * BM, n0 = n_t * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -136,12 +145,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int i = 0; i < BM / 64; ++i)
                             tma_load_2d(a_dst + i * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
                     }
-                    if (!p.b_mn) {
-                        tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
-                    } else {
+                    if (p.cluster == 1) {
+                        if (!p.b_mn) {
+                            tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(b_dst + i * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+                            for (int i = 0; i < BN / 64; ++i)
+                                tma_load_2d(b_dst + i * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+                        }
+                    } else {
+                        // this CTA fetches HALF of the shared B tile and multicasts it into both CTAs' smem (same
+                        // offset, each CTA's own full barrier gets the bytes): 32 KB instead of 48 KB of L2 reads per
+                        // CTA and k-block.
+                        const int h = static_cast<int>(cta_rank);
+                        if (!p.b_mn) {
+                            tma_load_2d_mcast(b_dst + h * (B_STAGE_BYTES / 2), &tmBh, &full_bar[stage], kb * BK, n0 + h * (BN / 2), mc_mask);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)
+                                tma_load_2d_mcast(b_dst + (2 * h + i) * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + (2 * h + i) * 64, kb * BK, mc_mask);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -154,9 +177,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int lt = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lt) {
+            for (int u = unit0; u < total_units; u += unit_stride, ++lt) {
                 int m_t, n_t, sp, kb0, kb1;
-                decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+                decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
                 const int as = lt & 1;
                 const uint32_t aph = (lt >> 1) & 1u;
                 mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
@@ -178,7 +201,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                       : make_smem_desc(b_base + kk * 32, 0, 1024, kSwz128);
                         umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire; with multicast the slot is also written by the peer's
+                    // TMA, so the release goes to the empty barrier of both CTAs
+                    if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
@@ -193,9 +219,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint64_t* my_aux_bar = &aux_bar[e];
         uint32_t aux_phase = 0;
         int lt = 0;
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++lt) {
+        for (int u = unit0; u < total_units; u += unit_stride, ++lt) {
             int m_t, n_t, sp, kb0, kb1;
-            decode_unit(p, u, m_t, n_t, sp, kb0, kb1);
+            decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1u;
             const int grow0 = m_t * BM + static_cast<int>(q) * 32;
@@ -343,7 +369,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 
     tc_fence_before_sync();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into / arrive on its smem
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -416,9 +443,11 @@ int num_sms() {
     return cached[dev];
 }
 
+static int g_gemm_multicast = 1;
+
 template <int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& o0, const CUtensorMap& o1,
-                       const CUtensorMap& ax, const GemmParams& p, int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& o0,
+                       const CUtensorMap& o1, const CUtensorMap& ax, const GemmParams& p, int grid, cudaStream_t stream) {
     static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
     cudaError_t e;
     if (!configured) {
@@ -426,7 +455,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
         configured = true;
     }
-    gemm_bf16_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, o0, o1, ax, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, tmA, tmB, tmBh, o0, o1, ax, p);
+    if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     count_launch(1);
@@ -436,6 +478,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_set_gemm_multicast(int enable) {
+    const int old = g_gemm_multicast;
+    g_gemm_multicast = enable ? 1 : 0;
+    return old;
+}
 
 extern "C" int b200_gemm_pick_splits(int M, int N, int K) {
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -471,7 +519,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     const int num_kb = (K + BK - 1) / BK;
     if (splits > num_kb) splits = num_kb;
 
-    CUtensorMap tmA, tmB, tmO0, tmO1, tmAx;
+    CUtensorMap tmA, tmB, tmBh, tmO0, tmO1, tmAx;
     int rc;
     {
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
@@ -485,6 +533,11 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         else             { d[0] = N; d[1] = K; bx[0] = 64; bx[1] = BK; }
         s[0] = static_cast<uint64_t>(ldb) * 2;
         if ((rc = make_tmap(&tmB, B, 2, 2, d, s, bx, 128)) != 0) return rc;
+        tmBh = tmB;
+        if (!b_mn_major) {  // half-tile box for the multicast path (MN-major boxes are 64 wide already)
+            bx[1] = BN / 2;
+            if ((rc = make_tmap(&tmBh, B, 2, 2, d, s, bx, 128)) != 0) return rc;
+        }
     }
     const bool out_f32 = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_PARTIAL_F32);
     {
@@ -514,16 +567,20 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     p.a_mn = a_mn_major ? 1 : 0;
     p.b_mn = b_mn_major ? 1 : 0;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-    const long long units = static_cast<long long>(p.num_m_tiles) * p.num_n_tiles * splits;
+    p.cluster = (g_gemm_multicast && max_ctas != 1) ? 2 : 1;
+    const long long units = static_cast<long long>((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * splits;
     int grid = num_sms();
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-    if (units < grid) grid = static_cast<int>(units);
+    int nclusters = grid / p.cluster;
+    if (nclusters < 1) nclusters = 1;
+    if (units < nclusters) nclusters = static_cast<int>(units);
+    grid = nclusters * p.cluster;
     switch (epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
         default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
     }
 }

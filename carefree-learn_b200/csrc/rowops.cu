@@ -466,9 +466,14 @@ __global__ void fill_f32_kernel(float* __restrict__ dst, float v, long long n) {
 // Adam over the flat parameter arena (torch.optim.Adam semantics, no amsgrad; L2 weight decay added to the grad)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n4, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt) {
+                            float bc1, float bc2_sqrt, const int* __restrict__ step_dev) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (step_dev != nullptr) {  // step counter lives on the device (CUDA-graph replay): derive the bias corrections here
+        const float t = static_cast<float>(step_dev[0]);
+        bc1 = 1.0f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    }
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -489,6 +494,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
 }
+
+__global__ void increment_kernel(int* counter) { counter[0] += 1; }
 
 template <int NV>
 static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, const float* beta, void* y, float* y32,
@@ -626,13 +633,20 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long
 }
 extern "C" int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                              cudaStream_t stream) {
-    if (n <= 0 || n % 4 != 0 || step < 1) return set_error(B200_ERR_ARG, "adam_step: n must be a positive multiple of 4, step >= 1");
-    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
-    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+                              int* step_dev, cudaStream_t stream) {
+    if (n <= 0 || n % 4 != 0) return set_error(B200_ERR_ARG, "adam_step: n must be a positive multiple of 4");
+    if (step_dev == nullptr && step < 1) return set_error(B200_ERR_ARG, "adam_step: step >= 1 (or pass step_dev)");
+    if (step_dev != nullptr) {
+        increment_kernel<<<1, 1, 0, stream>>>(step_dev);
+        int rc = check_launch("adam_step_increment");
+        if (rc) return rc;
+    }
+    const float t = static_cast<float>(step < 1 ? 1 : step);
+    const float bc1 = 1.0f - powf(beta1, t);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, t));
     const long long n4 = n / 4;
     adam_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n4, lr, beta1,
-                                                                          beta2, eps, weight_decay, bc1, bc2_sqrt);
+                                                                          beta2, eps, weight_decay, bc1, bc2_sqrt, step_dev);
     return check_launch("adam_step");
 }
 extern "C" int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream) {

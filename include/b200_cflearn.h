@@ -68,6 +68,9 @@ int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
                    long long ldo, int splits, int max_ctas, cudaStream_t stream);
 /* split count that fills the 148 SMs best for an [M,N] output with reduction length K */
 int b200_gemm_pick_splits(int M, int N, int K);
+/* 1 (default): CTA pairs (thread-block clusters of 2) multicast the shared B tile through TMA; 0: every CTA loads
+ * its own operands.  Returns the previous setting.  Results are identical; only L2 traffic differs. */
+int b200_set_gemm_multicast(int enable);
 /* out[f32][n] (+)= round( sum_s partial[s][n] ); round_bf16 mirrors autocast (the weight grad of a bf16 matmul
  * is produced in bf16, cf. cflearn/schema.py:1266-1276 autocast + :980 backward). accumulate: 0 overwrite. */
 int b200_splitk_reduce(const float* partial, int splits, long long n, float* out, int round_bf16, int accumulate,
@@ -137,10 +140,13 @@ int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimizer step on the flat fp32 arenas (torch.optim.Adam semantics without amsgrad; the reference's default
- * optimizer "adam", cflearn/optimizers.py:29-32, stepped at cflearn/schema.py:983).  n % 4 == 0; step >= 1.
+ * optimizer "adam", cflearn/optimizers.py:29-32, stepped at cflearn/schema.py:983).  n % 4 == 0.
+ * step_dev == NULL: `step` (>= 1) is the host-side step count.  step_dev != NULL: a device int that is incremented
+ * (on the stream) and then used as the step count, so the call can be replayed from a CUDA graph.
  * --------------------------------------------------------------------------------------------------------- */
 int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t stream);
+                   float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
+                   cudaStream_t stream);
 
 /* element-wise helpers */
 int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream);

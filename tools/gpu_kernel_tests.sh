@@ -11,7 +11,7 @@ run() { # name, -k expression
 run rowops "cast or layernorm or colsum or patch or softmax"
 run gemm_kmajor "gemm_kmajor"
 run gemm_mn "gemm_mn_major"
-run gemm_persist "gemm_persistent"
+run gemm_persist "gemm_persistent or multicast"
 run gemm_epi "gelu_epilogue or residual_epilogue or dgelu_epilogue or wgrad"
 run attn_fwd "attention_fwd"
 run attn_bwd "attention_bwd"
