@@ -7,12 +7,13 @@
 // and their autograd.  T <= 256 (197 for ViT-B/16, 50 / 77 for CLIP) so one KV tile covers the whole
 // sequence: no online-softmax rescaling is needed and every score row lives in one TMEM lane.
 //
-// Forward, one CTA per (batch, head, 128-query tile), 2 CTAs / SM:
+// Forward, one CTA per (batch, head, 128-query tile), 2 CTAs / SM (18 warps):
 //   TMA: Q[128x64], K[Tp x64], V[Tp x64] (3-D tensor map over qkv, rows >= T zero-filled)
 //   tcgen05.mma  S = Q K^T            (128 x Tp x 64, fp32 in TMEM)
-//   4 warps      row-per-thread softmax straight out of TMEM (tcgen05.ld), P -> bf16 -> 128B-swizzled smem
+//   8 warps      softmax straight out of TMEM (tcgen05.ld): two threads per score row (one per column half, max / sum
+//                exchanged through 2 KB of smem), P -> bf16 -> 128B-swizzled smem
 //   tcgen05.mma  O = P V              (A = P K-major from smem, B = V MN-major from smem)
-//   4 warps      O / rowsum -> bf16 -> out[B, T, H*64]  (already in the layout the out-projection GEMM reads)
+//   8 warps      O / rowsum -> bf16 -> out[B, T, H*64]  (already in the layout the out-projection GEMM reads)
 //
 // Backward, one CTA per (batch, head): outer loop over 128-key tiles, inner loop over 128-query tiles.
 //   S = Q K^T, dP = dO V^T            (TMEM cols [0,128) and [128,256))
@@ -38,12 +39,13 @@ constexpr float kLog2e = 1.4426950408889634f;
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int AF_THREADS = 160;
+constexpr int AF_THREADS = 288;     // 8 softmax warps (two threads per score row) + 1 TMA/MMA warp
 constexpr int AF_SQ = 0;            // 16 KB
 constexpr int AF_SK = 16384;        // 32 KB
 constexpr int AF_SP = 0;            // 64 KB, aliases Q and K (written only after S = QK^T has retired)
 constexpr int AF_SV = 65536;        // 32 KB
-constexpr int AF_BAR = 98304;
+constexpr int AF_XCH = 98304;       // 2 KB: per-row max / sum exchanged between the two column halves
+constexpr int AF_BAR = AF_XCH + 2048;
 constexpr int AF_SMEM = AF_BAR + 64 + 1024;
 
 struct AttnParams {
@@ -67,6 +69,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* bar_p = bar_load + 2;
     uint64_t* bar_o = bar_load + 3;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_load + 4);
+    float* xch_max = reinterpret_cast<float*>(smem + AF_XCH);  // [2][128]
+    float* xch_sum = xch_max + 256;                            // [2][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,13 +80,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int h = bh % p.H;
     const int b = bh / p.H;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmKV);
             mbar_init(bar_load, 1);
             mbar_init(bar_s, 1);
-            mbar_init(bar_p, 128);
+            mbar_init(bar_p, 256);
             mbar_init(bar_o, 1);
             fence_mbar_init();
         }
@@ -95,7 +99,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             mbar_expect_tx(bar_load, 16384u + 2u * static_cast<uint32_t>(p.tp) * 128u);
             tma_load_3d(sQ, &tmQ, bar_load, h * 64, mt * 128, b);
@@ -121,18 +125,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(bar_o);
         }
     } else {
-        const int r = threadIdx.x;  // row inside the query tile == TMEM lane
-        const int i = mt * 128 + r;  // query index
-        const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(warp) * 32u) << 16);
+        const uint32_t q = static_cast<uint32_t>(warp & 3);  // TMEM lane quadrant
+        const int half = warp >> 2;                           // which half of the score columns this thread owns
+        const int r = static_cast<int>(q) * 32 + lane;        // row inside the query tile == TMEM lane
+        const int i = mt * 128 + r;                           // query index
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16);
         const float sl2 = p.scale * kLog2e;
         int nvalid = p.T;
         if (p.causal && i + 1 < nvalid) nvalid = i + 1;
         const int nchunk = p.tp / 16;
+        const int nc0 = (nchunk + 1) / 2;
+        const int c_begin = half ? nc0 : 0, c_end = half ? nchunk : nc0;
         mbar_wait(bar_s, 0);
         tc_fence_after_sync();
-        // pass 1: row max
+        // pass 1: row max over this thread's column half, then combine the two halves
         float m = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
             tmem_ld_wait();
@@ -145,10 +153,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     if (c * 16 + j < nvalid) m = fmaxf(m, __uint_as_float(v[j]));
             }
         }
+        xch_max[half * 128 + r] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(xch_max[r], xch_max[128 + r]);
         const float m2 = m * sl2;
         // pass 2: p = exp2(s*c - m*c), row sum, P -> smem (bf16, K-major 128B swizzle)
         float sum = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
             tmem_ld_wait();
@@ -175,9 +186,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             *reinterpret_cast<uint4*>(blk + (((ch + 1) ^ (r & 7u)) << 4)) =
                 make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
         }
+        xch_sum[half * 128 + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(bar_p);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        sum = xch_sum[r] + xch_sum[128 + r];
         // O = P V
         mbar_wait(bar_o, 0);
         tc_fence_after_sync();
@@ -185,7 +199,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool valid = i < p.T;
         __nv_bfloat16* orow = out + (static_cast<long long>(b) * p.T + i) * p.D + h * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {  // each half writes 32 of the 64 output columns
+            const int c = half * 2 + cc;
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
             tmem_ld_wait();
@@ -203,11 +218,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 reinterpret_cast<uint4*>(orow + c * 16)[1] = o1;
             }
         }
-        if (valid) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
+        if (valid && half == 0) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 256);
     }

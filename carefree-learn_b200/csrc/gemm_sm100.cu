@@ -368,6 +368,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
     }
 
+    __syncwarp();  // reconverge warps 0 / 1 (only one elected lane ran the role loop): the cluster barrier is .aligned
     tc_fence_before_sync();
     if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into / arrive on its smem
     else __syncthreads();
