@@ -188,7 +188,9 @@ def run_b200(args):
     if world > 1:
         dp.broadcast_parameters(model)
         dp.attach_reducer(model)
-    use_graph = (world == 1 and not args.no_graph) or args.graph_dp
+    use_graph = not (args.no_graph or args.overlap_dp)
+    if use_graph and world > 1:
+        model.engine.reducer = None  # graphed DP step: one all-reduce of the flat gradient arena after the replay
     opt = ArenaAdam(model, lr=1e-3, capturable=use_graph)
     B = PER_GPU_BATCH
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)  # rank r uses its own data seed
@@ -200,7 +202,7 @@ def run_b200(args):
     loss_host = torch.zeros(1).pin_memory()
 
     gstep = None
-    if use_graph:  # the whole step (zero_grad, fwd, CE, bwd, all-reduce, Adam) as ONE CUDA graph
+    if use_graph:  # zero_grad + fwd + CE + bwd (+ Adam at N = 1) as ONE CUDA graph; N > 1: all-reduce + Adam follow it
         from cflearn_b200.optim import GraphedTrainStep
 
         model.arena.ensure()
@@ -268,7 +270,12 @@ def run_b200(args):
             stage_y[s].copy_(host_y[i % n_host], non_blocking=True)
             ready[s].record(copy_stream)
 
+    loss_dev = [torch.zeros(1, device=dev) for _ in range(2)]
+    loss_pinned = [torch.zeros(1).pin_memory() for _ in range(2)]
+    losses_seen = []
+
     def e2e_loop(n):
+        pending = None
         for s in range(2):
             consumed[s].record(torch.cuda.current_stream())
         prefetch(0)
@@ -279,7 +286,19 @@ def run_b200(args):
             torch.cuda.current_stream().wait_event(ready[s])
             ls = do_step(stage_x[s], stage_y[s])
             consumed[s].record(torch.cuda.current_stream())
-            loss_host.copy_(ls.reshape(1), non_blocking=False)  # device->host read of the loss, every step (like .item())
+            # device->host read of the loss every step (the reference's per-step .item(), models/common.py:42); the
+            # read of step i is waited for after step i+1 has been queued so the GPU never idles on the host
+            loss_dev[i % 2].copy_(ls.reshape(1))
+            if pending is not None:
+                pending[0].synchronize()
+                losses_seen.append(float(loss_pinned[pending[1]][0]))
+            loss_pinned[i % 2].copy_(loss_dev[i % 2], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            pending = (ev, i % 2)
+        if pending is not None:
+            pending[0].synchronize()
+            losses_seen.append(float(loss_pinned[pending[1]][0]))
 
     e2e_loop(max(1, min(3, args.warmup)))
     barrier()
@@ -359,7 +378,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--graph-dp", action="store_true", help="also capture the N > 1 step (NCCL all-reduce inside the graph)")
+    ap.add_argument("--overlap-dp", action="store_true", help="N > 1: eager launches with the bucketed, overlapped all-reduce (implies --no-graph)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -71,8 +71,8 @@ def _load() -> None:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if os.environ.get("B200_GEMM_MULTICAST", "1") == "0":  # A/B switch for profiling; results are identical
-            lib.b200_set_gemm_multicast(0)
+        if os.environ.get("B200_GEMM_MULTICAST", "") in ("0", "1", "2"):  # A/B/C switch for profiling; results are identical
+            lib.b200_set_gemm_multicast(int(os.environ["B200_GEMM_MULTICAST"]))
         _lib = lib
     except (OSError, AttributeError) as err:  # pragma: no cover - depends on the build
         _load_error = f"failed to load {LIB_PATH}: {err}"

@@ -47,7 +47,9 @@ struct GemmParams {
     int M, N, K;
     int num_m_tiles, num_n_tiles, splits, num_kb;
     int a_mn, b_mn;  // 1 = MN-major operand
-    int cluster;     // 1, or 2: CTA pairs work on vertically adjacent tiles and multicast the shared B tile
+    int cluster;     // 1, or 2: CTA pairs work on vertically adjacent tiles and share the B tile
+    int two_sm;      // cluster == 2 only.  0: each CTA runs its own 128x256 MMA, the B tile is TMA-multicast to both;
+                     //                     1: tcgen05 cta_group::2 -- ONE 256x256 MMA per pair, each CTA holds HALF of B
     const __nv_bfloat16* bias;  // [N] bf16 or nullptr
 };
 
@@ -75,7 +77,8 @@ template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
-                 const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmAuxPf,
+                 const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem + SMEM_A_OFF;
@@ -105,18 +108,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAux);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], static_cast<uint32_t>(p.cluster));  // released by the MMA warp of EVERY CTA in the cluster
+            // multicast mode: released by the MMA warp of EVERY CTA in the cluster; 2-SM mode: by the leader's commit
+            mbar_init(&empty_bar[i], p.two_sm ? 1u : static_cast<uint32_t>(p.cluster));
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[i], p.two_sm ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // 2-SM: both CTAs' epilogues report to the leader
         }
         for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-        tmem_relinquish();
+        if (p.two_sm) {  // pair allocation: the same warp of both CTAs, same destination offset
+            tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before_sync();
     if (p.cluster > 1) cluster_sync_all();  // the peer's barriers must be initialised before we multicast into them
@@ -133,11 +142,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int m_t, n_t, sp, kb0, kb1;
                 decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
                 const int m0 = m_t * BM, n0 = n_t * BN;
+                if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
+                    // the epilogue will TMA-load this tile of the residual / pre-activation: start pulling it into L2
+                    // now, a whole mainloop ahead, so those loads see L2 (not HBM) latency
+                    if (m0 < p.M && n0 < p.N) tma_prefetch_l2_3d(&tmAuxPf, n0, m0, 0);
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                     uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+                    if (p.two_sm) {
+                        // cta_group::2: every load of BOTH CTAs is credited to the LEADER's full barrier, which the
+                        // leader arms once with the bytes of the whole pair (2 x (A 16 KB + half B 16 KB)).
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2));
+                        const int h = static_cast<int>(cta_rank);
+                        if (!p.a_mn) {
+                            tma_load_2d_2sm(a_dst, &tmA, lead_full, kb * BK, m0);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BM / 64; ++i)
+                                tma_load_2d_2sm(a_dst + i * MN_BOX_BYTES, &tmA, lead_full, m0 + i * 64, kb * BK);
+                        }
+                        if (!p.b_mn) {  // this CTA's half of the B tile (128 of the 256 n rows), at offset 0 of the stage
+                            tma_load_2d_2sm(b_dst, &tmBh, lead_full, kb * BK, n0 + h * (BN / 2));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)
+                                tma_load_2d_2sm(b_dst + i * MN_BOX_BYTES, &tmB, lead_full, n0 + (2 * h + i) * 64, kb * BK);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     if (!p.a_mn) {
                         tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
                     } else {
@@ -172,8 +209,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+        if (elect_one() && (!p.two_sm || cta_rank == 0)) {  // 2-SM mode: only the pair leader issues MMAs
+            const uint32_t idesc = make_idesc_bf16(p.two_sm ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
             int stage = 0;
             uint32_t phase = 0;
             int lt = 0;
@@ -199,15 +236,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                       : make_smem_desc(a_base + kk * 32, 0, 1024, kSwz128);
                         const uint64_t bdesc = p.b_mn ? make_smem_desc(b_base + kk * 2048, MN_BOX_BYTES, 1024, kSwz128)
                                                       : make_smem_desc(b_base + kk * 32, 0, 1024, kSwz128);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        if (p.two_sm) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
                     // smem slot reusable once these MMAs retire; with multicast the slot is also written by the peer's
                     // TMA, so the release goes to the empty barrier of both CTAs
-                    if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
+                    if (p.two_sm) umma_commit_2sm_mcast(&empty_bar[stage], mc_mask);
+                    else if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
                     else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (2-SM: each CTA's epilogue owns 128 of the 256 accumulator rows)
+                if (p.two_sm) umma_commit_2sm_mcast(&tmem_full_bar[as], mc_mask);
+                else umma_commit(&tmem_full_bar[as]);
             }
         }
     } else {
@@ -233,9 +274,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int col = half * 128 + c * 32;
                 const int gcol = n_t * BN + col;
                 const bool active = (gcol < p.N) && (grow0 < p.M);  // warp-uniform
-                // staging buffer must have been drained by the previous TMA store
-                if (lane == 0) tma_store_wait_read0();
+                // staging buffer must have been drained by the TMA store that last used it (bf16 chunks rotate over the
+                // two 2 KB halves, so only the store before the previous one has to be finished)
+                if (lane == 0) {
+                    if constexpr (EPI == EPI_BIAS_BF16) tma_store_wait_read1();
+                    else tma_store_wait_read0();
+                }
                 __syncwarp();
+                uint8_t* const stg_c = (EPI == EPI_BIAS_BF16) ? stg + (c & 1) * 2048 : stg;
                 if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
                     if (active && lane == 0) {
                         mbar_expect_tx(my_aux_bar, EPI == EPI_BIAS_RESID_F32 ? 4096u : 2048u);
@@ -248,7 +294,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (c == 3) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    if (lane == 0) {
+                        if (p.two_sm) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        else mbar_arrive(&tmem_empty_bar[as]);
+                    }
                 }
                 if (!active) continue;
 
@@ -276,12 +325,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         o.y = pack_bf16x2(__uint_as_float(v[j4 * 8 + 2]) + bv[j4 * 8 + 2], __uint_as_float(v[j4 * 8 + 3]) + bv[j4 * 8 + 3]);
                         o.z = pack_bf16x2(__uint_as_float(v[j4 * 8 + 4]) + bv[j4 * 8 + 4], __uint_as_float(v[j4 * 8 + 5]) + bv[j4 * 8 + 5]);
                         o.w = pack_bf16x2(__uint_as_float(v[j4 * 8 + 6]) + bv[j4 * 8 + 6], __uint_as_float(v[j4 * 8 + 7]) + bv[j4 * 8 + 7]);
-                        *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = o;
+                        *reinterpret_cast<uint4*>(stg_c + swz64_off(lane, j4)) = o;
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
+                        tma_store_3d(&tmOut0, stg_c, gcol, grow0, sp);
                         tma_store_commit();
                     }
                 } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
@@ -293,7 +342,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int t = 0; t < 4; ++t) {
                             const int j = j4 * 8 + t * 2;
                             hp[t] = pack_bf16x2(__uint_as_float(v[j]) + bv[j], __uint_as_float(v[j + 1]) + bv[j + 1]);
-                            gp[t] = pack_bf16x2(gelu_erf(bf16lo(hp[t])), gelu_erf(bf16hi(hp[t])));
+                            float g0, g1;
+                            gelu_erf2(bf16lo(hp[t]), bf16hi(hp[t]), g0, g1);
+                            gp[t] = pack_bf16x2(g0, g1);
                         }
                         *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                         *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
@@ -337,9 +388,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const int j = j4 * 8 + t * 2;
-                            const float d0 = bf16_round(__uint_as_float(v[j])) * gelu_erf_grad(bf16lo(hw[t]));
-                            const float d1 = bf16_round(__uint_as_float(v[j + 1])) * gelu_erf_grad(bf16hi(hw[t]));
-                            op[t] = pack_bf16x2(d0, d1);
+                            float g0, g1;
+                            gelu_erf_grad2(bf16lo(hw[t]), bf16hi(hw[t]), g0, g1);
+                            const uint32_t dg = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));  // bf16(acc)
+                            op[t] = pack_bf16x2(bf16lo(dg) * g0, bf16hi(dg) * g1);
                         }
                         *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(op[0], op[1], op[2], op[3]);
                     }
@@ -374,7 +426,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (p.two_sm) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -444,11 +497,12 @@ int num_sms() {
     return cached[dev];
 }
 
-static int g_gemm_multicast = 1;
+static int g_gemm_multicast = 1;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2: CTA pairs + cta_group::2 MMA
 
 template <int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& o0,
-                       const CUtensorMap& o1, const CUtensorMap& ax, const GemmParams& p, int grid, cudaStream_t stream) {
+                       const CUtensorMap& o1, const CUtensorMap& ax, const CUtensorMap& axpf, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
     static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
     cudaError_t e;
     if (!configured) {
@@ -468,7 +522,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, tmA, tmB, tmBh, o0, o1, ax, p);
+    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, tmA, tmB, tmBh, o0, o1, ax, axpf, p);
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
@@ -482,7 +536,7 @@ using namespace b200;
 
 extern "C" int b200_set_gemm_multicast(int enable) {
     const int old = g_gemm_multicast;
-    g_gemm_multicast = enable ? 1 : 0;
+    g_gemm_multicast = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return old;
 }
 
@@ -520,7 +574,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     const int num_kb = (K + BK - 1) / BK;
     if (splits > num_kb) splits = num_kb;
 
-    CUtensorMap tmA, tmB, tmBh, tmO0, tmO1, tmAx;
+    CUtensorMap tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf;
     int rc;
     {
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
@@ -550,6 +604,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         if ((rc = make_tmap(&tmO0, out0, eb, 3, d, s, bx, swz)) != 0) return rc;
         tmO1 = tmO0;
         tmAx = tmO0;
+        tmAxPf = tmO0;
         if (epilogue == EPI_BIAS_GELU_BF16) {
             if (out1 == nullptr) return set_error(B200_ERR_ARG, "gemm: GELU epilogue needs out1");
             if ((rc = make_tmap(&tmO1, out1, eb, 3, d, s, bx, swz)) != 0) return rc;
@@ -557,6 +612,8 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         if (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_DGELU_BF16) {
             if (aux == nullptr) return set_error(B200_ERR_ARG, "gemm: epilogue needs aux");
             if ((rc = make_tmap(&tmAx, aux, eb, 3, d, s, bx, swz)) != 0) return rc;
+            uint32_t bxpf[3] = {static_cast<uint32_t>(BN), static_cast<uint32_t>(BM), 1};  // whole-tile L2 prefetch box
+            if ((rc = make_tmap(&tmAxPf, aux, eb, 3, d, s, bxpf, 0)) != 0) return rc;
         }
     }
     GemmParams p;
@@ -569,6 +626,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     p.b_mn = b_mn_major ? 1 : 0;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.cluster = (g_gemm_multicast && max_ctas != 1) ? 2 : 1;
+    p.two_sm = (p.cluster == 2 && g_gemm_multicast == 2) ? 1 : 0;
     const long long units = static_cast<long long>((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * splits;
     int grid = num_sms();
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
@@ -577,11 +635,11 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     if (units < nclusters) nclusters = static_cast<int>(units);
     grid = nclusters * p.cluster;
     switch (epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
-        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, p, grid, stream);
+        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
+        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
+        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
+        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
         default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
     }
 }

@@ -109,6 +109,54 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tm
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
         : "memory");
 }
+// ---- cta_group::2 (CTA-pair) forms --------------------------------------------------------------------------
+// address of the same smem offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on a (possibly remote) mbarrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the bytes are credited to the mbarrier
+// at `bar_cluster_addr` (the pair leader's barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 split over the pair: each CTA supplies its 128 rows of A and its half
+// of B (N/2 rows) at the SAME smem offsets; issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -128,6 +176,16 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
                      reinterpret_cast<uint64_t>(tmap)),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+// L2 prefetch of a tile (no smem destination): lets a later TMA load of the same bytes hit L2 instead of HBM
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// wait until at most 1 committed bulk store still has to read its smem source (two staging buffers in rotation)
+__device__ __forceinline__ void tma_store_wait_read1() {
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the smem source of all committed bulk stores has been read (buffer reusable)
@@ -302,6 +360,70 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float e = fast_ex2(x * x * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
+// ---- packed fp32x2 versions (sm_100 FFMA2 / FMUL2 / FADD2: two lanes of fp32 per issue slot) --------------------
+// The GELU epilogues are issue-bound (one 128x256 tile = 32768 activations against 6144 cycles of MMA), so the
+// polynomial work is done two elements at a time.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// (1 + erf(z0)), (1 + erf(z1)); optionally also exp(-z^2) for both (needed by the derivative)
+template <bool kWantExp>
+__device__ __forceinline__ void one_plus_erf2(float z0, float z1, float& o0, float& o1, float& e0, float& e1) {
+    const float a0 = fabsf(z0), a1 = fabsf(z1);
+    const f32x2_t az = pk2(a0, a1);
+    float d0, d1;
+    upk2(fma2(az, pk2(0.5f, 0.5f), pk2(1.0f, 1.0f)), d0, d1);
+    const f32x2_t t = pk2(fast_rcp(d0), fast_rcp(d1));
+    f32x2_t p = fma2(pk2(0.17087277f, 0.17087277f), t, pk2(-0.82215223f, -0.82215223f));
+    p = fma2(p, t, pk2(1.48851587f, 1.48851587f));
+    p = fma2(p, t, pk2(-1.13520398f, -1.13520398f));
+    p = fma2(p, t, pk2(0.27886807f, 0.27886807f));
+    p = fma2(p, t, pk2(-0.18628806f, -0.18628806f));
+    p = fma2(p, t, pk2(0.09678418f, 0.09678418f));
+    p = fma2(p, t, pk2(0.37409196f, 0.37409196f));
+    p = fma2(p, t, pk2(1.00002368f, 1.00002368f));
+    p = fma2(p, t, pk2(-1.26551223f, -1.26551223f));
+    const f32x2_t nz2 = mul2(pk2(-a0, -a1), az);  // -z^2
+    float g0, g1;
+    upk2(mul2(fma2(p, pk2(1.0f, 1.0f), nz2), pk2(1.4426950408889634f, 1.4426950408889634f)), g0, g1);
+    float w0, w1;
+    upk2(mul2(t, pk2(fast_ex2(g0), fast_ex2(g1))), w0, w1);
+    o0 = z0 >= 0.f ? 2.0f - w0 : w0;
+    o1 = z1 >= 0.f ? 2.0f - w1 : w1;
+    if (kWantExp) {
+        float n0, n1;
+        upk2(mul2(nz2, pk2(1.4426950408889634f, 1.4426950408889634f)), n0, n1);
+        e0 = fast_ex2(n0);
+        e1 = fast_ex2(n1);
+    }
+}
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float& g0, float& g1) {
+    float o0, o1, u0, u1;
+    one_plus_erf2<false>(x0 * 0.70710678118654752440f, x1 * 0.70710678118654752440f, o0, o1, u0, u1);
+    upk2(mul2(mul2(pk2(x0, x1), pk2(0.5f, 0.5f)), pk2(o0, o1)), g0, g1);
+}
+__device__ __forceinline__ void gelu_erf_grad2(float x0, float x1, float& g0, float& g1) {
+    float o0, o1, e0, e1;
+    one_plus_erf2<true>(x0 * 0.70710678118654752440f, x1 * 0.70710678118654752440f, o0, o1, e0, e1);
+    // cdf + x * pdf = 0.5 (1 + erf) + x * exp(-x^2/2) / sqrt(2 pi)
+    upk2(fma2(mul2(pk2(x0, x1), pk2(0.39894228040143267794f, 0.39894228040143267794f)), pk2(e0, e1),
+              mul2(pk2(o0, o1), pk2(0.5f, 0.5f))), g0, g1);
+}
+
 // CLIP's QuickGELU: x * sigmoid(1.702 x)
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {

@@ -65,9 +65,17 @@ class GraphedTrainStep:
     ``step(x, labels)`` copies the batch into the static buffers (device->device or pinned-host->device, on the
     current stream), replays the graph and returns the static loss tensor (fp32 scalar, on the device)."""
 
-    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2):
+    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, process_group: Any = None):
         if not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs ArenaAdam(capturable=True)")
+        import torch.distributed as dist
+
+        # data parallel: the graph holds zero_grad + forward + loss + backward; the gradient mean (one NCCL all-reduce of
+        # the flat arena) and Adam run right after each replay.  (Capturing NCCL inside the graph hung on this stack.)
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.group = process_group
+        if self.world > 1 and model.engine.reducer is not None:
+            raise ValueError("detach the bucket reducer (model.engine.reducer = None) before graphing the DP step")
         g = model.geo
         dev = model.arena.flat.device
         self.model, self.optimizer = model, optimizer
@@ -93,11 +101,17 @@ class GraphedTrainStep:
     def _eager(self) -> None:
         self.optimizer.zero_grad()
         loss = self.model.train_step(self.x, self.labels)
-        self.optimizer.step()
+        if self.world == 1:
+            self.optimizer.step()
         self.loss.copy_(loss)
 
     def step(self, x: Tensor, labels: Tensor) -> Tensor:
         self.x.copy_(x, non_blocking=True)
         self.labels.copy_(labels.reshape(self.labels.shape), non_blocking=True)
         self.graph.replay()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.model.arena.grad, op=dist.ReduceOp.AVG, group=self.group)
+            self.optimizer.step()
         return self.loss

@@ -219,12 +219,16 @@ def test_gemm_multicast_matches_unicast(M, N, K, a_mn, b_mn):
     old = _cabi.lib().b200_set_gemm_multicast(0)
     try:
         uni = ops.gemm(a_arg, b_arg, a_mn_major=a_mn, b_mn_major=b_mn)
-        _cabi.lib().b200_set_gemm_multicast(1)
+        _cabi.lib().b200_set_gemm_multicast(1)  # CTA pairs, TMA multicast of B, one 128x256 MMA per CTA
         multi = ops.gemm(a_arg, b_arg, a_mn_major=a_mn, b_mn_major=b_mn)
+        _cabi.lib().b200_set_gemm_multicast(2)  # CTA pairs, tcgen05 cta_group::2: one 256x256 MMA per pair
+        two_sm = ops.gemm(a_arg, b_arg, a_mn_major=a_mn, b_mn_major=b_mn)
         torch.cuda.synchronize()
     finally:
         _cabi.lib().b200_set_gemm_multicast(old)
     assert torch.equal(uni, multi)
+    _assert_bf16_close(two_sm, a.float() @ b.float().t(), "gemm cta_group::2")
+    assert torch.equal(uni, two_sm)
     _assert_bf16_close(multi, a.float() @ b.float().t(), "gemm multicast")
 
 
