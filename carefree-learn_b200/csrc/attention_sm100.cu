@@ -89,6 +89,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(bar_p, 256);
             mbar_init(bar_o, 1);
             fence_mbar_init();
+            // issue the loads right away: they overlap the TMEM allocation and the CTA-wide sync below
+            mbar_expect_tx(bar_load, 16384u + 2u * static_cast<uint32_t>(p.tp) * 128u);
+            tma_load_3d(sQ, &tmQ, bar_load, h * 64, mt * 128, b);
+            tma_load_3d(sK, &tmKV, bar_load, p.D + h * 64, 0, b);
+            tma_load_3d(sV, &tmKV, bar_load, 2 * p.D + h * 64, 0, b);
         }
         __syncwarp();
         tmem_alloc(tmem_ptr_smem, 256);
@@ -101,10 +106,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (warp == 8) {
         if (elect_one()) {
-            mbar_expect_tx(bar_load, 16384u + 2u * static_cast<uint32_t>(p.tp) * 128u);
-            tma_load_3d(sQ, &tmQ, bar_load, h * 64, mt * 128, b);
-            tma_load_3d(sK, &tmKV, bar_load, p.D + h * 64, 0, b);
-            tma_load_3d(sV, &tmKV, bar_load, 2 * p.D + h * 64, 0, b);
             mbar_wait(bar_load, 0);
             tc_fence_after_sync();
             const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(p.tp), 0, 0);
@@ -308,6 +309,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             mbar_init(bar_kv, 1);
             mbar_init(bar_kvfree, 256);
             fence_mbar_init();
+            // issue the first loads right away: they overlap the TMEM allocation and the delta prologue of the other warps
+            mbar_expect_tx(bar_qdo, static_cast<uint32_t>(n_mt) * 2u * 16384u);
+            for (int mt = 0; mt < n_mt; ++mt) {
+                tma_load_3d(sQ + mt * 16384, &tmQKV, bar_qdo, h * 64, mt * 128, b);
+                tma_load_3d(sDO + mt * 16384, &tmDO, bar_qdo, h * 64, mt * 128, b);
+            }
+            mbar_expect_tx(bar_kvload, 2u * 16384u);
+            tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, 0, b);
+            tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, 0, b);
         }
         __syncwarp();
         tmem_alloc(tmem_ptr_smem, 512);
@@ -337,21 +347,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 8) {
         if (elect_one()) {
-            mbar_expect_tx(bar_qdo, static_cast<uint32_t>(n_mt) * 2u * 16384u);
-            for (int mt = 0; mt < n_mt; ++mt) {
-                tma_load_3d(sQ + mt * 16384, &tmQKV, bar_qdo, h * 64, mt * 128, b);
-                tma_load_3d(sDO + mt * 16384, &tmDO, bar_qdo, h * 64, mt * 128, b);
-            }
             const uint32_t idesc_nn = make_idesc_bf16(128, 128, 0, 0);  // S, dP   : A K-major,  B K-major
             const uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);   // dV, dK  : A MN-major, B MN-major
             const uint32_t idesc_nt = make_idesc_bf16(128, 64, 0, 1);   // dQ      : A K-major,  B MN-major
             const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
             uint32_t it = 0;
             for (int kt = 0; kt < n_kt; ++kt) {
-                if (kt > 0) mbar_wait(bar_kv, static_cast<uint32_t>(kt - 1) & 1u);  // MMAs reading sK / sV retired
-                mbar_expect_tx(bar_kvload, 2u * 16384u);
-                tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, kt * 128, b);
-                tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, kt * 128, b);
+                if (kt > 0) {  // (key tile 0 was requested before the CTA-wide sync)
+                    mbar_wait(bar_kv, static_cast<uint32_t>(kt - 1) & 1u);  // MMAs reading sK / sV retired
+                    mbar_expect_tx(bar_kvload, 2u * 16384u);
+                    tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, kt * 128, b);
+                    tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, kt * 128, b);
+                }
                 if (kt == 0) mbar_wait(bar_qdo, 0);
                 mbar_wait(bar_kvload, static_cast<uint32_t>(kt) & 1u);
                 tc_fence_after_sync();

@@ -51,6 +51,10 @@ struct GemmParams {
     int two_sm;      // cluster == 2 only.  0: each CTA runs its own 128x256 MMA, the B tile is TMA-multicast to both;
                      //                     1: tcgen05 cta_group::2 -- ONE 256x256 MMA per pair, each CTA holds HALF of B
     const __nv_bfloat16* bias;  // [N] bf16 or nullptr
+    void* out0;                 // epilogue outputs / aux operand: plain pointers, leading dimension ldo (elements)
+    void* out1;
+    const void* aux;
+    long long ldo;
 };
 
 // Work unit u (per cluster) -> (m tile of THIS CTA, n tile, split, k-block range).  With cluster == 2 the two CTAs of
@@ -73,12 +77,12 @@ __device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {  /
     return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
 }
 
-template <int EPI>
+// TWO_SM is a template parameter (not a runtime flag): a kernel image that contains cta_group::2 instructions can only
+// be launched with a cluster size of 2, so the 1-CTA / multicast variants must be separate instantiations.
+template <int EPI, bool TWO_SM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmOut1,
-                 const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmAuxPf,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmAuxPf, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem + SMEM_A_OFF;
@@ -103,23 +107,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        tma_prefetch_desc(&tmOut0);
-        if (EPI == EPI_BIAS_GELU_BF16) tma_prefetch_desc(&tmOut1);
-        if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAux);
+        if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAuxPf);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             // multicast mode: released by the MMA warp of EVERY CTA in the cluster; 2-SM mode: by the leader's commit
-            mbar_init(&empty_bar[i], p.two_sm ? 1u : static_cast<uint32_t>(p.cluster));
+            mbar_init(&empty_bar[i], TWO_SM ? 1u : static_cast<uint32_t>(p.cluster));
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], p.two_sm ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // 2-SM: both CTAs' epilogues report to the leader
+            mbar_init(&tmem_empty_bar[i], TWO_SM ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // 2-SM: both CTAs' epilogues report to the leader
         }
-        for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        if (p.two_sm) {  // pair allocation: the same warp of both CTAs, same destination offset
+        if constexpr (TWO_SM) {  // pair allocation: the same warp of both CTAs, same destination offset
             tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
             tmem_relinquish_2sm();
         } else {
@@ -151,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                     uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
-                    if (p.two_sm) {
+                    if constexpr (TWO_SM) {
                         // cta_group::2: every load of BOTH CTAs is credited to the LEADER's full barrier, which the
                         // leader arms once with the bytes of the whole pair (2 x (A 16 KB + half B 16 KB)).
                         const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -209,8 +210,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (elect_one() && (!p.two_sm || cta_rank == 0)) {  // 2-SM mode: only the pair leader issues MMAs
-            const uint32_t idesc = make_idesc_bf16(p.two_sm ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
+        if (elect_one() && (!TWO_SM || cta_rank == 0)) {  // 2-SM mode: only the pair leader issues MMAs
+            const uint32_t idesc = make_idesc_bf16(TWO_SM ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
             int stage = 0;
             uint32_t phase = 0;
             int lt = 0;
@@ -236,29 +237,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                       : make_smem_desc(a_base + kk * 32, 0, 1024, kSwz128);
                         const uint64_t bdesc = p.b_mn ? make_smem_desc(b_base + kk * 2048, MN_BOX_BYTES, 1024, kSwz128)
                                                       : make_smem_desc(b_base + kk * 32, 0, 1024, kSwz128);
-                        if (p.two_sm) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        if constexpr (TWO_SM) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                         else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
                     // smem slot reusable once these MMAs retire; with multicast the slot is also written by the peer's
                     // TMA, so the release goes to the empty barrier of both CTAs
-                    if (p.two_sm) umma_commit_2sm_mcast(&empty_bar[stage], mc_mask);
-                    else if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
-                    else umma_commit(&empty_bar[stage]);
+                    if constexpr (TWO_SM) {
+                        umma_commit_2sm_mcast(&empty_bar[stage], mc_mask);
+                    } else {
+                        if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
+                        else umma_commit(&empty_bar[stage]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 // accumulator complete -> epilogue (2-SM: each CTA's epilogue owns 128 of the 256 accumulator rows)
-                if (p.two_sm) umma_commit_2sm_mcast(&tmem_full_bar[as], mc_mask);
+                if constexpr (TWO_SM) umma_commit_2sm_mcast(&tmem_full_bar[as], mc_mask);
                 else umma_commit(&tmem_full_bar[as]);
             }
         }
     } else {
         // ===================================== epilogue warps ===================================
+        // Each warp owns 32 accumulator rows (its TMEM lane quadrant) x 128 columns, processed in 4 chunks of 32
+        // columns.  Phase 1 (row-per-thread, the tcgen05.ld layout): acc (+bias) -> bf16 (or fp32) -> swizzled staging
+        // smem.  Phase 2 (coalesced layout: 4 lanes x 16 B per 64-byte row segment): staging + aux operand read
+        // straight from global -> fused math -> 16-byte global stores.  No asynchronous store completion is waited on
+        // (the first version used TMA stores and spent ~1 us per chunk in cp.async.bulk.wait_group.read); aux loads are
+        // issued before the TMEM load and were L2-prefetched by the producer warp a whole mainloop earlier.
         const int e = warp - 2;               // 0..7
         const uint32_t q = warp & 3;          // TMEM lane quadrant this warp may access
         const int half = e >> 2;              // which 128-column half of the accumulator
         uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
-        uint64_t* my_aux_bar = &aux_bar[e];
-        uint32_t aux_phase = 0;
+        const long long ldo = p.ldo;
         int lt = 0;
         for (int u = unit0; u < total_units; u += unit_stride, ++lt) {
             int m_t, n_t, sp, kb0, kb1;
@@ -274,20 +283,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int col = half * 128 + c * 32;
                 const int gcol = n_t * BN + col;
                 const bool active = (gcol < p.N) && (grow0 < p.M);  // warp-uniform
-                // staging buffer must have been drained by the TMA store that last used it (bf16 chunks rotate over the
-                // two 2 KB halves, so only the store before the previous one has to be finished)
-                if (lane == 0) {
-                    if constexpr (EPI == EPI_BIAS_BF16) tma_store_wait_read1();
-                    else tma_store_wait_read0();
-                }
-                __syncwarp();
-                uint8_t* const stg_c = (EPI == EPI_BIAS_BF16) ? stg + (c & 1) * 2048 : stg;
-                if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
-                    if (active && lane == 0) {
-                        mbar_expect_tx(my_aux_bar, EPI == EPI_BIAS_RESID_F32 ? 4096u : 2048u);
-                        tma_load_3d(stg, &tmAux, my_aux_bar, gcol, grow0, 0);
+                // phase-2 coordinates of this lane inside a bf16-staged chunk: 4 row groups of 8 rows, 4 lanes per row
+                const int prow = lane >> 2, pch = lane & 3;
+                const int pcol = gcol + pch * 8;
+
+                // ---- aux operand (coalesced layout), requested before the TMEM load so its latency is hidden ----
+                uint4 aux_h[4];       // DGELU : 8 bf16 of h per row group
+                float4 aux_r[4][2];   // RESID : 8 fp32 of the residual per row group
+                if constexpr (EPI == EPI_DGELU_BF16) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = grow0 + it * 8 + prow;
+                        aux_h[it] = make_uint4(0, 0, 0, 0);
+                        if (active && row < p.M && pcol + 8 <= p.N)
+                            aux_h[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pcol);
                     }
                 }
+                if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = grow0 + it * 8 + prow;
+                        aux_r[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        aux_r[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (active && row < p.M && pcol + 8 <= p.N) {
+                            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + row * ldo + pcol);
+                            aux_r[it][0] = src[0];
+                            aux_r[it][1] = src[1];
+                        }
+                    }
+                }
+
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(col), v);
                 tmem_ld_wait();
@@ -295,129 +320,135 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.two_sm) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
                         else mbar_arrive(&tmem_empty_bar[as]);
                     }
                 }
                 if (!active) continue;
 
-                // bias for these 32 columns (bf16, broadcast 16-byte loads; must be readable up to roundup(N, 8))
-                float bv[32];
-                if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
+                if constexpr (EPI == EPI_PARTIAL_F32) {
+                    // ---- fp32 split-K partial: stage 32 x 128 B, then 8 lanes x 16 B per row ----
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4 t = make_uint4(0, 0, 0, 0);
-                        if (p.bias != nullptr && gcol + j8 * 8 < p.N)
-                            t = *reinterpret_cast<const uint4*>(p.bias + gcol + j8 * 8);
-                        bv[j8 * 8 + 0] = bf16lo(t.x); bv[j8 * 8 + 1] = bf16hi(t.x);
-                        bv[j8 * 8 + 2] = bf16lo(t.y); bv[j8 * 8 + 3] = bf16hi(t.y);
-                        bv[j8 * 8 + 4] = bf16lo(t.z); bv[j8 * 8 + 5] = bf16hi(t.z);
-                        bv[j8 * 8 + 6] = bf16lo(t.w); bv[j8 * 8 + 7] = bf16hi(t.w);
-                    }
-                }
-
-                if constexpr (EPI == EPI_BIAS_BF16) {
-                    // out0 = bf16(acc + bias)
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[j4 * 8 + 0]) + bv[j4 * 8 + 0], __uint_as_float(v[j4 * 8 + 1]) + bv[j4 * 8 + 1]);
-                        o.y = pack_bf16x2(__uint_as_float(v[j4 * 8 + 2]) + bv[j4 * 8 + 2], __uint_as_float(v[j4 * 8 + 3]) + bv[j4 * 8 + 3]);
-                        o.z = pack_bf16x2(__uint_as_float(v[j4 * 8 + 4]) + bv[j4 * 8 + 4], __uint_as_float(v[j4 * 8 + 5]) + bv[j4 * 8 + 5]);
-                        o.w = pack_bf16x2(__uint_as_float(v[j4 * 8 + 6]) + bv[j4 * 8 + 6], __uint_as_float(v[j4 * 8 + 7]) + bv[j4 * 8 + 7]);
-                        *reinterpret_cast<uint4*>(stg_c + swz64_off(lane, j4)) = o;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg_c, gcol, grow0, sp);
-                        tma_store_commit();
-                    }
-                } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-                    // out0 = h = bf16(acc + bias);  out1 = bf16(gelu(h))   (GELU sees the ROUNDED h, like eager)
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        uint32_t hp[4], gp[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int j = j4 * 8 + t * 2;
-                            hp[t] = pack_bf16x2(__uint_as_float(v[j]) + bv[j], __uint_as_float(v[j + 1]) + bv[j + 1]);
-                            float g0, g1;
-                            gelu_erf2(bf16lo(hp[t]), bf16hi(hp[t]), g0, g1);
-                            gp[t] = pack_bf16x2(g0, g1);
-                        }
-                        *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                        *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
-                        tma_store_3d(&tmOut1, stg + 2048, gcol, grow0, sp);
-                        tma_store_commit();
-                    }
-                } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                    // out0(fp32) = aux(fp32) + float(bf16(acc + bias))     (aux may alias out0)
-                    mbar_wait(my_aux_bar, aux_phase);
-                    aux_phase ^= 1u;
-#pragma unroll
-                    for (int j8 = 0; j8 < 8; ++j8) {
-                        float4* ptr = reinterpret_cast<float4*>(stg + swz128_off(lane, j8));
-                        float4 r = *ptr;
-                        r.x += bf16_round(__uint_as_float(v[j8 * 4 + 0]) + bv[j8 * 4 + 0]);
-                        r.y += bf16_round(__uint_as_float(v[j8 * 4 + 1]) + bv[j8 * 4 + 1]);
-                        r.z += bf16_round(__uint_as_float(v[j8 * 4 + 2]) + bv[j8 * 4 + 2]);
-                        r.w += bf16_round(__uint_as_float(v[j8 * 4 + 3]) + bv[j8 * 4 + 3]);
-                        *ptr = r;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
-                        tma_store_commit();
-                    }
-                } else if constexpr (EPI == EPI_DGELU_BF16) {
-                    // out0 = bf16( float(bf16(acc)) * gelu'(h) ),  h = aux (bf16)
-                    mbar_wait(my_aux_bar, aux_phase);
-                    aux_phase ^= 1u;
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const uint4 h = *reinterpret_cast<const uint4*>(stg + swz64_off(lane, j4));
-                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-                        uint32_t op[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int j = j4 * 8 + t * 2;
-                            float g0, g1;
-                            gelu_erf_grad2(bf16lo(hw[t]), bf16hi(hw[t]), g0, g1);
-                            const uint32_t dg = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));  // bf16(acc)
-                            op[t] = pack_bf16x2(bf16lo(dg) * g0, bf16hi(dg) * g1);
-                        }
-                        *reinterpret_cast<uint4*>(stg + 2048 + swz64_off(lane, j4)) = make_uint4(op[0], op[1], op[2], op[3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg + 2048, gcol, grow0, sp);
-                        tma_store_commit();
-                    }
-                } else {  // EPI_PARTIAL_F32: out0[sp] = acc (fp32)
-#pragma unroll
-                    for (int j8 = 0; j8 < 8; ++j8) {
+                    for (int j8 = 0; j8 < 8; ++j8)
                         *reinterpret_cast<uint4*>(stg + swz128_off(lane, j8)) =
                             make_uint4(v[j8 * 4 + 0], v[j8 * 4 + 1], v[j8 * 4 + 2], v[j8 * 4 + 3]);
-                    }
-                    fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmOut0, stg, gcol, grow0, sp);
-                        tma_store_commit();
+                    float* out = reinterpret_cast<float*>(p.out0) + static_cast<long long>(sp) * p.M * ldo;
+                    const int frow = lane >> 3, fch = lane & 7;
+                    const int fcol = gcol + fch * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + frow;
+                        const int row = grow0 + r;
+                        const uint4 t = *reinterpret_cast<const uint4*>(stg + swz128_off(r, fch));
+                        if (row < p.M) {
+                            float* dst = out + row * ldo + fcol;
+                            if (fcol + 4 <= p.N) {
+                                *reinterpret_cast<uint4*>(dst) = t;
+                            } else {
+                                const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+                                for (int k = 0; k < 4; ++k)
+                                    if (fcol + k < p.N) dst[k] = __uint_as_float(tt[k]);
+                            }
+                        }
+                    }
+                    __syncwarp();  // staging is rewritten by the next chunk
+                } else {
+                    // ---- phase 1: bf16(acc + bias) -> staging half (c & 1) ----
+                    uint8_t* const sh = stg + (c & 1) * 2048;
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float bv[8];
+                        {
+                            uint4 t = make_uint4(0, 0, 0, 0);
+                            if constexpr (EPI != EPI_DGELU_BF16) {
+                                if (p.bias != nullptr && gcol + j4 * 8 < p.N)
+                                    t = *reinterpret_cast<const uint4*>(p.bias + gcol + j4 * 8);
+                            }
+                            bv[0] = bf16lo(t.x); bv[1] = bf16hi(t.x); bv[2] = bf16lo(t.y); bv[3] = bf16hi(t.y);
+                            bv[4] = bf16lo(t.z); bv[5] = bf16hi(t.z); bv[6] = bf16lo(t.w); bv[7] = bf16hi(t.w);
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j4 * 8 + 0]) + bv[0], __uint_as_float(v[j4 * 8 + 1]) + bv[1]);
+                        o.y = pack_bf16x2(__uint_as_float(v[j4 * 8 + 2]) + bv[2], __uint_as_float(v[j4 * 8 + 3]) + bv[3]);
+                        o.z = pack_bf16x2(__uint_as_float(v[j4 * 8 + 4]) + bv[4], __uint_as_float(v[j4 * 8 + 5]) + bv[5]);
+                        o.w = pack_bf16x2(__uint_as_float(v[j4 * 8 + 6]) + bv[6], __uint_as_float(v[j4 * 8 + 7]) + bv[7]);
+                        *reinterpret_cast<uint4*>(sh + swz64_off(lane, j4)) = o;
+                    }
+                    __syncwarp();  // (the two halves alternate, so one barrier per chunk also covers the WAR hazard)
+                    // ---- phase 2: coalesced layout ----
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + prow;
+                        const int row = grow0 + r;
+                        const uint4 t = *reinterpret_cast<const uint4*>(sh + swz64_off(r, pch));  // 8 x bf16(acc + bias)
+                        if (row >= p.M) continue;
+                        const bool full = pcol + 8 <= p.N;
+                        const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+                        if constexpr (EPI == EPI_BIAS_BF16) {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
+                            if (full) *reinterpret_cast<uint4*>(dst) = t;
+                            else for (int k = 0; k < 8; ++k) if (pcol + k < p.N) dst[k] = __ushort_as_bfloat16(static_cast<unsigned short>(tw[k >> 1] >> ((k & 1) * 16)));
+                        } else if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                            // out0 = h (rounded pre-activation), out1 = bf16(gelu(h)): GELU sees the ROUNDED h, like eager
+                            uint32_t gw[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float g0, g1;
+                                gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                gw[k] = pack_bf16x2(g0, g1);
+                            }
+                            __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
+                            __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + row * ldo + pcol;
+                            if (full) {
+                                *reinterpret_cast<uint4*>(d0) = t;
+                                *reinterpret_cast<uint4*>(d1) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+                            } else {
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) {
+                                        d0[k] = __ushort_as_bfloat16(static_cast<unsigned short>(tw[k >> 1] >> ((k & 1) * 16)));
+                                        d1[k] = __ushort_as_bfloat16(static_cast<unsigned short>(gw[k >> 1] >> ((k & 1) * 16)));
+                                    }
+                            }
+                        } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                            // out0(fp32) = aux(fp32) + float(bf16(acc + bias))     (aux may alias out0)
+                            float* dst = reinterpret_cast<float*>(p.out0) + row * ldo + pcol;
+                            if (full) {
+                                float4 a = aux_r[it][0], b = aux_r[it][1];
+                                a.x += bf16lo(tw[0]); a.y += bf16hi(tw[0]); a.z += bf16lo(tw[1]); a.w += bf16hi(tw[1]);
+                                b.x += bf16lo(tw[2]); b.y += bf16hi(tw[2]); b.z += bf16lo(tw[3]); b.w += bf16hi(tw[3]);
+                                reinterpret_cast<float4*>(dst)[0] = a;
+                                reinterpret_cast<float4*>(dst)[1] = b;
+                            } else {
+                                const float* src = reinterpret_cast<const float*>(p.aux) + row * ldo + pcol;
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) dst[k] = src[k] + ((k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]));
+                            }
+                        } else {  // EPI_DGELU_BF16: out0 = bf16( float(bf16(acc)) * gelu'(h) ),  h = aux (bf16)
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
+                            if (full) {
+                                const uint32_t hw[4] = {aux_h[it].x, aux_h[it].y, aux_h[it].z, aux_h[it].w};
+                                uint32_t ow[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float g0, g1;
+                                    gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
+                                    ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                }
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                            } else {
+                                const __nv_bfloat16* hsrc = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pcol;
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) {
+                                        const float dv = (k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]);
+                                        dst[k] = __float2bfloat16_rn(dv * gelu_erf_grad(__bfloat162float(hsrc[k])));
+                                    }
+                            }
+                        }
                     }
                 }
             }
         }
-        if (lane == 0) tma_store_wait_all0();
-        __syncwarp();
     }
 
     __syncwarp();  // reconverge warps 0 / 1 (only one elected lane ran the role loop): the cluster barrier is .aligned
@@ -426,7 +457,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
-        if (p.two_sm) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        if constexpr (TWO_SM) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
         else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
@@ -499,14 +530,13 @@ int num_sms() {
 
 static int g_gemm_multicast = 1;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2: CTA pairs + cta_group::2 MMA
 
-template <int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& o0,
-                       const CUtensorMap& o1, const CUtensorMap& ax, const CUtensorMap& axpf, const GemmParams& p, int grid,
-                       cudaStream_t stream) {
+template <int EPI, bool TWO_SM>
+static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& axpf,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
     static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
     cudaError_t e;
     if (!configured) {
-        e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+        e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI, TWO_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
         configured = true;
     }
@@ -522,12 +552,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI>, tmA, tmB, tmBh, o0, o1, ax, axpf, p);
+    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, TWO_SM>, tmA, tmB, tmBh, axpf, p);
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     count_launch(1);
     return 0;
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& axpf,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
+    return p.two_sm ? launch_gemm_impl<EPI, true>(tmA, tmB, tmBh, axpf, p, grid, stream)
+                    : launch_gemm_impl<EPI, false>(tmA, tmB, tmBh, axpf, p, grid, stream);
 }
 
 }  // namespace b200
@@ -574,7 +611,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     const int num_kb = (K + BK - 1) / BK;
     if (splits > num_kb) splits = num_kb;
 
-    CUtensorMap tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf;
+    CUtensorMap tmA, tmB, tmBh, tmAxPf;
     int rc;
     {
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
@@ -596,24 +633,20 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     }
     const bool out_f32 = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_PARTIAL_F32);
     {
+        // The epilogue writes with plain 16-byte global stores: rows must start 16-byte aligned.
         const int eb = out_f32 ? 4 : 2;
-        uint64_t d[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), static_cast<uint64_t>(splits)};
-        uint64_t s[2] = {static_cast<uint64_t>(ldo) * eb, static_cast<uint64_t>(ldo) * eb * static_cast<uint64_t>(M)};
-        uint32_t bx[3] = {32, 32, 1};
-        const int swz = out_f32 ? 128 : 64;
-        if ((rc = make_tmap(&tmO0, out0, eb, 3, d, s, bx, swz)) != 0) return rc;
-        tmO1 = tmO0;
-        tmAx = tmO0;
-        tmAxPf = tmO0;
-        if (epilogue == EPI_BIAS_GELU_BF16) {
-            if (out1 == nullptr) return set_error(B200_ERR_ARG, "gemm: GELU epilogue needs out1");
-            if ((rc = make_tmap(&tmO1, out1, eb, 3, d, s, bx, swz)) != 0) return rc;
-        }
+        if ((static_cast<unsigned long long>(ldo) * eb) % 16 != 0) return set_error(B200_ERR_ALIGN, "gemm: ldo rows must be 16-byte aligned");
+        if ((reinterpret_cast<uintptr_t>(out0) & 15u) != 0) return set_error(B200_ERR_ALIGN, "gemm: out0 not 16-byte aligned");
+        if (epilogue == EPI_BIAS_GELU_BF16 && (out1 == nullptr || (reinterpret_cast<uintptr_t>(out1) & 15u) != 0))
+            return set_error(B200_ERR_ARG, "gemm: GELU epilogue needs a 16-byte aligned out1");
+        tmAxPf = tmA;  // placeholder, unused unless there is an aux operand
         if (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_DGELU_BF16) {
-            if (aux == nullptr) return set_error(B200_ERR_ARG, "gemm: epilogue needs aux");
-            if ((rc = make_tmap(&tmAx, aux, eb, 3, d, s, bx, swz)) != 0) return rc;
-            uint32_t bxpf[3] = {static_cast<uint32_t>(BN), static_cast<uint32_t>(BM), 1};  // whole-tile L2 prefetch box
-            if ((rc = make_tmap(&tmAxPf, aux, eb, 3, d, s, bxpf, 0)) != 0) return rc;
+            if (aux == nullptr || (reinterpret_cast<uintptr_t>(aux) & 15u) != 0) return set_error(B200_ERR_ARG, "gemm: epilogue needs a 16-byte aligned aux");
+            // whole-tile box, used only for cp.async.bulk.prefetch.tensor (pull the aux tile into L2 a mainloop ahead)
+            uint64_t d[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
+            uint64_t st[2] = {static_cast<uint64_t>(ldo) * eb, static_cast<uint64_t>(ldo) * eb * static_cast<uint64_t>(M)};
+            uint32_t bxpf[3] = {static_cast<uint32_t>(BN), static_cast<uint32_t>(BM), 1};
+            if ((rc = make_tmap(&tmAxPf, aux, eb, 3, d, st, bxpf, 0)) != 0) return rc;
         }
     }
     GemmParams p;
@@ -625,6 +658,10 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     p.a_mn = a_mn_major ? 1 : 0;
     p.b_mn = b_mn_major ? 1 : 0;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.out0 = out0;
+    p.out1 = out1;
+    p.aux = aux;
+    p.ldo = ldo;
     p.cluster = (g_gemm_multicast && max_ctas != 1) ? 2 : 1;
     p.two_sm = (p.cluster == 2 && g_gemm_multicast == 2) ? 1 : 0;
     const long long units = static_cast<long long>((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * splits;
@@ -635,11 +672,11 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     if (units < nclusters) nclusters = static_cast<int>(units);
     grid = nclusters * p.cluster;
     switch (epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
-        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
-        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
-        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmO0, tmO1, tmAx, tmAxPf, p, grid, stream);
+        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
+        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
+        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
+        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
         default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
     }
 }
