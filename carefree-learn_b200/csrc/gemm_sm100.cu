@@ -278,8 +278,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tmem_full_bar[as], aph);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(as * BN);
-#pragma unroll 1
+            // The accumulator buffer can only be handed back to the MMA warp once it has been READ completely, and
+            // MMA(i+2) waits for that.  So the TMEM reads run two chunks ahead of the processing (register ping-pong
+            // va / vb): the buffer is released after chunk 1 instead of after chunk 3, i.e. after about half of the
+            // epilogue -- otherwise a K = 768 tile (3.6 us of MMA) stalls behind a ~6 us serial epilogue.
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 128), va);
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 128 + 32), vb);
+            tmem_ld_wait();
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
+                uint32_t (&v)[32] = (c & 1) ? vb : va;
                 const int col = half * 128 + c * 32;
                 const int gcol = n_t * BN + col;
                 const bool active = (gcol < p.N) && (grow0 < p.M);  // warp-uniform
@@ -313,18 +322,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
 
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(col), v);
-                tmem_ld_wait();
-                if (c == 3) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
-                        else mbar_arrive(&tmem_empty_bar[as]);
-                    }
-                }
-                if (!active) continue;
+                if (active) {
 
                 if constexpr (EPI == EPI_PARTIAL_F32) {
                     // ---- fp32 split-K partial: stage 32 x 128 B, then 8 lanes x 16 B per row ----
@@ -445,6 +443,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     }
                             }
                         }
+                    }
+                }
+                }  // if (active)
+                // ---- refill the register set just consumed with the chunk two ahead; release TMEM after chunk 1 ----
+                if (c + 2 < 4) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 128 + (c + 2) * 32), v);
+                if (c == 1) {
+                    tmem_ld_wait();  // chunks 2 and 3 are now in registers: the accumulator has been read completely
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        else mbar_arrive(&tmem_empty_bar[as]);
                     }
                 }
             }
