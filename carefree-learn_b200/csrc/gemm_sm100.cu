@@ -143,11 +143,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int m_t, n_t, sp, kb0, kb1;
                 decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
                 const int m0 = m_t * BM, n0 = n_t * BN;
-                if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
-                    // the epilogue will TMA-load this tile of the residual / pre-activation: start pulling it into L2
-                    // now, a whole mainloop ahead, so those loads see L2 (not HBM) latency
-                    if (m0 < p.M && n0 < p.N) tma_prefetch_l2_3d(&tmAuxPf, n0, m0, 0);
-                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
@@ -275,13 +270,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1u;
             const int grow0 = m_t * BM + static_cast<int>(q) * 32;
-            mbar_wait(&tmem_full_bar[as], aph);
-            tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(as * BN);
             // The accumulator buffer can only be handed back to the MMA warp once it has been READ completely, and
             // MMA(i+2) waits for that.  So the TMEM reads run two chunks ahead of the processing (register ping-pong
             // va / vb): the buffer is released after chunk 1 instead of after chunk 3, i.e. after about half of the
             // epilogue -- otherwise a K = 768 tile (3.6 us of MMA) stalls behind a ~6 us serial epilogue.
+            // aux operand (residual / pre-activation) in the coalesced phase-2 layout, requested one chunk ahead; the first
+            // chunk's loads are issued BEFORE the accumulator is ready, so their HBM latency hides behind the mainloop
+            uint4 aux_h[2][4];      // DGELU : 8 bf16 of h per row group
+            float4 aux_r[2][4][2];  // RESID : 8 fp32 of the residual per row group
+            auto load_aux = [&](int cc, int slot) {
+                const int gc = n_t * BN + half * 128 + cc * 32;
+                const int pc = gc + (lane & 3) * 8;
+                const bool act = (gc < p.N) && (grow0 < p.M);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = grow0 + it * 8 + (lane >> 2);
+                    const bool ok = act && row < p.M && pc + 8 <= p.N;
+                    if constexpr (EPI == EPI_DGELU_BF16) {
+                        aux_h[slot][it] = make_uint4(0, 0, 0, 0);
+                        if (ok) aux_h[slot][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pc);
+                    }
+                    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                        aux_r[slot][it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        aux_r[slot][it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) {
+                            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + row * ldo + pc);
+                            aux_r[slot][it][0] = src[0];
+                            aux_r[slot][it][1] = src[1];
+                        }
+                    }
+                }
+            };
+            if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) load_aux(0, 0);
+            mbar_wait(&tmem_full_bar[as], aph);
+            tc_fence_after_sync();
             uint32_t va[32], vb[32];
             tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 128), va);
             tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(half * 128 + 32), vb);
@@ -296,32 +319,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int prow = lane >> 2, pch = lane & 3;
                 const int pcol = gcol + pch * 8;
 
-                // ---- aux operand (coalesced layout), requested before the TMEM load so its latency is hidden ----
-                uint4 aux_h[4];       // DGELU : 8 bf16 of h per row group
-                float4 aux_r[4][2];   // RESID : 8 fp32 of the residual per row group
-                if constexpr (EPI == EPI_DGELU_BF16) {
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int row = grow0 + it * 8 + prow;
-                        aux_h[it] = make_uint4(0, 0, 0, 0);
-                        if (active && row < p.M && pcol + 8 <= p.N)
-                            aux_h[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pcol);
-                    }
+                if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) {
+                    if (c + 1 < 4) load_aux(c + 1, (c + 1) & 1);
                 }
-                if constexpr (EPI == EPI_BIAS_RESID_F32) {
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int row = grow0 + it * 8 + prow;
-                        aux_r[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        aux_r[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (active && row < p.M && pcol + 8 <= p.N) {
-                            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + row * ldo + pcol);
-                            aux_r[it][0] = src[0];
-                            aux_r[it][1] = src[1];
-                        }
-                    }
-                }
-
                 if (active) {
 
                 if constexpr (EPI == EPI_PARTIAL_F32) {
@@ -412,7 +412,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             // out0(fp32) = aux(fp32) + float(bf16(acc + bias))     (aux may alias out0)
                             float* dst = reinterpret_cast<float*>(p.out0) + row * ldo + pcol;
                             if (full) {
-                                float4 a = aux_r[it][0], b = aux_r[it][1];
+                                float4 a = aux_r[c & 1][it][0], b = aux_r[c & 1][it][1];
                                 a.x += bf16lo(tw[0]); a.y += bf16hi(tw[0]); a.z += bf16lo(tw[1]); a.w += bf16hi(tw[1]);
                                 b.x += bf16lo(tw[2]); b.y += bf16hi(tw[2]); b.z += bf16lo(tw[3]); b.w += bf16hi(tw[3]);
                                 reinterpret_cast<float4*>(dst)[0] = a;
@@ -425,7 +425,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         } else {  // EPI_DGELU_BF16: out0 = bf16( float(bf16(acc)) * gelu'(h) ),  h = aux (bf16)
                             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
                             if (full) {
-                                const uint32_t hw[4] = {aux_h[it].x, aux_h[it].y, aux_h[it].z, aux_h[it].w};
+                                const uint32_t hw[4] = {aux_h[c & 1][it].x, aux_h[c & 1][it].y, aux_h[c & 1][it].z, aux_h[c & 1][it].w};
                                 uint32_t ow[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {

@@ -380,48 +380,40 @@ __device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-// (1 + erf(z0)), (1 + erf(z1)); optionally also exp(-z^2) for both (needed by the derivative)
-template <bool kWantExp>
-__device__ __forceinline__ void one_plus_erf2(float z0, float z1, float& o0, float& o1, float& e0, float& e1) {
-    const float a0 = fabsf(z0), a1 = fabsf(z1);
-    const f32x2_t az = pk2(a0, a1);
+// w = erfc(|x| / sqrt 2) for two values, ax = |x|, x2 = x^2 (packed).  erfc(z) = t exp(-z^2 + P(t)), t = 1 / (1 + z / 2):
+// degree-6 minimax fit of P (max relative error 5.6e-6 in fp32), coefficients pre-multiplied by log2(e).
+__device__ __forceinline__ void erfc_abs2(float x0, float x1, f32x2_t& w, f32x2_t& ax, f32x2_t& x2) {
+    ax = pk2(fabsf(x0), fabsf(x1));
     float d0, d1;
-    upk2(fma2(az, pk2(0.5f, 0.5f), pk2(1.0f, 1.0f)), d0, d1);
+    upk2(fma2(ax, pk2(0.35355339059327373f, 0.35355339059327373f), pk2(1.0f, 1.0f)), d0, d1);  // 1 + |x| / (2 sqrt 2)
     const f32x2_t t = pk2(fast_rcp(d0), fast_rcp(d1));
-    f32x2_t p = fma2(pk2(0.17087277f, 0.17087277f), t, pk2(-0.82215223f, -0.82215223f));
-    p = fma2(p, t, pk2(1.48851587f, 1.48851587f));
-    p = fma2(p, t, pk2(-1.13520398f, -1.13520398f));
-    p = fma2(p, t, pk2(0.27886807f, 0.27886807f));
-    p = fma2(p, t, pk2(-0.18628806f, -0.18628806f));
-    p = fma2(p, t, pk2(0.09678418f, 0.09678418f));
-    p = fma2(p, t, pk2(0.37409196f, 0.37409196f));
-    p = fma2(p, t, pk2(1.00002368f, 1.00002368f));
-    p = fma2(p, t, pk2(-1.26551223f, -1.26551223f));
-    const f32x2_t nz2 = mul2(pk2(-a0, -a1), az);  // -z^2
+    constexpr float kL = 1.4426950408889634f;
+    f32x2_t p = fma2(pk2(-0.0630452529f * kL, -0.0630452529f * kL), t, pk2(0.465173551f * kL, 0.465173551f * kL));
+    p = fma2(p, t, pk2(-1.06472952f * kL, -1.06472952f * kL));
+    p = fma2(p, t, pk2(0.747652742f * kL, 0.747652742f * kL));
+    p = fma2(p, t, pk2(0.14202046f * kL, 0.14202046f * kL));
+    p = fma2(p, t, pk2(1.04137768f * kL, 1.04137768f * kL));
+    p = fma2(p, t, pk2(-1.26844758f * kL, -1.26844758f * kL));
+    x2 = mul2(ax, ax);
     float g0, g1;
-    upk2(mul2(fma2(p, pk2(1.0f, 1.0f), nz2), pk2(1.4426950408889634f, 1.4426950408889634f)), g0, g1);
-    float w0, w1;
-    upk2(mul2(t, pk2(fast_ex2(g0), fast_ex2(g1))), w0, w1);
-    o0 = z0 >= 0.f ? 2.0f - w0 : w0;
-    o1 = z1 >= 0.f ? 2.0f - w1 : w1;
-    if (kWantExp) {
-        float n0, n1;
-        upk2(mul2(nz2, pk2(1.4426950408889634f, 1.4426950408889634f)), n0, n1);
-        e0 = fast_ex2(n0);
-        e1 = fast_ex2(n1);
-    }
+    upk2(fma2(x2, pk2(-0.5f * kL, -0.5f * kL), p), g0, g1);  // (-x^2/2 + P(t)) log2 e
+    w = mul2(t, pk2(fast_ex2(g0), fast_ex2(g1)));
 }
+// gelu(x) = x Phi(x) = relu(x) - |x| erfc(|x| / sqrt 2) / 2   (exact identity; no sign-dependent select)
 __device__ __forceinline__ void gelu_erf2(float x0, float x1, float& g0, float& g1) {
-    float o0, o1, u0, u1;
-    one_plus_erf2<false>(x0 * 0.70710678118654752440f, x1 * 0.70710678118654752440f, o0, o1, u0, u1);
-    upk2(mul2(mul2(pk2(x0, x1), pk2(0.5f, 0.5f)), pk2(o0, o1)), g0, g1);
+    f32x2_t w, ax, x2;
+    erfc_abs2(x0, x1, w, ax, x2);
+    upk2(fma2(mul2(ax, w), pk2(-0.5f, -0.5f), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), g0, g1);
 }
+// gelu'(x) = Phi(x) + x phi(x),  Phi(x) = 1/2 + sign(x) (1/2 - erfc(|x| / sqrt 2) / 2),  phi(x) = exp(-x^2/2) / sqrt(2 pi)
 __device__ __forceinline__ void gelu_erf_grad2(float x0, float x1, float& g0, float& g1) {
-    float o0, o1, e0, e1;
-    one_plus_erf2<true>(x0 * 0.70710678118654752440f, x1 * 0.70710678118654752440f, o0, o1, e0, e1);
-    // cdf + x * pdf = 0.5 (1 + erf) + x * exp(-x^2/2) / sqrt(2 pi)
-    upk2(fma2(mul2(pk2(x0, x1), pk2(0.39894228040143267794f, 0.39894228040143267794f)), pk2(e0, e1),
-              mul2(pk2(o0, o1), pk2(0.5f, 0.5f))), g0, g1);
+    f32x2_t w, ax, x2;
+    erfc_abs2(x0, x1, w, ax, x2);
+    float h0, h1, n0, n1;
+    upk2(fma2(w, pk2(-0.5f, -0.5f), pk2(0.5f, 0.5f)), h0, h1);
+    upk2(mul2(x2, pk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), n0, n1);
+    const f32x2_t phi = pk2(0.5f + copysignf(h0, x0), 0.5f + copysignf(h1, x1));
+    upk2(fma2(mul2(pk2(x0, x1), pk2(0.39894228040143267794f, 0.39894228040143267794f)), pk2(fast_ex2(n0), fast_ex2(n1)), phi), g0, g1);
 }
 
 // CLIP's QuickGELU: x * sigmoid(1.702 x)
