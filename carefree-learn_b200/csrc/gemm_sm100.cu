@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages of 48 KB)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma 128x256x16)
-//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused epilogue -> swizzled smem -> TMA store)
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> fused math -> coalesced 16-byte
+//                 global stores; aux operands by coalesced global loads issued one chunk ahead)
 //
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
@@ -82,7 +83,7 @@ __device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {  /
 template <int EPI, bool TWO_SM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmAuxPf, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmBh, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem + SMEM_A_OFF;
@@ -92,8 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint64_t* aux_bar = tmem_empty_bar + 2;  // [NUM_EPI_WARPS]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + NUM_EPI_WARPS);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -107,7 +107,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) tma_prefetch_desc(&tmAuxPf);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             // multicast mode: released by the MMA warp of EVERY CTA in the cluster; 2-SM mode: by the leader's commit
@@ -541,7 +540,7 @@ int num_sms() {
 static int g_gemm_multicast = 1;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2: CTA pairs + cta_group::2 MMA
 
 template <int EPI, bool TWO_SM>
-static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& axpf,
+static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
                        const GemmParams& p, int grid, cudaStream_t stream) {
     static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
     cudaError_t e;
@@ -562,7 +561,7 @@ static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, TWO_SM>, tmA, tmB, tmBh, axpf, p);
+    e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, TWO_SM>, tmA, tmB, tmBh, p);
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
@@ -571,10 +570,10 @@ static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh, const CUtensorMap& axpf,
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
                        const GemmParams& p, int grid, cudaStream_t stream) {
-    return p.two_sm ? launch_gemm_impl<EPI, true>(tmA, tmB, tmBh, axpf, p, grid, stream)
-                    : launch_gemm_impl<EPI, false>(tmA, tmB, tmBh, axpf, p, grid, stream);
+    return p.two_sm ? launch_gemm_impl<EPI, true>(tmA, tmB, tmBh, p, grid, stream)
+                    : launch_gemm_impl<EPI, false>(tmA, tmB, tmBh, p, grid, stream);
 }
 
 }  // namespace b200
@@ -621,7 +620,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     const int num_kb = (K + BK - 1) / BK;
     if (splits > num_kb) splits = num_kb;
 
-    CUtensorMap tmA, tmB, tmBh, tmAxPf;
+    CUtensorMap tmA, tmB, tmBh;
     int rc;
     {
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
@@ -649,15 +648,9 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         if ((reinterpret_cast<uintptr_t>(out0) & 15u) != 0) return set_error(B200_ERR_ALIGN, "gemm: out0 not 16-byte aligned");
         if (epilogue == EPI_BIAS_GELU_BF16 && (out1 == nullptr || (reinterpret_cast<uintptr_t>(out1) & 15u) != 0))
             return set_error(B200_ERR_ARG, "gemm: GELU epilogue needs a 16-byte aligned out1");
-        tmAxPf = tmA;  // placeholder, unused unless there is an aux operand
-        if (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_DGELU_BF16) {
-            if (aux == nullptr || (reinterpret_cast<uintptr_t>(aux) & 15u) != 0) return set_error(B200_ERR_ARG, "gemm: epilogue needs a 16-byte aligned aux");
-            // whole-tile box, used only for cp.async.bulk.prefetch.tensor (pull the aux tile into L2 a mainloop ahead)
-            uint64_t d[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
-            uint64_t st[2] = {static_cast<uint64_t>(ldo) * eb, static_cast<uint64_t>(ldo) * eb * static_cast<uint64_t>(M)};
-            uint32_t bxpf[3] = {static_cast<uint32_t>(BN), static_cast<uint32_t>(BM), 1};
-            if ((rc = make_tmap(&tmAxPf, aux, eb, 3, d, st, bxpf, 0)) != 0) return rc;
-        }
+        if ((epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_DGELU_BF16) &&
+            (aux == nullptr || (reinterpret_cast<uintptr_t>(aux) & 15u) != 0))
+            return set_error(B200_ERR_ARG, "gemm: epilogue needs a 16-byte aligned aux");
     }
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
@@ -682,11 +675,11 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     if (units < nclusters) nclusters = static_cast<int>(units);
     grid = nclusters * p.cluster;
     switch (epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
-        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
-        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
-        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, tmAxPf, p, grid, stream);
+        case EPI_BIAS_BF16: return launch_gemm<EPI_BIAS_BF16>(tmA, tmB, tmBh, p, grid, stream);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<EPI_BIAS_GELU_BF16>(tmA, tmB, tmBh, p, grid, stream);
+        case EPI_BIAS_RESID_F32: return launch_gemm<EPI_BIAS_RESID_F32>(tmA, tmB, tmBh, p, grid, stream);
+        case EPI_DGELU_BF16: return launch_gemm<EPI_DGELU_BF16>(tmA, tmB, tmBh, p, grid, stream);
+        case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, p, grid, stream);
         default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
     }
 }
