@@ -176,3 +176,46 @@ def test_gradient_accumulation_and_adam_step():
     assert all(p.grad is None for p in m.parameters())
     m.train_step(x, y)
     assert all(p.grad is not None for p in m.parameters())
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """CUDA-graphed zero_grad + fwd + CE + bwd + Adam == the same three steps launched eagerly (same kernels)."""
+    from cflearn_b200.optim import ArenaAdam, GraphedTrainStep
+
+    cfg = vo.vit_config("vit_tiny")
+    sd = vo.init_state_dict(cfg, seed=0)
+    xs = [vo.synthetic_batch(cfg, 4, seed=s) for s in (1, 2, 3)]
+    eager = build(cfg, sd)
+    opt_e = ArenaAdam(eager, lr=1e-3)
+    losses_e = []
+    for x, y in xs:
+        opt_e.zero_grad()
+        losses_e.append(eager.train_step(x.to(DEV), y.to(DEV)).item())
+        opt_e.step()
+    graphed = build(cfg, sd)
+    graphed.arena.ensure()
+    opt_g = ArenaAdam(graphed, lr=1e-3, capturable=True)
+    # capture runs warm-up steps on the static (zero) batch: undo their effect so both models start identically
+    gs = GraphedTrainStep(graphed, opt_g, batch=4, warmup=1)
+    graphed.load_state_dict(sd)
+    opt_g.exp_avg.zero_()
+    opt_g.exp_avg_sq.zero_()
+    opt_g.step_dev.zero_()
+    losses_g = [gs.step(x.to(DEV), y.to(DEV)).item() for x, y in xs]
+    torch.cuda.synchronize()
+    assert gs.launches_per_replay > 50
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (losses_e, losses_g)
+    for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_bucketed_allreduce_matches_single_process():
+    import subprocess
+
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")],
+        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "dp_check: world 2" in res.stdout, res.stdout[-2000:]
