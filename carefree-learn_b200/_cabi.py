@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 from typing import Any, Callable, Dict, List, Optional
 
 LIB_NAME = "libb200_cflearn.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# B200_LIB_PATH: load another BUILD of the same library (A/B timing of two kernel versions on one box); never a fallback
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class B200Error(RuntimeError):

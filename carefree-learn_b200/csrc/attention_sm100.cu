@@ -36,6 +36,49 @@ namespace b200 {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// Writes this warp's 32 accumulator rows (TMEM lane == row, NCH chunks of 16 fp32 columns starting at `taddr`) to
+// global memory as bf16, scaled by `sc`.  A row-per-thread store would touch 32 different 128-byte lines per
+// instruction; instead the rows are transposed through a warp-private staging area (NCH * 1 KB, 16-byte chunks
+// XOR-swizzled so both passes are bank-conflict free) and written with whole rows per group of lanes.
+// `g0` addresses (row 0, first column); rows >= rows_valid are skipped.
+template <int NCH>
+__device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, __nv_bfloat16* g0, long long row_stride, uint32_t taddr,
+                                                     float sc, int rows_valid, int lane) {
+    constexpr int CPR = NCH * 2;    // 16-byte chunks per row
+    constexpr int RB = NCH * 32;    // bytes per row
+    constexpr int RPI = 32 / CPR;   // rows written per store instruction
+    const uint32_t ul = static_cast<uint32_t>(lane);
+    const uint32_t sw = NCH == 4 ? (ul & 7u) : ((ul >> 1) & 3u);
+    uint8_t* mine = stage + lane * RB;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+        tmem_ld_wait();
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+        o0.y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+        o0.z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+        o0.w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+        o1.x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+        o1.y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+        o1.z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+        o1.w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c) ^ sw) << 4)) = o0;
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c + 1) ^ sw) << 4)) = o1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+        const int row = it * RPI + lane / CPR;
+        const uint32_t ch = ul % CPR;
+        const uint32_t rsw = NCH == 4 ? (static_cast<uint32_t>(row) & 7u) : ((static_cast<uint32_t>(row) >> 1) & 3u);
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * RB + ((ch ^ rsw) << 4));
+        if (row < rows_valid) *reinterpret_cast<uint4*>(g0 + row * row_stride + ch * 8) = val;
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -198,26 +241,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after_sync();
         const float inv = 1.0f / sum;
         const bool valid = i < p.T;
-        __nv_bfloat16* orow = out + (static_cast<long long>(b) * p.T + i) * p.D + h * 64;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {  // each half writes 32 of the 64 output columns
-            const int c = half * 2 + cc;
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
-            tmem_ld_wait();
-            if (valid) {
-                uint4 o0, o1;
-                o0.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-                o0.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-                o0.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-                o0.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-                o1.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
-                o1.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
-                o1.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
-                o1.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
-                reinterpret_cast<uint4*>(orow + c * 16)[0] = o0;
-                reinterpret_cast<uint4*>(orow + c * 16)[1] = o1;
-            }
+        {
+            // every MMA reading sQ / sK / sP has retired (bar_o): the front of the buffer is free for staging
+            const int row0 = mt * 128 + static_cast<int>(q) * 32;
+            __nv_bfloat16* g0 = out + (static_cast<long long>(b) * p.T + row0) * p.D + h * 64 + half * 32;
+            store_rows_coalesced<2>(smem + warp * 2048, g0, p.D, taddr + static_cast<uint32_t>(half * 32), inv, p.T - row0, lane);
         }
         if (valid && half == 0) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
     }
@@ -246,28 +274,6 @@ constexpr int AB_SMEM = AB_BAR + 128 + 1024;
 
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DK = 256, TM_DV = 320, TM_DQ = 384;
 
-__device__ __forceinline__ void store_row64_scaled(__nv_bfloat16* dst, uint32_t taddr, float sc, bool valid) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
-        tmem_ld_wait();
-        if (valid) {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-            o0.y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-            o0.z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-            o0.w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-            o1.x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-            o1.y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-            o1.z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-            o1.w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
-            reinterpret_cast<uint4*>(dst + c * 16)[0] = o0;
-            reinterpret_cast<uint4*>(dst + c * 16)[1] = o1;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
@@ -284,11 +290,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     float* delta_s = reinterpret_cast<float*>(smem + AB_DELTA);
     uint64_t* bar_qdo = reinterpret_cast<uint64_t*>(smem + AB_BAR);
     uint64_t* bar_kvload = bar_qdo + 1;
-    uint64_t* bar_sdp = bar_qdo + 2;
-    uint64_t* bar_pds = bar_qdo + 3;
-    uint64_t* bar_kv = bar_qdo + 4;
-    uint64_t* bar_kvfree = bar_qdo + 5;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_qdo + 6);
+    uint64_t* bar_s = bar_qdo + 2;     // S of this (key, query) tile pair is in TMEM
+    uint64_t* bar_sdp = bar_qdo + 3;   // ... and so is dP
+    uint64_t* bar_pds = bar_qdo + 4;
+    uint64_t* bar_kv = bar_qdo + 5;
+    uint64_t* bar_kvfree = bar_qdo + 6;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_qdo + 7);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -298,18 +305,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int b = blockIdx.x / p.H;
     const long long D3 = 3ll * p.D;
 
+    // rows of O and dO for delta_i = sum_d dO[i,d] * O[i,d]: the loads are issued before the CTA-wide sync and consumed
+    // after it, so their latency overlaps barrier init, the TMEM allocation, the TMA loads and the first S / dP MMAs
+    uint4 ro[8], rg[8];
+    float ls = 0.f;
+    const int irow = threadIdx.x;
+    const bool has_row = warp < 8 && irow < p.T;
     if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQKV);
             tma_prefetch_desc(&tmDO);
             mbar_init(bar_qdo, 1);
             mbar_init(bar_kvload, 1);
+            mbar_init(bar_s, 1);
             mbar_init(bar_sdp, 1);
             mbar_init(bar_pds, 256);
             mbar_init(bar_kv, 1);
             mbar_init(bar_kvfree, 256);
             fence_mbar_init();
-            // issue the first loads right away: they overlap the TMEM allocation and the delta prologue of the other warps
             mbar_expect_tx(bar_qdo, static_cast<uint32_t>(n_mt) * 2u * 16384u);
             for (int mt = 0; mt < n_mt; ++mt) {
                 tma_load_3d(sQ + mt * 16384, &tmQKV, bar_qdo, h * 64, mt * 128, b);
@@ -322,23 +335,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         __syncwarp();
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
-    } else {
-        // delta_i = sum_d dO[i,d] * O[i,d] (fp32) and lse_i for all (<= 256) query rows of this (b, h)
-        const int i = threadIdx.x;
-        float dl = 0.f, ls = 0.f;
-        if (i < p.T) {
-            const uint4* po = reinterpret_cast<const uint4*>(o_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
-            const uint4* pd = reinterpret_cast<const uint4*>(do_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
+    } else if (has_row) {
+        const uint4* po = reinterpret_cast<const uint4*>(o_in + (static_cast<long long>(b) * p.T + irow) * p.D + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(do_in + (static_cast<long long>(b) * p.T + irow) * p.D + h * 64);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint4 a = po[k], g = pd[k];
-                dl += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
-                      bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
-            }
-            ls = lse_in[(static_cast<long long>(b) * p.H + h) * p.T + i];
+        for (int k = 0; k < 8; ++k) {
+            ro[k] = __ldg(po + k);
+            rg[k] = __ldg(pd + k);
         }
-        lse_s[i] = i < p.T ? ls * kLog2e : INFINITY;  // padded query rows: exp2(s - inf) = 0 -> P = dS = 0 for free
-        delta_s[i] = dl;
+        ls = __ldg(lse_in + (static_cast<long long>(b) * p.H + h) * p.T + irow);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -347,12 +352,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (warp == 8) {
         if (elect_one()) {
-            const uint32_t idesc_nn = make_idesc_bf16(128, 128, 0, 0);  // S, dP   : A K-major,  B K-major
             const uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);   // dV, dK  : A MN-major, B MN-major
             const uint32_t idesc_nt = make_idesc_bf16(128, 64, 0, 1);   // dQ      : A K-major,  B MN-major
             const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
             uint32_t it = 0;
             for (int kt = 0; kt < n_kt; ++kt) {
+                // only the (16-padded) valid keys / queries of a tile enter the MMAs: T = 197 leaves 80 of 128 in tile 1
+                const int nk = min(128, p.tp - kt * 128);
+                const int nkc = nk >> 4;
+                const uint32_t idesc_nn = make_idesc_bf16(128, static_cast<uint32_t>(nk), 0, 0);  // S, dP: A, B K-major
                 if (kt > 0) {  // (key tile 0 was requested before the CTA-wide sync)
                     mbar_wait(bar_kv, static_cast<uint32_t>(kt - 1) & 1u);  // MMAs reading sK / sV retired
                     mbar_expect_tx(bar_kvload, 2u * 16384u);
@@ -363,11 +371,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 mbar_wait(bar_kvload, static_cast<uint32_t>(kt) & 1u);
                 tc_fence_after_sync();
                 for (int mt = 0; mt < n_mt; ++mt, ++it) {
+                    const int nqc = min(128, p.tp - mt * 128) >> 4;
                     const uint32_t q_base = smem_u32(sQ + mt * 16384), do_base = smem_u32(sDO + mt * 16384);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base + TM_S, make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
                                   make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), idesc_nn, kk > 0 ? 1u : 0u);
+                    umma_commit(bar_s);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base + TM_DP, make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
@@ -379,8 +389,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         mbar_wait(bar_kvfree, static_cast<uint32_t>(kt - 1) & 1u);  // dK / dV of the previous key tile read out
                         tc_fence_after_sync();
                     }
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 queries of this tile, 16 per step
+                    for (int kk = 0; kk < nqc; ++kk) {  // reduction over the queries of this tile, 16 per step
                         const uint64_t a_p = make_smem_desc(p_base + kk * 2048, 16384, 1024, kSwz128);
                         const uint64_t a_ds = make_smem_desc(ds_base + kk * 2048, 16384, 1024, kSwz128);
                         const uint64_t b_do = make_smem_desc(do_base + kk * 2048, 0, 1024, kSwz128);
@@ -389,8 +398,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         umma_bf16(tmem_base + TM_DV, a_p, b_do, idesc_tt, acc);
                         umma_bf16(tmem_base + TM_DK, a_ds, b_q, idesc_tt, acc);
                     }
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {  // reduction over the 128 keys of this tile
+                    for (int kk = 0; kk < nkc; ++kk) {  // reduction over the keys of this tile
                         const uint64_t a_ds = make_smem_desc(ds_base + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, kSwz128);
                         const uint64_t b_k = make_smem_desc(k_base + kk * 2048, 0, 1024, kSwz128);
                         umma_bf16(tmem_base + TM_DQ + static_cast<uint32_t>(mt * 64), a_ds, b_k, idesc_nt, (kt > 0 || kk > 0) ? 1u : 0u);
@@ -400,73 +408,109 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
         }
     } else {
+        {
+            float dl = 0.f;
+            if (has_row) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 a = ro[k], g = rg[k];
+                    dl += bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+                          bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+                }
+            }
+            lse_s[irow] = has_row ? ls * kLog2e : INFINITY;  // padded query rows: exp2(s - inf) = 0 -> P = dS = 0 for free
+            delta_s[irow] = dl;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         const uint32_t q = static_cast<uint32_t>(warp & 3);
-        const int ch = warp >> 2;                  // which 64-key half of the key tile
-        const int r = static_cast<int>(q) * 32 + lane;  // row in the query tile
+        const int ch = warp >> 2;                       // ch 0 takes the first half of the key chunks, ch 1 the rest
+        const int r = static_cast<int>(q) * 32 + lane;  // row in the query tile == TMEM lane
         const uint32_t taddr = tmem_base + ((q * 32u) << 16);
         const float sl2 = p.scale * kLog2e;
+        uint8_t* stage = sP + ch * 16384 + static_cast<int>(q) * 4096;  // this warp's rows of block `ch`: epilogue staging
+        const uint32_t rsw = static_cast<uint32_t>(r) & 7u;
         uint32_t it = 0;
         for (int kt = 0; kt < n_kt; ++kt) {
+            const int nkc = min(128, p.tp - kt * 128) >> 4;
+            const int n0 = (nkc + 1) >> 1;
+            const int cbeg = ch ? n0 : 0;
             for (int mt = 0; mt < n_mt; ++mt, ++it) {
+                const int nq = min(128, p.tp - mt * 128);
+                // warps whose 32 query rows are all padding skip the math: their P / dS rows are outside every reduction
+                const int nmine = (static_cast<int>(q) * 32 < nq) ? (ch ? nkc - n0 : n0) : 0;
                 const int i = mt * 128 + r;
                 const float lse2 = lse_s[i];
                 const float delta = delta_s[i];
+                uint32_t sv[2][16], dv[2][16];
+                mbar_wait(bar_s, it & 1u);
+                tc_fence_after_sync();
+                if (nmine > 0) tmem_ld_32x32b_x16(taddr + TM_S + static_cast<uint32_t>(cbeg * 16), sv[0]);
                 mbar_wait(bar_sdp, it & 1u);
                 tc_fence_after_sync();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int col = ch * 64 + c * 16;
-                    const int j0 = kt * 128 + col;
-                    uint32_t sv[16], dv[16];
-                    tmem_ld_32x32b_x16(taddr + TM_S + static_cast<uint32_t>(col), sv);
-                    tmem_ld_32x32b_x16(taddr + TM_DP + static_cast<uint32_t>(col), dv);
-                    tmem_ld_wait();
-                    float pv[16], ds[16];
-                    if (!p.causal && j0 + 16 <= p.T) {  // warp-uniform fast path: every key of the chunk is valid
+                if (nmine > 0) tmem_ld_32x32b_x16(taddr + TM_DP + static_cast<uint32_t>(cbeg * 16), dv[0]);
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            pv[jj] = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -lse2));
-                            ds[jj] = pv[jj] * (__uint_as_float(dv[jj]) - delta);
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (cc < nmine) {  // warp-uniform
+                        tmem_ld_wait();
+                        if (cc + 1 < nmine) {  // next chunk's TMEM reads fly under this chunk's math
+                            tmem_ld_32x32b_x16(taddr + TM_S + static_cast<uint32_t>((cbeg + cc + 1) * 16), sv[(cc + 1) & 1]);
+                            tmem_ld_32x32b_x16(taddr + TM_DP + static_cast<uint32_t>((cbeg + cc + 1) * 16), dv[(cc + 1) & 1]);
                         }
-                    } else {
+                        const uint32_t(&s_)[16] = sv[cc & 1];
+                        const uint32_t(&d_)[16] = dv[cc & 1];
+                        const int col = (cbeg + cc) * 16;
+                        const int j0 = kt * 128 + col;
+                        float pv[16], ds[16];
+                        if (!p.causal && j0 + 16 <= p.T) {  // warp-uniform fast path: every key of the chunk is valid
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const int j = j0 + jj;
-                            const bool ok = (j < p.T) && (!p.causal || j <= i);
-                            const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -lse2));
-                            pv[jj] = ok ? e : 0.f;
-                            ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - delta) : 0.f;
+                            for (int jj = 0; jj < 16; ++jj) {
+                                pv[jj] = fast_ex2(fmaf(__uint_as_float(s_[jj]), sl2, -lse2));
+                                ds[jj] = pv[jj] * (__uint_as_float(d_[jj]) - delta);
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                const int j = j0 + jj;
+                                const bool ok = (j < p.T) && (!p.causal || j <= i);
+                                const float e = fast_ex2(fmaf(__uint_as_float(s_[jj]), sl2, -lse2));
+                                pv[jj] = ok ? e : 0.f;
+                                ds[jj] = ok ? e * (__uint_as_float(d_[jj]) - delta) : 0.f;
+                            }
                         }
+                        const uint32_t blk = static_cast<uint32_t>(col >> 6) * 16384u + static_cast<uint32_t>(r) * 128u;
+                        const uint32_t c16 = static_cast<uint32_t>((col & 63) >> 3);
+                        const uint32_t off0 = blk + ((c16 ^ rsw) << 4);
+                        const uint32_t off1 = blk + (((c16 + 1) ^ rsw) << 4);
+                        *reinterpret_cast<uint4*>(sP + off0) = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+                        *reinterpret_cast<uint4*>(sP + off1) = make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
+                        *reinterpret_cast<uint4*>(sDS + off0) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+                        *reinterpret_cast<uint4*>(sDS + off1) = make_uint4(pack_bf16x2(ds[8], ds[9]), pack_bf16x2(ds[10], ds[11]), pack_bf16x2(ds[12], ds[13]), pack_bf16x2(ds[14], ds[15]));
                     }
-                    const uint32_t c16 = static_cast<uint32_t>(c * 2);
-                    const uint32_t off0 = static_cast<uint32_t>(ch) * 16384u + static_cast<uint32_t>(r) * 128u + (((c16) ^ (static_cast<uint32_t>(r) & 7u)) << 4);
-                    const uint32_t off1 = static_cast<uint32_t>(ch) * 16384u + static_cast<uint32_t>(r) * 128u + (((c16 + 1) ^ (static_cast<uint32_t>(r) & 7u)) << 4);
-                    *reinterpret_cast<uint4*>(sP + off0) = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
-                    *reinterpret_cast<uint4*>(sP + off1) = make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
-                    *reinterpret_cast<uint4*>(sDS + off0) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
-                    *reinterpret_cast<uint4*>(sDS + off1) = make_uint4(pack_bf16x2(ds[8], ds[9]), pack_bf16x2(ds[10], ds[11]), pack_bf16x2(ds[12], ds[13]), pack_bf16x2(ds[14], ds[15]));
                 }
                 fence_proxy_async_smem();
                 tc_fence_before_sync();
                 mbar_arrive(bar_pds);
                 if (mt == n_mt - 1) {
-                    // dK / dV of this key tile are complete (and, on the last key tile, so are all dQ)
+                    // dK / dV of this key tile are complete (and, on the last key tile, so are all dQ); every MMA that read
+                    // sP / sDS has retired, so sP doubles as the staging area of the coalesced stores
                     mbar_wait(bar_kv, static_cast<uint32_t>(kt) & 1u);
                     tc_fence_after_sync();
-                    const int key = kt * 128 + r;
-                    __nv_bfloat16* drow = dqkv + (static_cast<long long>(b) * p.T + key) * D3 + h * 64;
-                    if (ch == 0) store_row64_scaled(drow + p.D, taddr + TM_DK, p.scale, key < p.T);
-                    else         store_row64_scaled(drow + 2 * p.D, taddr + TM_DV, 1.0f, key < p.T);
+                    const int key0 = kt * 128 + static_cast<int>(q) * 32;
+                    __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + key0) * D3 + h * 64;
+                    if (ch == 0) store_rows_coalesced<4>(stage, g0 + p.D, D3, taddr + TM_DK, p.scale, p.T - key0, lane);
+                    else         store_rows_coalesced<4>(stage, g0 + 2 * p.D, D3, taddr + TM_DV, 1.0f, p.T - key0, lane);
                     tc_fence_before_sync();
                     mbar_arrive(bar_kvfree);
+                    // the next key tile's P / dS chunks of another warp may land in this warp's staging rows
+                    if (kt + 1 < n_kt) asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             }
         }
         // dQ tiles: warps with ch < n_mt each write query tile `ch`
         if (ch < n_mt) {
-            const int i = ch * 128 + r;
-            __nv_bfloat16* drow = dqkv + (static_cast<long long>(b) * p.T + i) * D3 + h * 64;
-            store_row64_scaled(drow, taddr + TM_DQ + static_cast<uint32_t>(ch * 64), p.scale, i < p.T);
+            const int row0 = ch * 128 + static_cast<int>(q) * 32;
+            __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + row0) * D3 + h * 64;
+            store_rows_coalesced<4>(stage, g0, D3, taddr + TM_DQ + static_cast<uint32_t>(ch * 64), p.scale, p.T - row0, lane);
         }
     }
     tc_fence_before_sync();

@@ -20,6 +20,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "b200_internal.h"
 #include "ptx.cuh"
 
@@ -270,6 +272,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t aph = (lt >> 1) & 1u;
             const int grow0 = m_t * BM + static_cast<int>(q) * 32;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(as * BN);
+            // Tiles that lie completely inside the output (every tile of the ViT shapes) run a copy of the epilogue with
+            // all bounds predicates compiled out: the ragged-edge checks were ~7 of its ~27 instructions per element.
+            const bool interior = (m_t * BM + BM <= p.M) && (n_t * BN + BN <= p.N);
+            auto tile_epilogue = [&](auto interior_tag) {
+            constexpr bool INT = decltype(interior_tag)::value;
             // The accumulator buffer can only be handed back to the MMA warp once it has been READ completely, and
             // MMA(i+2) waits for that.  So the TMEM reads run two chunks ahead of the processing (register ping-pong
             // va / vb): the buffer is released after chunk 1 instead of after chunk 3, i.e. after about half of the
@@ -281,11 +288,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             auto load_aux = [&](int cc, int slot) {
                 const int gc = n_t * BN + half * 128 + cc * 32;
                 const int pc = gc + (lane & 3) * 8;
-                const bool act = (gc < p.N) && (grow0 < p.M);
+                const bool act = INT || ((gc < p.N) && (grow0 < p.M));
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int row = grow0 + it * 8 + (lane >> 2);
-                    const bool ok = act && row < p.M && pc + 8 <= p.N;
+                    const bool ok = INT || (act && row < p.M && pc + 8 <= p.N);
                     if constexpr (EPI == EPI_DGELU_BF16) {
                         aux_h[slot][it] = make_uint4(0, 0, 0, 0);
                         if (ok) aux_h[slot][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pc);
@@ -301,7 +308,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             };
+            // bias of the chunk's 32 columns (row-per-thread layout: every lane needs all of them).  Loaded at the point
+            // of use, each of the four 16-byte loads exposed its L2 latency in every chunk; now the next chunk's bias is
+            // requested right after phase 1 has consumed this one, so phase 2 covers the latency.
+            uint4 bias_r[4];
+            auto load_bias = [&](int cc) {
+                const int gc = n_t * BN + half * 128 + cc * 32;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    bias_r[j4] = make_uint4(0, 0, 0, 0);
+                    // (the fp32-residual epilogue is at the 168-register ceiling of a 10-warp CTA: it keeps point-of-use loads)
+                    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+                        if (p.bias != nullptr && (INT || (gc + j4 * 8 < p.N && grow0 < p.M)))
+                            bias_r[j4] = *reinterpret_cast<const uint4*>(p.bias + gc + j4 * 8);
+                    }
+                }
+            };
             if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) load_aux(0, 0);
+            load_bias(0);
             mbar_wait(&tmem_full_bar[as], aph);
             tc_fence_after_sync();
             uint32_t va[32], vb[32];
@@ -313,7 +337,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t (&v)[32] = (c & 1) ? vb : va;
                 const int col = half * 128 + c * 32;
                 const int gcol = n_t * BN + col;
-                const bool active = (gcol < p.N) && (grow0 < p.M);  // warp-uniform
+                const bool active = INT || ((gcol < p.N) && (grow0 < p.M));  // warp-uniform
                 // phase-2 coordinates of this lane inside a bf16-staged chunk: 4 row groups of 8 rows, 4 lanes per row
                 const int prow = lane >> 2, pch = lane & 3;
                 const int pcol = gcol + pch * 8;
@@ -338,9 +362,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int r = it * 4 + frow;
                         const int row = grow0 + r;
                         const uint4 t = *reinterpret_cast<const uint4*>(stg + swz128_off(r, fch));
-                        if (row < p.M) {
+                        if (INT || row < p.M) {
                             float* dst = out + row * ldo + fcol;
-                            if (fcol + 4 <= p.N) {
+                            if (INT || fcol + 4 <= p.N) {
                                 *reinterpret_cast<uint4*>(dst) = t;
                             } else {
                                 const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
@@ -357,9 +381,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j4 = 0; j4 < 4; ++j4) {
                         float bv[8];
                         {
-                            uint4 t = make_uint4(0, 0, 0, 0);
-                            if constexpr (EPI != EPI_DGELU_BF16) {
-                                if (p.bias != nullptr && gcol + j4 * 8 < p.N)
+                            uint4 t = bias_r[j4];
+                            if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                                if (p.bias != nullptr && (INT || gcol + j4 * 8 < p.N))
                                     t = *reinterpret_cast<const uint4*>(p.bias + gcol + j4 * 8);
                             }
                             bv[0] = bf16lo(t.x); bv[1] = bf16hi(t.x); bv[2] = bf16lo(t.y); bv[3] = bf16hi(t.y);
@@ -373,14 +397,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         *reinterpret_cast<uint4*>(sh + swz64_off(lane, j4)) = o;
                     }
                     __syncwarp();  // (the two halves alternate, so one barrier per chunk also covers the WAR hazard)
+                    if (c + 1 < 4) load_bias(c + 1);
                     // ---- phase 2: coalesced layout ----
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int r = it * 8 + prow;
                         const int row = grow0 + r;
                         const uint4 t = *reinterpret_cast<const uint4*>(sh + swz64_off(r, pch));  // 8 x bf16(acc + bias)
-                        if (row >= p.M) continue;
-                        const bool full = pcol + 8 <= p.N;
+                        if (!INT && row >= p.M) continue;
+                        const bool full = INT || pcol + 8 <= p.N;
                         const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
                         if constexpr (EPI == EPI_BIAS_BF16) {
                             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
@@ -457,6 +482,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            };  // tile_epilogue
+            if (interior) tile_epilogue(std::true_type{});
+            else tile_epilogue(std::false_type{});
         }
     }
 
