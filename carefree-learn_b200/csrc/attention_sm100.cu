@@ -179,7 +179,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (p.causal && i + 1 < nvalid) nvalid = i + 1;
         const int nchunk = p.tp / 16;
         const int nc0 = (nchunk + 1) / 2;
-        const int c_begin = half ? nc0 : 0, c_end = half ? nchunk : nc0;
+        // warps whose 32 query rows are all padding (T = 197: 59 of the second tile's 128 rows) only keep the barrier
+        // protocol: their P rows feed output rows that are never stored
+        const bool dead = mt * 128 + static_cast<int>(q) * 32 >= p.T;
+        const int c_begin = dead ? 0 : (half ? nc0 : 0), c_end = dead ? 0 : (half ? nchunk : nc0);
         mbar_wait(bar_s, 0);
         tc_fence_after_sync();
         // pass 1: row max over this thread's column half, then combine the two halves
@@ -245,7 +248,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // every MMA reading sQ / sK / sP has retired (bar_o): the front of the buffer is free for staging
             const int row0 = mt * 128 + static_cast<int>(q) * 32;
             __nv_bfloat16* g0 = out + (static_cast<long long>(b) * p.T + row0) * p.D + h * 64 + half * 32;
-            store_rows_coalesced<2>(smem + warp * 2048, g0, p.D, taddr + static_cast<uint32_t>(half * 32), inv, p.T - row0, lane);
+            if (!dead) store_rows_coalesced<2>(smem + warp * 2048, g0, p.D, taddr + static_cast<uint32_t>(half * 32), inv, p.T - row0, lane);
         }
         if (valid && half == 0) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
     }
@@ -263,11 +266,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 constexpr int AB_THREADS = 288;
 constexpr int AB_SQ = 0;        // 2 x 16 KB (query tiles 0,1)
 constexpr int AB_SDO = 32768;   // 2 x 16 KB
-constexpr int AB_SK = 65536;    // 16 KB (current key tile)
-constexpr int AB_SV = 81920;    // 16 KB
-constexpr int AB_SP = 98304;    // 32 KB: P  [128 q x 128 keys] as two 64-key blocks
-constexpr int AB_SDS = 131072;  // 32 KB: dS
-constexpr int AB_LSE = 163840;  // 256 floats
+constexpr int AB_SK = 65536;    // 2 x 16 KB (key tiles 0,1: resident, a reload at the tile switch stalled every warp ~1 us)
+constexpr int AB_SV = 98304;    // 2 x 16 KB
+constexpr int AB_SP = 131072;   // 32 KB: P  [128 q x 128 keys] as two 64-key blocks
+constexpr int AB_SDS = 163840;  // 32 KB: dS
+constexpr int AB_LSE = 196608;  // 256 floats
 constexpr int AB_DELTA = AB_LSE + 1024;
 constexpr int AB_BAR = AB_DELTA + 1024;
 constexpr int AB_SMEM = AB_BAR + 128 + 1024;
@@ -328,9 +331,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 tma_load_3d(sQ + mt * 16384, &tmQKV, bar_qdo, h * 64, mt * 128, b);
                 tma_load_3d(sDO + mt * 16384, &tmDO, bar_qdo, h * 64, mt * 128, b);
             }
-            mbar_expect_tx(bar_kvload, 2u * 16384u);
-            tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, 0, b);
-            tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, 0, b);
+            mbar_expect_tx(bar_kvload, static_cast<uint32_t>(n_kt) * 2u * 16384u);
+            for (int kt = 0; kt < n_kt; ++kt) {
+                tma_load_3d(sK + kt * 16384, &tmQKV, bar_kvload, p.D + h * 64, kt * 128, b);
+                tma_load_3d(sV + kt * 16384, &tmQKV, bar_kvload, 2 * p.D + h * 64, kt * 128, b);
+            }
         }
         __syncwarp();
         tmem_alloc(tmem_ptr_smem, 512);
@@ -354,22 +359,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (elect_one()) {
             const uint32_t idesc_tt = make_idesc_bf16(128, 64, 1, 1);   // dV, dK  : A MN-major, B MN-major
             const uint32_t idesc_nt = make_idesc_bf16(128, 64, 0, 1);   // dQ      : A K-major,  B MN-major
-            const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+            const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
             uint32_t it = 0;
+            mbar_wait(bar_qdo, 0);
+            mbar_wait(bar_kvload, 0);
+            tc_fence_after_sync();
             for (int kt = 0; kt < n_kt; ++kt) {
+                const uint32_t k_base = smem_u32(sK + kt * 16384), v_base = smem_u32(sV + kt * 16384);
                 // only the (16-padded) valid keys / queries of a tile enter the MMAs: T = 197 leaves 80 of 128 in tile 1
                 const int nk = min(128, p.tp - kt * 128);
                 const int nkc = nk >> 4;
                 const uint32_t idesc_nn = make_idesc_bf16(128, static_cast<uint32_t>(nk), 0, 0);  // S, dP: A, B K-major
-                if (kt > 0) {  // (key tile 0 was requested before the CTA-wide sync)
-                    mbar_wait(bar_kv, static_cast<uint32_t>(kt - 1) & 1u);  // MMAs reading sK / sV retired
-                    mbar_expect_tx(bar_kvload, 2u * 16384u);
-                    tma_load_3d(sK, &tmQKV, bar_kvload, p.D + h * 64, kt * 128, b);
-                    tma_load_3d(sV, &tmQKV, bar_kvload, 2 * p.D + h * 64, kt * 128, b);
-                }
-                if (kt == 0) mbar_wait(bar_qdo, 0);
-                mbar_wait(bar_kvload, static_cast<uint32_t>(kt) & 1u);
-                tc_fence_after_sync();
                 for (int mt = 0; mt < n_mt; ++mt, ++it) {
                     const int nqc = min(128, p.tp - mt * 128) >> 4;
                     const uint32_t q_base = smem_u32(sQ + mt * 16384), do_base = smem_u32(sDO + mt * 16384);

@@ -42,9 +42,15 @@ constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
 constexpr int SMEM_A_OFF = 0;
 constexpr int SMEM_B_OFF = SMEM_A_OFF + STAGES * A_STAGE_BYTES;
 constexpr int SMEM_EPI_OFF = SMEM_B_OFF + STAGES * B_STAGE_BYTES;
-constexpr int SMEM_BAR_OFF = SMEM_EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;  // per epilogue warp: bias of its 128 columns
+constexpr int EPI_BIAS_BYTES = 256;
+constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + NUM_EPI_WARPS * EPI_BIAS_BYTES;
 constexpr int SMEM_BAR_BYTES = 256;
-constexpr int GEMM_SMEM_BYTES = SMEM_BAR_OFF + SMEM_BAR_BYTES + 1024;  // + slack for manual 1 KB alignment
+constexpr int GEMM_SMEM_USED = SMEM_BAR_OFF + SMEM_BAR_BYTES;
+// everything an SM offers (227 KB); the manual 1 KB alignment of the base may take the 768 bytes that are left (in
+// practice the dynamic segment starts 1 KB aligned; the kernel traps if the layout ever does not fit)
+constexpr int GEMM_SMEM_BYTES = 232448;
+static_assert(GEMM_SMEM_USED + 768 <= GEMM_SMEM_BYTES, "GEMM shared-memory layout does not fit");
 
 struct GemmParams {
     int M, N, K;
@@ -91,6 +97,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* sA = smem + SMEM_A_OFF;
     uint8_t* sB = smem + SMEM_B_OFF;
     uint8_t* sEpi = smem + SMEM_EPI_OFF;
+    if (smem + GEMM_SMEM_USED > smem_raw + GEMM_SMEM_BYTES) {
+        if (threadIdx.x == 0) printf("b200 gemm: dynamic shared memory base %p is not 256-byte aligned\n", smem_raw);
+        __trap();
+    }
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -263,6 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t q = warp & 3;          // TMEM lane quadrant this warp may access
         const int half = e >> 2;              // which 128-column half of the accumulator
         uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
+        uint8_t* sbias = smem + SMEM_BIAS_OFF + e * EPI_BIAS_BYTES;
         const long long ldo = p.ldo;
         int lt = 0;
         for (int u = unit0; u < total_units; u += unit_stride, ++lt) {
@@ -308,24 +319,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             };
-            // bias of the chunk's 32 columns (row-per-thread layout: every lane needs all of them).  Loaded at the point
-            // of use, each of the four 16-byte loads exposed its L2 latency in every chunk; now the next chunk's bias is
-            // requested right after phase 1 has consumed this one, so phase 2 covers the latency.
-            uint4 bias_r[4];
-            auto load_bias = [&](int cc) {
-                const int gc = n_t * BN + half * 128 + cc * 32;
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    bias_r[j4] = make_uint4(0, 0, 0, 0);
-                    // (the fp32-residual epilogue is at the 168-register ceiling of a 10-warp CTA: it keeps point-of-use loads)
-                    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-                        if (p.bias != nullptr && (INT || (gc + j4 * 8 < p.N && grow0 < p.M)))
-                            bias_r[j4] = *reinterpret_cast<const uint4*>(p.bias + gc + j4 * 8);
-                    }
+            // bias of this warp's 128 columns -> its private 256 B of shared memory, before the accumulator is awaited.
+            // (Loaded from global at the point of use, the four 16-byte loads of every chunk exposed their L2 latency.)
+            if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
+                if (lane < 16) {
+                    const int gc = n_t * BN + half * 128 + lane * 8;
+                    uint4 t = make_uint4(0, 0, 0, 0);
+                    if (p.bias != nullptr && (INT || gc < p.N)) t = *reinterpret_cast<const uint4*>(p.bias + gc);
+                    *reinterpret_cast<uint4*>(sbias + lane * 16) = t;
                 }
-            };
+                __syncwarp();
+            }
             if constexpr (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16) load_aux(0, 0);
-            load_bias(0);
             mbar_wait(&tmem_full_bar[as], aph);
             tc_fence_after_sync();
             uint32_t va[32], vb[32];
@@ -381,11 +386,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j4 = 0; j4 < 4; ++j4) {
                         float bv[8];
                         {
-                            uint4 t = bias_r[j4];
-                            if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                                if (p.bias != nullptr && (INT || gcol + j4 * 8 < p.N))
-                                    t = *reinterpret_cast<const uint4*>(p.bias + gcol + j4 * 8);
-                            }
+                            uint4 t = make_uint4(0, 0, 0, 0);
+                            if constexpr (EPI != EPI_DGELU_BF16) t = *reinterpret_cast<const uint4*>(sbias + c * 64 + j4 * 16);
                             bv[0] = bf16lo(t.x); bv[1] = bf16hi(t.x); bv[2] = bf16lo(t.y); bv[3] = bf16hi(t.y);
                             bv[4] = bf16lo(t.z); bv[5] = bf16hi(t.z); bv[6] = bf16lo(t.w); bv[7] = bf16hi(t.w);
                         }
@@ -397,7 +399,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         *reinterpret_cast<uint4*>(sh + swz64_off(lane, j4)) = o;
                     }
                     __syncwarp();  // (the two halves alternate, so one barrier per chunk also covers the WAR hazard)
-                    if (c + 1 < 4) load_bias(c + 1);
                     // ---- phase 2: coalesced layout ----
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {

@@ -117,8 +117,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // blocks fit per SM; the first version (148 registers, dres loaded after the reductions) sat at 2 TB/s.
 // Per-lane dgamma/dbeta partials live in registers and are reduced across the block's warps through shared memory
 // -> part[blockIdx][0:dim] (dgamma) and part[blockIdx][dim:2*dim] (dbeta).
+// DXSUM: additionally part[blockIdx][2*dim:3*dim] = column sums of the bf16-ROUNDED dx rows this block wrote, i.e. the
+// bias gradient of the Linear whose dY this dx is (it used to be a separate pass over dx_bf16).  These partials are
+// accumulated in each warp's private shared-memory row: 24 more accumulator registers would break the 128 budget.
 // ------------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool DXSUM>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                const float* __restrict__ x, long long ld_x,
                                                                const float* __restrict__ gamma,
@@ -127,10 +130,15 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
                                                                const float* __restrict__ dres, float* __restrict__ dx_out,
                                                                long long ld_dx, __nv_bfloat16* __restrict__ dx_bf16,
                                                                float* __restrict__ part, int rows, int dim) {
-    extern __shared__ float sred[];  // [8 warps][2][dim]
+    extern __shared__ float sred[];  // [8 warps][2][dim] (+ [8 warps][dim] with DXSUM)
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    constexpr int NP = DXSUM ? 3 : 2;
+    float* sx = sred + (warps_per_block * 2 + wib) * dim;  // this warp's running column sums of bf16(dx)
+    if constexpr (DXSUM) {
+        for (int c = lane * 4; c < dim; c += 128) *reinterpret_cast<float4*>(sx + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float4 dg[NV], db[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -191,6 +199,11 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
                     p.x = pack_bf16x2(o.x, o.y);
                     p.y = pack_bf16x2(o.z, o.w);
                     *reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * dim + c) = p;
+                    if constexpr (DXSUM) {  // (lane-private columns: no synchronisation)
+                        float4 a = *reinterpret_cast<float4*>(sx + c);
+                        a.x += bf16lo(p.x); a.y += bf16hi(p.x); a.z += bf16lo(p.y); a.w += bf16hi(p.y);
+                        *reinterpret_cast<float4*>(sx + c) = a;
+                    }
                 }
             }
         }
@@ -213,8 +226,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
             a += sred[(w * 2 + 0) * dim + c];
             b += sred[(w * 2 + 1) * dim + c];
         }
-        part[static_cast<long long>(blockIdx.x) * 2 * dim + c] = a;
-        part[static_cast<long long>(blockIdx.x) * 2 * dim + dim + c] = b;
+        part[static_cast<long long>(blockIdx.x) * NP * dim + c] = a;
+        part[static_cast<long long>(blockIdx.x) * NP * dim + dim + c] = b;
+        if constexpr (DXSUM) {
+            float d = 0.f;
+            for (int w = 0; w < warps_per_block; ++w) d += sred[(warps_per_block * 2 + w) * dim + c];
+            part[static_cast<long long>(blockIdx.x) * NP * dim + 2 * dim + c] = d;
+        }
     }
 }
 
@@ -278,6 +296,28 @@ __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restr
         for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
         if (round_bf16) t = bf16_round(t);
         out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+// two destinations in one launch: columns [0, cols0) -> out0, [cols0, cols0 + cols1) -> out1 (own rounding flag each)
+__global__ void __launch_bounds__(256) colsum_finish2_kernel(const float* __restrict__ part, long long part_ld, int nparts,
+                                                             int cols0, float* __restrict__ out0, int round0, int cols1,
+                                                             float* __restrict__ out1, int round1, int accumulate) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int cols = cols0 + cols1;
+    float s = 0.f;
+    if (c < cols)
+        for (int p = threadIdx.y; p < nparts; p += 8) s += part[static_cast<long long>(p) * part_ld + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        float* o = c < cols0 ? out0 + c : out1 + (c - cols0);
+        if (c < cols0 ? round0 : round1) t = bf16_round(t);
+        *o = accumulate ? *o + t : t;
     }
 }
 
@@ -505,18 +545,25 @@ static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, con
                                                      mean, rstd, rows, dim, eps);
     return check_launch("layernorm_fwd");
 }
+template <int NV, bool DXSUM>
+static int ln_bwd_launch2(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
+                          const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
+                          float* part, int nparts, int rows, int dim, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(8) * (DXSUM ? 3 : 2) * dim * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(layernorm_bwd_kernel<NV, DXSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    }
+    layernorm_bwd_kernel<NV, DXSUM><<<nparts, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, ld_x, gamma, mean,
+                                                               rstd, dres, dx_out, ld_dx,
+                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16), part, rows, dim);
+    return check_launch("layernorm_bwd");
+}
 template <int NV>
 static int ln_bwd_launch(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
-                         float* part, int nparts, int rows, int dim, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(8) * 2 * dim * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    }
-    layernorm_bwd_kernel<NV><<<nparts, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, ld_x, gamma, mean,
-                                                        rstd, dres, dx_out, ld_dx,
-                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), part, rows, dim);
-    return check_launch("layernorm_bwd");
+                         float* part, int nparts, int rows, int dim, bool dxsum, cudaStream_t st) {
+    if (dxsum) return ln_bwd_launch2<NV, true>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
+    return ln_bwd_launch2<NV, false>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
 }
 
 }  // namespace b200
@@ -541,19 +588,21 @@ extern "C" int b200_layernorm_fwd(const float* x, long long ld_x, const float* g
 extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma,
                                   const float* mean, const float* rstd, const float* dres, float* dx_out,
                                   long long ld_dx, void* dx_bf16, float* dgb_part, int max_parts, int* nparts_out,
-                                  int rows, int dim, cudaStream_t stream) {
+                                  int rows, int dim, int dx_colsum, cudaStream_t stream) {
     if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 128 * LN_MAX_V4) return set_error(B200_ERR_ARG, "layernorm_bwd: need 0 < dim <= 1024, dim % 4 == 0");
     if (ld_x % 4 != 0 || ld_dx % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_bwd: ld % 4 != 0");
     if (max_parts < 1) return set_error(B200_ERR_ARG, "layernorm_bwd: max_parts < 1");
+    if (dx_colsum && dx_bf16 == nullptr) return set_error(B200_ERR_ARG, "layernorm_bwd: dx_colsum needs dx_bf16");
+    const bool dxs = dx_colsum != 0;
     int nparts = num_sms() * 2  /* two resident 256-thread blocks per SM: one wave */;
     const int need = (rows + 7) / 8;
     if (nparts > need) nparts = need;
     if (nparts > max_parts) nparts = max_parts;
     if (nparts_out) *nparts_out = nparts;
     const int nv = (dim + 127) / 128;
-    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
-    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
-    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, stream);
+    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
+    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
+    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
 }
 
 extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,
@@ -575,6 +624,13 @@ extern "C" int b200_colsum_finish(const float* part, long long part_ld, int npar
     if (nparts <= 0 || cols <= 0 || part_ld < cols) return set_error(B200_ERR_ARG, "colsum_finish: bad size");
     colsum_finish_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, stream>>>(part, part_ld, nparts, cols, out, round_bf16, accumulate);
     return check_launch("colsum_finish");
+}
+
+extern "C" int b200_colsum_finish2(const float* part, long long part_ld, int nparts, int cols0, float* out0, int round0,
+                                   int cols1, float* out1, int round1, int accumulate, cudaStream_t stream) {
+    if (nparts <= 0 || cols0 <= 0 || cols1 <= 0 || part_ld < cols0 + cols1) return set_error(B200_ERR_ARG, "colsum_finish2: bad size");
+    colsum_finish2_kernel<<<(cols0 + cols1 + 31) / 32, dim3(32, 8), 0, stream>>>(part, part_ld, nparts, cols0, out0, round0, cols1, out1, round1, accumulate);
+    return check_launch("colsum_finish2");
 }
 
 extern "C" int b200_splitk_reduce(const float* partial, int splits, long long n, float* out, int round_bf16,

@@ -151,20 +151,30 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, rows: i
 def layernorm_bwd(
     dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, *, rows: int, dim: int, ld_x: int,
     dres: Optional[Tensor], dx_out: Tensor, ld_dx: int, dx_bf16: Optional[Tensor],
-    dgamma: Tensor, dbeta: Tensor, accumulate: bool = False,
+    dgamma: Tensor, dbeta: Tensor, accumulate: bool = False, dx_colsum: Optional[Tensor] = None,
 ) -> None:
-    part = WORKSPACE.get(x.device, 2 * _MAX_PARTS * dim, "lnbwd")
+    """LayerNorm backward.  ``dx_colsum`` (fp32 [dim]): also receives the bf16-rounded column sums of ``dx_bf16``,
+    i.e. the bias gradient of the Linear layer whose dY this dx is -- fused, no extra pass over dx."""
+    nw = 3 if dx_colsum is not None else 2
+    part = WORKSPACE.get(x.device, 3 * _MAX_PARTS * dim, "lnbwd")
     nparts = ctypes.c_int(0)
     call(
         "b200_layernorm_bwd", dy.data_ptr(), x.data_ptr(), ld_x, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
         _ptr(dres), dx_out.data_ptr(), ld_dx, _ptr(dx_bf16), part.data_ptr(), _MAX_PARTS,
-        ctypes.byref(nparts), rows, dim, _stream(),
+        ctypes.byref(nparts), rows, dim, int(dx_colsum is not None), _stream(),
     )
-    if dbeta.data_ptr() == dgamma.data_ptr() + 4 * dim:  # adjacent in the gradient arena: one reduction for both
-        call("b200_colsum_finish", part.data_ptr(), 2 * dim, nparts.value, 2 * dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
+    adjacent = dbeta.data_ptr() == dgamma.data_ptr() + 4 * dim  # adjacent in the gradient arena: one reduction for both
+    if adjacent and dx_colsum is not None:
+        call("b200_colsum_finish2", part.data_ptr(), nw * dim, nparts.value, 2 * dim, dgamma.data_ptr(), 0,
+             dim, dx_colsum.data_ptr(), 1, int(accumulate), _stream())
+        return
+    if adjacent:
+        call("b200_colsum_finish", part.data_ptr(), nw * dim, nparts.value, 2 * dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
     else:
-        call("b200_colsum_finish", part.data_ptr(), 2 * dim, nparts.value, dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
-        call("b200_colsum_finish", part.data_ptr() + 4 * dim, 2 * dim, nparts.value, dim, dbeta.data_ptr(), 0, int(accumulate), _stream())
+        call("b200_colsum_finish", part.data_ptr(), nw * dim, nparts.value, dim, dgamma.data_ptr(), 0, int(accumulate), _stream())
+        call("b200_colsum_finish", part.data_ptr() + 4 * dim, nw * dim, nparts.value, dim, dbeta.data_ptr(), 0, int(accumulate), _stream())
+    if dx_colsum is not None:
+        call("b200_colsum_finish", part.data_ptr() + 8 * dim, nw * dim, nparts.value, dim, dx_colsum.data_ptr(), 1, int(accumulate), _stream())
 
 
 # ----------------------------------------------------------------------------------------------------------------

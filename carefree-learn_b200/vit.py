@@ -271,6 +271,9 @@ class ViTEngine:
                           rows=B, dim=D, ld_x=T * D, dres=None, dx_out=dnet, ld_dx=T * D, dx_bf16=None,
                           dgamma=A.g("encoder.head.norms.0.weight", G), dbeta=A.g("encoder.head.norms.0.bias", G))
         dnet_bf = ops.cast_bf16(dnet)
+        # bias gradient of the last block's FF2 (dY = dnet_bf); every other Linear whose dY comes out of a LayerNorm
+        # backward gets its bias gradient from that kernel (dx_colsum)
+        self._bias_grad(dnet_bf, A.g(f"encoder.mixing_blocks.{g.L - 1}.channel_mixing.net.3.linear.bias", G))
         if red is not None:
             red.ready("tail", G)
         for i in reversed(range(g.L)):
@@ -279,7 +282,6 @@ class ViTEngine:
             # FeedForward: net_out = mid + W2 gelu(W1 ln2 + b1) + b2
             dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=h)
             ops.wgrad(dnet_bf, act, A.g(b + "channel_mixing.net.3.linear.weight", G))
-            self._bias_grad(dnet_bf, A.g(b + "channel_mixing.net.3.linear.bias", G))
             dln2 = ops.gemm(dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
             ops.wgrad(dh, ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
             self._bias_grad(dh, A.g(b + "channel_mixing.net.0.linear.bias", G))
@@ -287,11 +289,11 @@ class ViTEngine:
             dmid_bf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.layernorm_bwd(dln2, mid, A.p(b + "channel_norm.weight"), mean2, rstd2, rows=M, dim=D, ld_x=D, dres=dnet,
                               dx_out=dmid, ld_dx=D, dx_bf16=dmid_bf,
-                              dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G))
+                              dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G),
+                              dx_colsum=A.g(b + "token_mixing.net.out_linear.linear.bias", G))
             # attention: mid = net + Wo attn + bo
             dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
             ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
-            self._bias_grad(dmid_bf, A.g(b + "token_mixing.net.out_linear.linear.bias", G))
             dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H)
             dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
             ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
@@ -299,7 +301,8 @@ class ViTEngine:
             self._join_side()  # dnet_bf is overwritten below, and this block's bias gradients must be complete
             ops.layernorm_bwd(dln1, net, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D, dres=dmid,
                               dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,
-                              dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G))
+                              dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G),
+                              dx_colsum=A.g(f"encoder.mixing_blocks.{i - 1}.channel_mixing.net.3.linear.bias", G) if i > 0 else None)
             sv.blocks[i] = None  # release this block's activations
             if red is not None:
                 red.ready(i, G)

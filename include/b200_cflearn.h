@@ -27,7 +27,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 enum {
     B200_OK = 0,
@@ -89,10 +89,14 @@ int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const
 /* dx_out[f32] = (dres ? dres : 0) + LN'(dy); dx_out row stride ld_dx (so the head LN can scatter into token 0).
  * dy: bf16 [rows, dim].  dx_bf16 (optional) receives bf16(dx_out) -- the gradient the preceding bf16 matmul
  * output sees under autocast.  dgb_part: f32 [nparts, 2*dim] workspace ([.., 0:dim] dgamma partials, [.., dim:2dim]
- * dbeta partials), reduced by b200_colsum_finish.  Returns nparts through *nparts_out (host int). */
+ * dbeta partials), reduced by b200_colsum_finish.  Returns nparts through *nparts_out (host int).
+ * dx_colsum != 0 (needs dx_bf16): the part rows are 3*dim wide and columns [2*dim, 3*dim) hold the column sums of
+ * the bf16-rounded dx rows, i.e. the bias gradient of the Linear layer whose output gradient this dx is (the
+ * separate b200_colsum_bf16 pass over dx_bf16 is then not needed). */
 int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
-                       float* dgb_part, int max_parts, int* nparts_out, int rows, int dim, cudaStream_t stream);
+                       float* dgb_part, int max_parts, int* nparts_out, int rows, int dim, int dx_colsum,
+                       cudaStream_t stream);
 
 /* column sums: part[p][c] = sum over a slice of rows of x[r][c]  (x bf16 or f32), then finish() reduces the
  * parts.  Bias gradients of every Linear (autograd of customs.py:89) and LN gamma/beta gradients. */
@@ -100,6 +104,9 @@ int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float
                      int* nparts_out, cudaStream_t stream);
 int b200_colsum_finish(const float* part, long long part_ld, int nparts, int cols, float* out, int round_bf16,
                        int accumulate, cudaStream_t stream);
+/* the same reduction with two destinations: columns [0, cols0) -> out0, [cols0, cols0 + cols1) -> out1 */
+int b200_colsum_finish2(const float* part, long long part_ld, int nparts, int cols0, float* out0, int round0, int cols1,
+                        float* out1, int round1, int accumulate, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention on the PACKED qkv tensor, replaces the split/permute/contiguous copies at

@@ -97,6 +97,17 @@ def test_layernorm_bwd(rows, dim, with_res):
     assert torch.equal(dxb, dx.to(torch.bfloat16))
     assert _relerr(dg, g.grad) < 1e-5
     assert _relerr(db, b.grad) < 1e-5
+    # fused bias gradient: bf16-rounded column sums of the bf16 dx (what a separate colsum pass over dx_bf16 returns)
+    dxs = torch.full((dim,), 7.0, device=DEV)
+    dxb2 = torch.empty_like(dxb)
+    dg2, db2 = torch.empty_like(dg), torch.empty_like(db)
+    ops.layernorm_bwd(dy, x.detach(), g.detach(), mean, rstd, rows=rows, dim=dim, ld_x=dim, dres=dres, dx_out=dx,
+                      ld_dx=dim, dx_bf16=dxb2, dgamma=dg2, dbeta=db2, dx_colsum=dxs)
+    assert torch.equal(dxb2, dxb)
+    assert _relerr(dg2, g.grad) < 1e-5 and _relerr(db2, b.grad) < 1e-5
+    ref = dxb.double().sum(0)
+    assert (dxs.double() - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-6
+    assert torch.equal(dxs, dxs.to(torch.bfloat16).float())
 
 
 @pytest.mark.parametrize("rows,cols", [(50432 // 4, 2304), (1000, 768), (256, 1000), (7, 3072)])
