@@ -41,9 +41,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 // instruction; instead the rows are transposed through a warp-private staging area (NCH * 1 KB, 16-byte chunks
 // XOR-swizzled so both passes are bank-conflict free) and written with whole rows per group of lanes.
 // `g0` addresses (row 0, first column); rows >= rows_valid are skipped.
-template <int NCH>
+// COLSUM (NCH == 4 only): csum[0..63] receives the fp32 column sums of the valid bf16 rows written (bias gradients).
+template <int NCH, bool COLSUM = false>
 __device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, __nv_bfloat16* g0, long long row_stride, uint32_t taddr,
-                                                     float sc, int rows_valid, int lane) {
+                                                     float sc, int rows_valid, int lane, float* csum = nullptr) {
     constexpr int CPR = NCH * 2;    // 16-byte chunks per row
     constexpr int RB = NCH * 32;    // bytes per row
     constexpr int RPI = 32 / CPR;   // rows written per store instruction
@@ -68,13 +69,32 @@ __device__ __forceinline__ void store_rows_coalesced(uint8_t* stage, __nv_bfloat
         *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c + 1) ^ sw) << 4)) = o1;
     }
     __syncwarp();
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int it = 0; it < CPR; ++it) {
         const int row = it * RPI + lane / CPR;
         const uint32_t ch = ul % CPR;
         const uint32_t rsw = NCH == 4 ? (static_cast<uint32_t>(row) & 7u) : ((static_cast<uint32_t>(row) >> 1) & 3u);
         const uint4 val = *reinterpret_cast<const uint4*>(stage + row * RB + ((ch ^ rsw) << 4));
-        if (row < rows_valid) *reinterpret_cast<uint4*>(g0 + row * row_stride + ch * 8) = val;
+        if (row < rows_valid) {
+            *reinterpret_cast<uint4*>(g0 + row * row_stride + ch * 8) = val;
+            if constexpr (COLSUM) {
+                acc[0] += bf16lo(val.x); acc[1] += bf16hi(val.x); acc[2] += bf16lo(val.y); acc[3] += bf16hi(val.y);
+                acc[4] += bf16lo(val.z); acc[5] += bf16hi(val.z); acc[6] += bf16lo(val.w); acc[7] += bf16hi(val.w);
+            }
+        }
+    }
+    if constexpr (COLSUM) {
+        static_assert(!COLSUM || NCH == 4, "column sums are implemented for 64-column tiles");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // lanes l, l^8, l^16, l^24 hold the same 8 columns of different rows
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+            acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+        }
+        if (lane < 8) {
+            reinterpret_cast<float4*>(csum + lane * 8)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            reinterpret_cast<float4*>(csum + lane * 8)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
     __syncwarp();
 }
@@ -102,7 +122,9 @@ __global__ void __launch_bounds__(AF_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment as an OFFSET from the __shared__ array: a round trip through an integer hides the address space
+    // from the compiler and turns every staging access into a generic LD / ST (long-scoreboard latency)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem + AF_SQ;
     uint8_t* sK = smem + AF_SK;
     uint8_t* sP = smem + AF_SP;
@@ -272,7 +294,8 @@ constexpr int AB_SP = 131072;   // 32 KB: P  [128 q x 128 keys] as two 64-key bl
 constexpr int AB_SDS = 163840;  // 32 KB: dS
 constexpr int AB_LSE = 196608;  // 256 floats
 constexpr int AB_DELTA = AB_LSE + 1024;
-constexpr int AB_BAR = AB_DELTA + 1024;
+constexpr int AB_CSUM = AB_DELTA + 1024;  // 24 x 64 floats: column sums of dQ / dK / dV per (tile, lane quadrant)
+constexpr int AB_BAR = AB_CSUM + 24 * 64 * 4;
 constexpr int AB_SMEM = AB_BAR + 128 + 1024;
 
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DK = 256, TM_DV = 320, TM_DQ = 384;
@@ -280,9 +303,13 @@ constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DK = 256, TM_DV = 320, TM_DQ = 384;
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
-                const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, const AttnParams p) {
+                const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_part,
+                const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment as an OFFSET from the __shared__ array: a round trip through an integer hides the address space
+    // from the compiler and turns every staging access into a generic LD / ST (long-scoreboard latency)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* csum = reinterpret_cast<float*>(smem + AB_CSUM);
     uint8_t* sQ = smem + AB_SQ;
     uint8_t* sDO = smem + AB_SDO;
     uint8_t* sK = smem + AB_SK;
@@ -420,6 +447,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
             lse_s[irow] = has_row ? ls * kLog2e : INFINITY;  // padded query rows: exp2(s - inf) = 0 -> P = dS = 0 for free
             delta_s[irow] = dl;
+            for (int k = irow; k < 24 * 64; k += 256) csum[k] = 0.f;  // (slots of absent tiles stay zero)
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const uint32_t q = static_cast<uint32_t>(warp & 3);
@@ -497,8 +525,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     tc_fence_after_sync();
                     const int key0 = kt * 128 + static_cast<int>(q) * 32;
                     __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + key0) * D3 + h * 64;
-                    if (ch == 0) store_rows_coalesced<4>(stage, g0 + p.D, D3, taddr + TM_DK, p.scale, p.T - key0, lane);
-                    else         store_rows_coalesced<4>(stage, g0 + 2 * p.D, D3, taddr + TM_DV, 1.0f, p.T - key0, lane);
+                    float* cs = csum + ((1 + ch) * 8 + kt * 4 + static_cast<int>(q)) * 64;
+                    if (ch == 0) store_rows_coalesced<4, true>(stage, g0 + p.D, D3, taddr + TM_DK, p.scale, p.T - key0, lane, cs);
+                    else         store_rows_coalesced<4, true>(stage, g0 + 2 * p.D, D3, taddr + TM_DV, 1.0f, p.T - key0, lane, cs);
                     tc_fence_before_sync();
                     mbar_arrive(bar_kvfree);
                     // the next key tile's P / dS chunks of another warp may land in this warp's staging rows
@@ -510,7 +539,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (ch < n_mt) {
             const int row0 = ch * 128 + static_cast<int>(q) * 32;
             __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + row0) * D3 + h * 64;
-            store_rows_coalesced<4>(stage, g0, D3, taddr + TM_DQ + static_cast<uint32_t>(ch * 64), p.scale, p.T - row0, lane);
+            store_rows_coalesced<4, true>(stage, g0, D3, taddr + TM_DQ + static_cast<uint32_t>(ch * 64), p.scale, p.T - row0, lane,
+                                          csum + (ch * 4 + static_cast<int>(q)) * 64);
+        }
+        if (dbias_part != nullptr) {
+            // per-(batch, head) column sums of dq | dk | dv in a fixed order: the qkv-bias gradient is their sum over the batch
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (irow < 192) {
+                const int sec = irow >> 6, c = irow & 63;
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += csum[(sec * 8 + k) * 64 + c];
+                dbias_part[static_cast<long long>(b) * D3 + sec * p.D + h * 64 + c] = t;
+            }
         }
     }
     tc_fence_before_sync();
@@ -560,7 +601,7 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
 
 extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
                                   void* dqkv_bf16, int B, int T, int H, int Dh, float scale, int causal,
-                                  cudaStream_t stream) {
+                                  float* dbias_part, cudaStream_t stream) {
     int rc = attn_check(B, T, H, Dh);
     if (rc) return rc;
     const int D = H * 64;
@@ -587,6 +628,6 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
     attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                             reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
-                                                            reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), p);
+                                                            reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
     return check_launch("attention_bwd");
 }

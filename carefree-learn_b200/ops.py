@@ -192,13 +192,20 @@ def attention_fwd(qkv: Tensor, B: int, T: int, H: int, *, scale: Optional[float]
     return out, lse
 
 
-def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, B: int, T: int, H: int, *, scale: Optional[float] = None, causal: bool = False, dqkv: Optional[Tensor] = None) -> Tensor:
+def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, B: int, T: int, H: int, *, scale: Optional[float] = None, causal: bool = False, dqkv: Optional[Tensor] = None,
+                  dbias: Optional[Tensor] = None) -> Tensor:
+    """dqkv (bf16 [B*T, 3*H*64]).  ``dbias`` (fp32 [3*H*64]): also receives the bf16-rounded column sums of dqkv -- the
+    gradient of the packed qkv bias -- accumulated inside the kernel (no separate pass over dqkv)."""
     _need_cuda(qkv, out, dout, lse)
     D = H * 64
     if dqkv is None:
         dqkv = torch.empty((B * T, 3 * D), dtype=torch.bfloat16, device=qkv.device)
     sc = float(scale) if scale is not None else 0.125
-    call("b200_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, 64, sc, int(causal), _stream())
+    part = WORKSPACE.get(qkv.device, B * 3 * D, "attn_dbias") if dbias is not None else None
+    call("b200_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, T, H, 64, sc, int(causal),
+         _ptr(part), _stream())
+    if dbias is not None:
+        call("b200_colsum_finish", part.data_ptr(), 3 * D, B, 3 * D, dbias.data_ptr(), 1, 0, _stream())
     return dqkv
 
 

@@ -294,10 +294,9 @@ class ViTEngine:
             # attention: mid = net + Wo attn + bo
             dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
             ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
-            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H)
+            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H, dbias=A.g(b + "token_mixing.net.qkv_bias", G))
             dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
             ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
-            self._bias_grad(dqkv, A.g(b + "token_mixing.net.qkv_bias", G))
             self._join_side()  # dnet_bf is overwritten below, and this block's bias gradients must be complete
             ops.layernorm_bwd(dln1, net, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D, dres=dmid,
                               dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,

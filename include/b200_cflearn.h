@@ -118,8 +118,11 @@ int b200_colsum_finish2(const float* part, long long part_ld, int nparts, int co
  * --------------------------------------------------------------------------------------------------------- */
 int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int H, int Dh, float scale,
                        int causal, cudaStream_t stream);
+/* dbias_part (optional, f32 [B, 3*H*Dh]): per-image column sums of the bf16 dqkv rows written; summed over the batch
+ * (b200_colsum_finish, nparts = B) they are the gradient of the packed qkv bias (attentions.py:112-119). */
 int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
-                       void* dqkv_bf16, int B, int T, int H, int Dh, float scale, int causal, cudaStream_t stream);
+                       void* dqkv_bf16, int B, int T, int H, int Dh, float scale, int causal, float* dbias_part,
+                       cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Patch embedding glue (cflearn/modules/core/high_level.py:143-149,181-188, mixed_stacks/api.py:419-438):

@@ -361,3 +361,10 @@ def test_attention_bwd(B, T, H, causal):
     o2 = F.scaled_dot_product_attention(q, k, v, is_causal=causal).permute(0, 2, 1, 3).reshape(B * T, D)
     o2.backward(dout)
     assert _relerr(dqkv, q2.grad) < 1.5e-2
+    # fused qkv-bias gradient: bf16-rounded column sums of the dqkv just written
+    dbias = torch.full((3 * D,), 3.0, device=DEV)
+    dqkv2 = ops.attention_bwd(qkv, out, dout, lse, B, T, H, causal=causal, dbias=dbias)
+    assert torch.equal(dqkv2, dqkv)
+    ref_b = dqkv.double().sum(0)
+    assert (dbias.double() - ref_b).abs().max().item() <= 2.0 ** -8 * ref_b.abs().max().item() + 1e-6
+    assert torch.equal(dbias, dbias.to(torch.bfloat16).float())
