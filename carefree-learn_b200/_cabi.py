@@ -44,6 +44,11 @@ SIGNATURES: Dict[str, Any] = {
     "b200_colsum_finish2": (c_int, [_P, _LL, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P]),
     "b200_attention_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "b200_attention_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P]),
+    "b200_fcnn_step": (
+        c_int,
+        [_P, _P, _P, _P, _P, _P, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, c_int, c_float, c_float,
+         POINTER(c_int), _P],
+    ),
     "b200_patch_im2col": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),

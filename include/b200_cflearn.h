@@ -125,6 +125,20 @@ int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d
                        cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * FCNN (cflearn/modules/ml/fcnn.py:12-59: Mapping(Linear + ReLU) x n, then nn.Linear) -- one launch per training
+ * step, fp32, for networks whose parameters + activations of 128 samples fit in shared memory (BASELINE.json
+ * configs[0]: 10 -> 32 -> 32 -> 1).  dims[0..n_layers] are the widths (host array); W_l ([dims[l+1], dims[l]],
+ * row-major like nn.Linear.weight) and b_l live at w_offsets[l] / b_offsets[l] (floats, -1 = no bias) inside the flat
+ * fp32 `params` arena of arena_len floats.  pred (optional): [M, dims[n]].  part == NULL: inference only.  Otherwise
+ * part[nblocks, arena_len + 1] receives per-128-sample gradient partials in arena layout (b200_colsum_finish sums
+ * them) and, in column arena_len, the loss partial.  loss_mode 1: w_mae * mean|p - y| + w_mse * mean (p - y)^2
+ * ("multi_task" of "mae" + "mse", losses/basic.py:45-61, losses/common.py:72-88); loss_mode 0: dpred [M, dims[n]] is
+ * the gradient of the output (autograd's backward).  *nblocks_out (host int) = number of partial rows written. */
+int b200_fcnn_step(const float* x, const float* y, const float* dpred, const float* params, float* pred, float* part,
+                   int M, int n_layers, const int* dims, const int* w_offsets, const int* b_offsets, int arena_len,
+                   int loss_mode, float w_mae, float w_mse, int* nblocks_out, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Patch embedding glue (cflearn/modules/core/high_level.py:143-149,181-188, mixed_stacks/api.py:419-438):
  *   im2col : x f32 [B, C, IMG, IMG] (NCHW) -> cols bf16 [B*(IMG/P)^2, C*P*P]  (k index = (c, ky, kx))
  *   assemble: net f32 [B, 1+np, D] = cat(cls, float(patch bf16 [B*np, D])) + pos[1+np, D]

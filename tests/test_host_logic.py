@@ -67,6 +67,22 @@ def test_registry_semantics_mirror_reference():
             registry.build_module("encoders.vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, **bad))
 
 
+def test_fcnn_surface_mirrors_reference():
+    # registry name, constructor defaults (fcnn.py:29-31), state_dict keys (golden fixture from the real reference)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "fcnn_reference.pt"))
+    m = registry.build_module("fcnn", config=dict(input_dim=10, output_dim=1, not_a_kwarg=1))
+    assert list(m.state_dict().keys()) == g["keys"] and m.hidden_units == [32, 32]
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [(32, 10), (32,), (32, 32), (32,), (1, 32), (1,)]
+    assert registry.build_module("fcnn", input_dim=600, output_dim=3).hidden_units == [1024, 1024]
+    assert list(registry.build_module("fcnn", input_dim=4, output_dim=2, bias=False).state_dict()) == [
+        "net.0.linear.linear.weight", "net.1.linear.linear.weight", "net.2.weight"]
+    for bad in (dict(batch_norm=True), dict(dropout=0.3), dict(activation="GELU"), dict(mapping_type="res"), dict(rank=4)):
+        with pytest.raises(NotImplementedError):
+            registry.build_module("fcnn", input_dim=10, output_dim=1, **bad)
+    with pytest.raises(cflearn_b200.B200Error):
+        m(torch.randn(4, 10))  # CPU tensor: no fallback
+
+
 def test_param_arena_views_and_state_dict_roundtrip():
     m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=16, img_size=32, latent_dim=128, encoder="vit",
                                                     encoder_config=dict(patch_size=16, num_layers=2)))

@@ -219,3 +219,59 @@ def test_two_gpu_bucketed_allreduce_matches_single_process():
          "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")],
         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and "dp_check: world 2" in res.stdout, res.stdout[-2000:]
+
+
+# ---- FCNN (BASELINE.json configs[0]; reference: modules/ml/fcnn.py + multi_task[mae, mse]) --------------------------
+@pytest.mark.gpu
+def test_fcnn_step_matches_reference_golden_and_oracle():
+    """fp32 fused FCNN step vs (1) the golden vectors written from the REAL reference on the toy batch and (2) the fp32
+    oracle on 1000 rows (8 blocks, ragged tail).  Tolerance 1e-5 relative (fp32, different summation order)."""
+    import fcnn_oracle as fo
+
+    dev = torch.device("cuda", 0)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "fcnn_reference.pt"))
+    sd = fo.init_state_dict(10, 1, seed=g["weights_seed"])
+    m = registry.build_module("fcnn", config=dict(input_dim=10, output_dim=1)).to(dev)
+    m.load_state_dict(sd, strict=True)
+
+    def rel(a, b):
+        return ((a.detach().cpu().double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+    loss, pred = m.train_step(g["x"].to(dev), g["y"].to(dev))
+    assert rel(pred, g["pred"]) < 1e-5 and abs(loss.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
+    for k, p in m.named_parameters():
+        assert rel(p.grad, g["grads"][k]) < 1e-5, k
+    # plain forward (inference) and the autograd route with a user-side loss
+    with torch.no_grad():
+        assert rel(m(g["x"].to(dev)), g["pred"]) < 1e-5
+    for p in m.parameters():
+        p.grad = None
+    out = m(g["x"].to(dev))
+    yd = g["y"].to(dev)
+    (torch.nn.functional.l1_loss(out, yd) + torch.nn.functional.mse_loss(out, yd)).backward()
+    for k, p in m.named_parameters():
+        assert rel(p.grad, g["grads"][k]) < 1e-5, k
+    # 1000 rows: 8 blocks of 128 with a ragged tail, against the oracle
+    x_all, y_all = fo.toy_data()
+    o_loss, o_pred, o_grads = fo.train_step(sd, x_all, y_all)
+    loss, pred = m.train_step(x_all.to(dev), y_all.to(dev))
+    assert rel(pred, o_pred) < 1e-5 and abs(loss.item() - o_loss.item()) < 1e-5 * abs(o_loss.item())
+    for k, p in m.named_parameters():
+        assert rel(p.grad, o_grads[k]) < 2e-5, k
+    # a wider / deeper network with 3 outputs and no bias
+    sd2 = fo.init_state_dict(7, 3, hidden=[48, 64, 16], seed=3)
+    sd2 = {k: v for k, v in sd2.items() if not k.endswith("bias")}
+    m2 = registry.build_module("fcnn", input_dim=7, output_dim=3, hidden_units=[48, 64, 16], bias=False).to(dev)
+    m2.load_state_dict(sd2, strict=True)
+    x2, y2 = torch.randn(300, 7), torch.randn(300, 3)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd2.items()}
+    net = x2
+    for i in range(3):
+        net = torch.relu(net @ params[f"net.{i}.linear.linear.weight"].t())
+    ref_pred = net @ params["net.3.weight"].t()
+    ref_loss = (ref_pred - y2).abs().mean() + ((ref_pred - y2) ** 2).mean()
+    ref_loss.backward()
+    loss, pred = m2.train_step(x2.to(dev), y2.to(dev))
+    assert rel(pred, ref_pred.detach()) < 1e-5 and abs(loss.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+    for k, p in m2.named_parameters():
+        assert rel(p.grad, params[k].grad) < 2e-5, k

@@ -62,3 +62,30 @@ def test_live_pin_against_reference():
     make_golden.known_answer_attention()
     make_golden.pin("vit_tiny", 2, False)
     make_golden.pin("vit_tiny", 2, True)
+
+
+# ---- FCNN (BASELINE.json configs[0]) ----------------------------------------------------------------------------
+def test_fcnn_oracle_matches_reference_golden():
+    """oracle/fcnn_oracle.py vs the fixture written from the REAL reference FCNN + MAELoss + MSELoss (bit-exact)."""
+    import fcnn_oracle as fo
+
+    torch.set_num_threads(1)
+    g = torch.load(os.path.join(GOLDEN, "fcnn_reference.pt"))
+    assert g["keys"] == [k for k, _ in fo.state_dict_spec(10, 1)]
+    x_all, y_all = fo.toy_data()
+    assert torch.equal(x_all[:128], g["x"]) and torch.equal(y_all[:128], g["y"])  # examples/ml/simple/toy.py recipe
+    sd = fo.init_state_dict(10, 1, seed=g["weights_seed"])
+    loss, pred, grads = fo.train_step(sd, g["x"], g["y"])
+    assert torch.equal(pred, g["pred"])
+    assert torch.equal(loss, g["loss"])
+    assert abs((g["mae"] + g["mse"]).item() - g["loss"].item()) <= 1e-6 * abs(g["loss"].item())
+    for k, v in g["grads"].items():
+        assert torch.equal(grads[k], v), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_fcnn_live_pin_against_reference(tmp_path, monkeypatch):
+    import make_golden_fcnn
+
+    monkeypatch.setattr(make_golden_fcnn, "GOLDEN", str(tmp_path))
+    make_golden_fcnn.main()
