@@ -30,7 +30,8 @@ namespace b200 {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;      // 1-CTA / multicast modes: 4 x (A 16 KB + B 32 KB)
+constexpr int STAGES_2SM = 6;  // cta_group::2: each CTA stores only its half of B -> 6 x (16 + 16 KB) in the same 192 KB
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int MN_BOX_BYTES = 64 * BK * 2;   // one MN-major TMA box: 64 (MN) x 64 (K) bf16 = 8 KB
@@ -40,8 +41,8 @@ constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
 
 constexpr int SMEM_A_OFF = 0;
-constexpr int SMEM_B_OFF = SMEM_A_OFF + STAGES * A_STAGE_BYTES;
-constexpr int SMEM_EPI_OFF = SMEM_B_OFF + STAGES * B_STAGE_BYTES;
+constexpr int SMEM_EPI_OFF = SMEM_A_OFF + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+static_assert(STAGES_2SM * (A_STAGE_BYTES + B_STAGE_BYTES / 2) == STAGES * (A_STAGE_BYTES + B_STAGE_BYTES), "both ring layouts must end at SMEM_EPI_OFF");
 constexpr int SMEM_BIAS_OFF = SMEM_EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;  // per epilogue warp: bias of its 128 columns
 constexpr int EPI_BIAS_BYTES = 256;
 constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + NUM_EPI_WARPS * EPI_BIAS_BYTES;
@@ -97,15 +98,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // from the compiler and turns every staging access into a generic LD / ST (long-scoreboard latency)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem + SMEM_A_OFF;
-    uint8_t* sB = smem + SMEM_B_OFF;
+    // The ring is what hides the L2 -> smem latency: by Little's law an SM needs (bytes per k-block / 512 MMA cycles) x
+    // ~3000 cycles of loaded TMA latency in flight -- 288 KB for 48 KB stages (we have 192 KB: the 1-CTA modes sit at ~65 %
+    // tensor-pipe activity), 187 KB for the 32 KB stages of the 2-SM mode, which is why that mode gets six of them.
+    constexpr int NSTAGE = TWO_SM ? STAGES_2SM : STAGES;
+    constexpr int BSTG = TWO_SM ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+    uint8_t* sB = smem + SMEM_A_OFF + NSTAGE * A_STAGE_BYTES;
     uint8_t* sEpi = smem + SMEM_EPI_OFF;
     if (smem + GEMM_SMEM_USED > smem_raw + GEMM_SMEM_BYTES) {
         if (threadIdx.x == 0) printf("b200 gemm: dynamic shared memory base %p is not 256-byte aligned\n", smem_raw);
         __trap();
     }
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* tmem_full_bar = empty_bar + NSTAGE;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -121,7 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_bar[i], 1);
             // multicast mode: released by the MMA warp of EVERY CTA in the cluster; 2-SM mode: by the leader's commit
             mbar_init(&empty_bar[i], TWO_SM ? 1u : static_cast<uint32_t>(p.cluster));
@@ -159,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-                    uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+                    uint8_t* b_dst = sB + stage * BSTG;
                     if constexpr (TWO_SM) {
                         // cta_group::2: every load of BOTH CTAs is credited to the LEADER's full barrier, which the
                         // leader arms once with the bytes of the whole pair (2 x (A 16 KB + half B 16 KB)).
@@ -180,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < BN / 128; ++i)
                                 tma_load_2d_2sm(b_dst + i * MN_BOX_BYTES, &tmB, lead_full, n0 + (2 * h + i) * 64, kb * BK);
                         }
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
                         continue;
                     }
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
@@ -212,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 tma_load_2d_mcast(b_dst + (2 * h + i) * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + (2 * h + i) * 64, kb * BK, mc_mask);
                         }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -235,7 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
                     const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+                    const uint32_t b_base = smem_u32(sB + stage * BSTG);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         // K-major  : 8-row groups 1024 B apart (SBO); +32 B per 16-element K step.
@@ -256,7 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.cluster > 1) umma_commit_mcast(&empty_bar[stage], mc_mask);
                         else umma_commit(&empty_bar[stage]);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
                 }
                 // accumulator complete -> epilogue (2-SM: each CTA's epilogue owns 128 of the 256 accumulator rows)
                 if constexpr (TWO_SM) umma_commit_2sm_mcast(&tmem_full_bar[as], mc_mask);
@@ -568,7 +574,7 @@ int num_sms() {
     return cached[dev];
 }
 
-static int g_gemm_multicast = 1;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2: CTA pairs + cta_group::2 MMA
+static int g_gemm_multicast = 2;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2 (default): CTA pairs + cta_group::2 MMA, 6-stage ring
 
 template <int EPI, bool TWO_SM>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,

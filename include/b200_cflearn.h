@@ -68,8 +68,10 @@ int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
                    long long ldo, int splits, int max_ctas, cudaStream_t stream);
 /* split count that fills the 148 SMs best for an [M,N] output with reduction length K */
 int b200_gemm_pick_splits(int M, int N, int K);
-/* 1 (default): CTA pairs (thread-block clusters of 2) multicast the shared B tile through TMA; 0: every CTA loads
- * its own operands.  Returns the previous setting.  Results are identical; only L2 traffic differs. */
+/* GEMM cluster mode.  2 (default): CTA pairs (thread-block clusters of 2) issue one 256x256 tcgen05.mma.cta_group::2 per
+ * k-step, each CTA holding its A rows and half of B, six 32 KB ring stages; 1: CTA pairs with one 128x256 MMA each,
+ * the shared B tile TMA-multicast, four 48 KB stages; 0: every CTA loads its own operands.  Returns the previous
+ * setting.  Results are bit-identical in all modes (tests/test_kernels_gpu.py); only speed differs. */
 int b200_set_gemm_multicast(int enable);
 /* out[f32][n] (+)= round( sum_s partial[s][n] ); round_bf16 mirrors autocast (the weight grad of a bf16 matmul
  * is produced in bf16, cf. cflearn/schema.py:1266-1276 autocast + :980 backward). accumulate: 0 overwrite. */
