@@ -87,10 +87,24 @@ __device__ __forceinline__ uint32_t swz64_off(uint32_t row, uint32_t chunk) {  /
     return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
 }
 
+// Epilogue warps per variant.  The bias-only and split-K epilogues hide behind the main loop with 8 warps (2 per scheduler).
+// The GELU / dGELU / fp32-residual epilogues do not: ~19 instructions per element at ~40 % issue efficiency is 7.5 us per
+// tile against a 5.3 us main loop.  They are latency-, not throughput-bound (MUFU 4.1k, FMA 2k, issue 4.9k cycles per tile),
+// so those variants run 16 epilogue warps (4 per scheduler), each owning 32 rows x 64 columns.  B200_EPI16=0 builds the
+// 8-warp epilogue for all variants (A/B timing).
+#ifndef B200_EPI16
+#define B200_EPI16 1
+#endif
+template <int EPI>
+struct EpiWarps {
+    static constexpr int value =
+        (B200_EPI16 && (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_DGELU_BF16)) ? 16 : NUM_EPI_WARPS;
+};
+
 // TWO_SM is a template parameter (not a runtime flag): a kernel image that contains cta_group::2 instructions can only
 // be launched with a cluster size of 2, so the 1-CTA / multicast variants must be separate instantiations.
 template <int EPI, bool TWO_SM>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<EPI>::value, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBh, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -115,6 +129,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+    constexpr int NEPI = EpiWarps<EPI>::value;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // clusters (of 1 or 2 CTAs) stride over the work units; both CTAs of a pair run the same unit sequence
@@ -134,7 +149,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], TWO_SM ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // 2-SM: both CTAs' epilogues report to the leader
+            mbar_init(&tmem_empty_bar[i], TWO_SM ? 2 * NEPI : NEPI);  // 2-SM: both CTAs' epilogues report to the leader
         }
         fence_mbar_init();
     }
@@ -268,6 +283,175 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if constexpr (TWO_SM) umma_commit_2sm_mcast(&tmem_full_bar[as], mc_mask);
                 else umma_commit(&tmem_full_bar[as]);
             }
+        }
+    } else if constexpr (NEPI == 16) {
+        // ===================================== epilogue warps (16-warp variants) ================================
+        // Each warp owns 32 accumulator rows (its TMEM lane quadrant) x 64 columns = 2 chunks of 32 columns.  Same two
+        // phases as below, but ONE 32-register accumulator chunk at a time (the 96-register budget of an 18-warp CTA) and a
+        // 2 KB staging buffer per warp; the TMEM buffer is handed back after the second chunk has been read, i.e. after
+        // half of this warp's work.
+        const int e = warp - 2;               // 0..15
+        const uint32_t q = warp & 3;          // TMEM lane quadrant this warp may access
+        const int part = e >> 2;              // which 64-column quarter of the accumulator
+        uint8_t* stg = sEpi + e * 2048;
+        uint8_t* sbias = smem + SMEM_BIAS_OFF + e * 128;
+        const long long ldo = p.ldo;
+        const int prow = lane >> 2, pch = lane & 3;  // phase-2 coordinates: 8 row groups of 4 lanes, 16 B per lane
+        int lt = 0;
+        for (int u = unit0; u < total_units; u += unit_stride, ++lt) {
+            int m_t, n_t, sp, kb0, kb1;
+            decode_unit(p, u, cta_rank, m_t, n_t, sp, kb0, kb1);
+            const int as = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1u;
+            const int grow0 = m_t * BM + static_cast<int>(q) * 32;
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(as * BN + part * 64);
+            const int gcol0 = n_t * BN + part * 64;
+            const bool interior = (m_t * BM + BM <= p.M) && (n_t * BN + BN <= p.N);
+            auto tile_epilogue = [&](auto interior_tag) {
+            constexpr bool INT = decltype(interior_tag)::value;
+            constexpr int NSLOT = EPI == EPI_BIAS_RESID_F32 ? 1 : 2;  // the fp32 residual is 32 registers per chunk
+            uint4 aux_h[2][4];
+            float4 aux_r[1][4][2];
+            auto load_aux = [&](int cc, int slot) {
+                const int pc = gcol0 + cc * 32 + pch * 8;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = grow0 + it * 8 + prow;
+                    const bool ok = INT || (row < p.M && pc + 8 <= p.N);
+                    if constexpr (EPI == EPI_DGELU_BF16) {
+                        aux_h[slot][it] = make_uint4(0, 0, 0, 0);
+                        if (ok) aux_h[slot][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pc);
+                    }
+                    if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                        aux_r[slot][it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        aux_r[slot][it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) {
+                            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + row * ldo + pc);
+                            aux_r[slot][it][0] = src[0];
+                            aux_r[slot][it][1] = src[1];
+                        }
+                    }
+                }
+            };
+            if constexpr (EPI != EPI_DGELU_BF16) {  // bias of this warp's 64 columns -> 128 B of private smem
+                if (lane < 8) {
+                    const int gc = gcol0 + lane * 8;
+                    uint4 t = make_uint4(0, 0, 0, 0);
+                    if (p.bias != nullptr && (INT || gc < p.N)) t = *reinterpret_cast<const uint4*>(p.bias + gc);
+                    *reinterpret_cast<uint4*>(sbias + lane * 16) = t;
+                }
+                __syncwarp();
+            }
+            if constexpr (EPI != EPI_BIAS_GELU_BF16) {
+                load_aux(0, 0);
+                if constexpr (NSLOT == 2) load_aux(1, 1);
+            }
+            mbar_wait(&tmem_full_bar[as], aph);
+            tc_fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int gcol = gcol0 + c * 32;
+                const int pcol = gcol + pch * 8;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+                tmem_ld_wait();
+                if (c == 1) {  // the accumulator has been read completely by this warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        else mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                }
+                const bool active = INT || ((gcol < p.N) && (grow0 < p.M));  // warp-uniform
+                if (active) {
+                    // ---- phase 1: bf16(acc + bias) -> staging (row-per-thread) ----
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint4 t = make_uint4(0, 0, 0, 0);
+                        if constexpr (EPI != EPI_DGELU_BF16) t = *reinterpret_cast<const uint4*>(sbias + c * 64 + j4 * 16);
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j4 * 8 + 0]) + bf16lo(t.x), __uint_as_float(v[j4 * 8 + 1]) + bf16hi(t.x));
+                        o.y = pack_bf16x2(__uint_as_float(v[j4 * 8 + 2]) + bf16lo(t.y), __uint_as_float(v[j4 * 8 + 3]) + bf16hi(t.y));
+                        o.z = pack_bf16x2(__uint_as_float(v[j4 * 8 + 4]) + bf16lo(t.z), __uint_as_float(v[j4 * 8 + 5]) + bf16hi(t.z));
+                        o.w = pack_bf16x2(__uint_as_float(v[j4 * 8 + 6]) + bf16lo(t.w), __uint_as_float(v[j4 * 8 + 7]) + bf16hi(t.w));
+                        *reinterpret_cast<uint4*>(stg + swz64_off(lane, j4)) = o;
+                    }
+                    __syncwarp();
+                    // ---- phase 2: coalesced layout ----
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + prow;
+                        const int row = grow0 + r;
+                        const uint4 t = *reinterpret_cast<const uint4*>(stg + swz64_off(r, pch));  // 8 x bf16(acc + bias)
+                        if (!INT && row >= p.M) continue;
+                        const bool full = INT || pcol + 8 <= p.N;
+                        const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+                        if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+                            uint32_t gw[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float g0, g1;
+                                gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                gw[k] = pack_bf16x2(g0, g1);
+                            }
+                            __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
+                            __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + row * ldo + pcol;
+                            if (full) {
+                                *reinterpret_cast<uint4*>(d0) = t;
+                                *reinterpret_cast<uint4*>(d1) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+                            } else {
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) {
+                                        d0[k] = __ushort_as_bfloat16(static_cast<unsigned short>(tw[k >> 1] >> ((k & 1) * 16)));
+                                        d1[k] = __ushort_as_bfloat16(static_cast<unsigned short>(gw[k >> 1] >> ((k & 1) * 16)));
+                                    }
+                            }
+                        } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                            float* dst = reinterpret_cast<float*>(p.out0) + row * ldo + pcol;
+                            if (full) {
+                                float4 a = aux_r[0][it][0], b = aux_r[0][it][1];
+                                a.x += bf16lo(tw[0]); a.y += bf16hi(tw[0]); a.z += bf16lo(tw[1]); a.w += bf16hi(tw[1]);
+                                b.x += bf16lo(tw[2]); b.y += bf16hi(tw[2]); b.z += bf16lo(tw[3]); b.w += bf16hi(tw[3]);
+                                reinterpret_cast<float4*>(dst)[0] = a;
+                                reinterpret_cast<float4*>(dst)[1] = b;
+                            } else {
+                                const float* src = reinterpret_cast<const float*>(p.aux) + row * ldo + pcol;
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) dst[k] = src[k] + ((k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]));
+                            }
+                        } else {  // EPI_DGELU_BF16
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
+                            if (full) {
+                                const uint4 hh = aux_h[c][it];
+                                const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w};
+                                uint32_t ow[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float g0, g1;
+                                    gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
+                                    ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                }
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                            } else {
+                                const __nv_bfloat16* hsrc = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * ldo + pcol;
+                                for (int k = 0; k < 8; ++k)
+                                    if (pcol + k < p.N) {
+                                        const float dv = (k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]);
+                                        dst[k] = __float2bfloat16_rn(dv * gelu_erf_grad(__bfloat162float(hsrc[k])));
+                                    }
+                            }
+                        }
+                    }
+                    __syncwarp();  // the single staging buffer is rewritten by the next chunk
+                }
+                if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                    if (c == 0) load_aux(1, 0);  // the only residual slot is free again
+                }
+            }
+            };  // tile_epilogue
+            if (interior) tile_epilogue(std::true_type{});
+            else tile_epilogue(std::false_type{});
         }
     } else {
         // ===================================== epilogue warps ===================================
@@ -588,7 +772,7 @@ static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(64 + 32 * EpiWarps<EPI>::value);
     cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
