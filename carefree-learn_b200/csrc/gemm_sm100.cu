@@ -359,7 +359,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) {
-                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        if constexpr (TWO_SM) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
                         else mbar_arrive(&tmem_empty_bar[as]);
                     }
                 }
@@ -670,7 +670,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) {
-                        if constexpr (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
+                        if constexpr (TWO_SM) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // leader's barrier
                         else mbar_arrive(&tmem_empty_bar[as]);
                     }
                 }

@@ -120,6 +120,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same without release semantics.  A cluster-scope RELEASE makes the warp drain every global store it has in flight
+// first (ERRBAR + membar: 22 % of the GELU GEMM's stall samples in 2-SM mode).  Handing a TMEM accumulator back needs
+// no memory ordering at all: the reads have completed (tcgen05.wait::ld) and tcgen05.fence::before_thread_sync orders
+// them against the arrive; nothing is communicated through memory.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the bytes are credited to the mbarrier
 // at `bar_cluster_addr` (the pair leader's barrier)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
