@@ -65,6 +65,7 @@ struct GemmParams {
     void* out1;
     const void* aux;
     long long ldo;
+    int act;  // GELU / dGELU epilogues: 0 = exact erf GELU (nn.GELU()), 1 = QuickGELU x * sigmoid(1.702 x) (activations.py:151-153)
 };
 
 // Work unit u (per cluster) -> (m tile of THIS CTA, n tile, split, k-block range).  With cluster == 2 the two CTAs of
@@ -392,7 +393,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 float g0, g1;
-                                gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                if (p.act == 0) {
+                                    gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                } else {
+                                    g0 = quick_gelu_bf16(bf16lo(tw[k]));
+                                    g1 = quick_gelu_bf16(bf16hi(tw[k]));
+                                }
                                 gw[k] = pack_bf16x2(g0, g1);
                             }
                             __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
@@ -428,9 +434,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 uint32_t ow[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float g0, g1;
-                                    gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
-                                    ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                    if (p.act == 0) {
+                                        float g0, g1;
+                                        gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
+                                        ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                    } else {
+                                        ow[k] = pack_bf16x2(quick_gelu_bf16_grad(bf16lo(hw[k]), bf16lo(tw[k])),
+                                                            quick_gelu_bf16_grad(bf16hi(hw[k]), bf16hi(tw[k])));
+                                    }
                                 }
                                 *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                             } else {
@@ -438,7 +449,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int k = 0; k < 8; ++k)
                                     if (pcol + k < p.N) {
                                         const float dv = (k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]);
-                                        dst[k] = __float2bfloat16_rn(dv * gelu_erf_grad(__bfloat162float(hsrc[k])));
+                                        const float hv = __bfloat162float(hsrc[k]);
+                                        dst[k] = __float2bfloat16_rn(p.act == 0 ? dv * gelu_erf_grad(hv) : quick_gelu_bf16_grad(hv, dv));
                                     }
                             }
                         }
@@ -610,7 +622,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 float g0, g1;
-                                gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                if (p.act == 0) {
+                                    gelu_erf2(bf16lo(tw[k]), bf16hi(tw[k]), g0, g1);
+                                } else {
+                                    g0 = quick_gelu_bf16(bf16lo(tw[k]));
+                                    g1 = quick_gelu_bf16(bf16hi(tw[k]));
+                                }
                                 gw[k] = pack_bf16x2(g0, g1);
                             }
                             __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * ldo + pcol;
@@ -646,9 +663,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 uint32_t ow[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float g0, g1;
-                                    gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
-                                    ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                    if (p.act == 0) {
+                                        float g0, g1;
+                                        gelu_erf_grad2(bf16lo(hw[k]), bf16hi(hw[k]), g0, g1);
+                                        ow[k] = pack_bf16x2(bf16lo(tw[k]) * g0, bf16hi(tw[k]) * g1);
+                                    } else {
+                                        ow[k] = pack_bf16x2(quick_gelu_bf16_grad(bf16lo(hw[k]), bf16lo(tw[k])),
+                                                            quick_gelu_bf16_grad(bf16hi(hw[k]), bf16hi(tw[k])));
+                                    }
                                 }
                                 *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                             } else {
@@ -656,7 +678,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 for (int k = 0; k < 8; ++k)
                                     if (pcol + k < p.N) {
                                         const float dv = (k & 1) ? bf16hi(tw[k >> 1]) : bf16lo(tw[k >> 1]);
-                                        dst[k] = __float2bfloat16_rn(dv * gelu_erf_grad(__bfloat162float(hsrc[k])));
+                                        const float hv = __bfloat162float(hsrc[k]);
+                                        dst[k] = __float2bfloat16_rn(p.act == 0 ? dv * gelu_erf_grad(hv) : quick_gelu_bf16_grad(hv, dv));
                                     }
                             }
                         }
@@ -832,6 +855,9 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
                               int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
                               void* out1, const void* aux, long long ldo, int splits, int max_ctas,
                               cudaStream_t stream) {
+    int act = 0;  // the QuickGELU epilogues are the GELU / dGELU kernels with another activation
+    if (epilogue == B200_EPI_BIAS_QGELU_BF16) { epilogue = EPI_BIAS_GELU_BF16; act = 1; }
+    if (epilogue == B200_EPI_DQGELU_BF16) { epilogue = EPI_DGELU_BF16; act = 1; }
     if (M <= 0 || N <= 0 || K <= 0) return set_error(B200_ERR_ARG, "gemm: non-positive dimension");
     // N need not be a multiple of 8: the bias is read in 16-byte groups (readable up to roundup(N, 8) elements) and the
     // TMA store clips columns >= N; the leading dimension must keep rows 16-byte aligned (checked in make_tmap).
@@ -874,6 +900,7 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
             return set_error(B200_ERR_ARG, "gemm: epilogue needs a 16-byte aligned aux");
     }
     GemmParams p;
+    p.act = act;
     p.M = M; p.N = N; p.K = K;
     p.num_m_tiles = (M + BM - 1) / BM;
     p.num_n_tiles = (N + BN - 1) / BN;

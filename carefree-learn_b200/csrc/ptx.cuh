@@ -437,11 +437,29 @@ __device__ __forceinline__ void gelu_erf_grad2(float x0, float x1, float& g0, fl
     upk2(fma2(mul2(pk2(x0, x1), pk2(0.39894228040143267794f, 0.39894228040143267794f)), e, cdf), g0, g1);
 }
 
-// CLIP's QuickGELU: x * sigmoid(1.702 x)
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
-__device__ __forceinline__ float quick_gelu_grad(float x) {
-    float s = 1.0f / (1.0f + expf(-1.702f * x));
-    return s + x * 1.702f * s * (1.0f - s);
+// CLIP's QuickGELU (cflearn/modules/core/activations.py:151-153): `net * torch.sigmoid(1.702 * net)` on a bf16 tensor.
+// Eager runs three elementwise kernels, each rounding its output to bf16; the same three roundings are made here.
+__device__ __forceinline__ float fast_sigmoid(float x) {  // 1 / (1 + 2^(-x log2 e)); fp32 accuracy ~1e-7 relative
+    return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float quick_gelu_bf16(float x) {  // x: a bf16 value
+    const float t = bf16_round(1.702f * x);
+    const float sg = bf16_round(fast_sigmoid(t));
+    return x * sg;  // (the caller rounds the product to bf16)
+}
+// autograd of the same three ops, with eager's bf16 rounding after every backward kernel (dy, x: bf16 values):
+//   mul:      d_net1 = bf16(dy * s),  d_s = bf16(dy * x)            s = bf16(sigmoid(t)), t = bf16(1.702 x)
+//   sigmoid:  d_t = bf16(d_s * (1 - s) * s)
+//   scale:    d_net2 = bf16(d_t * 1.702)
+//   sum:      bf16(d_net1 + d_net2)   (the caller rounds the sum)
+__device__ __forceinline__ float quick_gelu_bf16_grad(float x, float dy) {
+    const float t = bf16_round(1.702f * x);
+    const float sg = bf16_round(fast_sigmoid(t));
+    const float d1 = bf16_round(dy * sg);
+    const float ds = bf16_round(dy * x);
+    const float dt = bf16_round(ds * (1.0f - sg) * sg);
+    const float d2 = bf16_round(dt * 1.702f);
+    return d1 + d2;
 }
 
 }  // namespace b200

@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // bias gradient of the Linear whose dY this dx is (it used to be a separate pass over dx_bf16).  These partials are
 // accumulated in each warp's private shared-memory row: 24 more accumulator registers would break the 128 budget.
 // ------------------------------------------------------------------------------------------------
-template <int NV, bool DXSUM>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+// DYF32: dy is fp32 (a LayerNorm whose output is the fp32 residual stream itself, e.g. CLIP's embedding_norm) instead of bf16.
+template <int NV, bool DXSUM, bool DYF32>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const void* __restrict__ dy_any,
                                                                const float* __restrict__ x, long long ld_x,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ mean_in,
@@ -148,16 +149,19 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     const float fn = static_cast<float>(dim);
     for (int row = blockIdx.x * warps_per_block + wib; row < rows; row += gridDim.x * warps_per_block) {
         const float* xr = x + static_cast<long long>(row) * ld_x;
-        const __nv_bfloat16* dyr = dy + static_cast<long long>(row) * dim;
+        const __nv_bfloat16* dyr = reinterpret_cast<const __nv_bfloat16*>(dy_any) + static_cast<long long>(row) * dim;
+        const float* dyr32 = reinterpret_cast<const float*>(dy_any) + static_cast<long long>(row) * dim;
         const float* rr = dres != nullptr ? dres + static_cast<long long>(row) * ld_dx : nullptr;
         float4 xv[NV], rv[NV];
         uint2 dv[NV];
+        float4 dv32[DYF32 ? NV : 1];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {  // issue every load of this row before touching any of them
             const int c = (lane + 32 * i) * 4;
             if (c < dim) {
                 xv[i] = *reinterpret_cast<const float4*>(xr + c);
-                dv[i] = *reinterpret_cast<const uint2*>(dyr + c);
+                if constexpr (DYF32) dv32[i] = *reinterpret_cast<const float4*>(dyr32 + c);
+                else dv[i] = *reinterpret_cast<const uint2*>(dyr + c);
                 rv[i] = rr != nullptr ? *reinterpret_cast<const float4*>(rr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -169,7 +173,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
             const int c = (lane + 32 * i) * 4;
             if (c < dim) {
                 const float4 g = *reinterpret_cast<const float4*>(gamma + c);  // L1-resident
-                const float d0 = bf16lo(dv[i].x), d1 = bf16hi(dv[i].x), d2 = bf16lo(dv[i].y), d3 = bf16hi(dv[i].y);
+                float d0, d1, d2, d3;
+                if constexpr (DYF32) { d0 = dv32[i].x; d1 = dv32[i].y; d2 = dv32[i].z; d3 = dv32[i].w; }
+                else { d0 = bf16lo(dv[i].x); d1 = bf16hi(dv[i].x); d2 = bf16lo(dv[i].y); d3 = bf16hi(dv[i].y); }
                 xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd);
                 const float g0 = d0 * g.x, g1 = d1 * g.y, g2 = d2 * g.z, g3 = d3 * g.w;
                 s1 += (g0 + g1) + (g2 + g3);
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
             const int c = (lane + 32 * i) * 4;
             if (c < dim) {
                 const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-                const float d0 = bf16lo(dv[i].x), d1 = bf16hi(dv[i].x), d2 = bf16lo(dv[i].y), d3 = bf16hi(dv[i].y);
+                float d0, d1, d2, d3;
+                if constexpr (DYF32) { d0 = dv32[i].x; d1 = dv32[i].y; d2 = dv32[i].z; d3 = dv32[i].w; }
+                else { d0 = bf16lo(dv[i].x); d1 = bf16hi(dv[i].x); d2 = bf16lo(dv[i].y); d3 = bf16hi(dv[i].y); }
                 float4 o;
                 o.x = (fn * (d0 * g.x) - s1 - xv[i].x * s2) * term + rv[i].x;
                 o.y = (fn * (d1 * g.y) - s1 - xv[i].y * s2) * term + rv[i].y;
@@ -545,15 +553,15 @@ static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, con
                                                      mean, rstd, rows, dim, eps);
     return check_launch("layernorm_fwd");
 }
-template <int NV, bool DXSUM>
+template <int NV, bool DXSUM, bool DYF32>
 static int ln_bwd_launch2(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
                           const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
                           float* part, int nparts, int rows, int dim, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(8) * (DXSUM ? 3 : 2) * dim * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(layernorm_bwd_kernel<NV, DXSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaFuncSetAttribute(layernorm_bwd_kernel<NV, DXSUM, DYF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     }
-    layernorm_bwd_kernel<NV, DXSUM><<<nparts, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, ld_x, gamma, mean,
+    layernorm_bwd_kernel<NV, DXSUM, DYF32><<<nparts, 256, smem, st>>>(dy, x, ld_x, gamma, mean,
                                                                rstd, dres, dx_out, ld_dx,
                                                                reinterpret_cast<__nv_bfloat16*>(dx_bf16), part, rows, dim);
     return check_launch("layernorm_bwd");
@@ -561,9 +569,10 @@ static int ln_bwd_launch2(const void* dy, const float* x, long long ld_x, const 
 template <int NV>
 static int ln_bwd_launch(const void* dy, const float* x, long long ld_x, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
-                         float* part, int nparts, int rows, int dim, bool dxsum, cudaStream_t st) {
-    if (dxsum) return ln_bwd_launch2<NV, true>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
-    return ln_bwd_launch2<NV, false>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
+                         float* part, int nparts, int rows, int dim, bool dxsum, bool dyf32, cudaStream_t st) {
+    if (dyf32) return ln_bwd_launch2<NV, false, true>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
+    if (dxsum) return ln_bwd_launch2<NV, true, false>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
+    return ln_bwd_launch2<NV, false, false>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, part, nparts, rows, dim, st);
 }
 
 }  // namespace b200
@@ -585,7 +594,7 @@ extern "C" int b200_layernorm_fwd(const float* x, long long ld_x, const float* g
     return ln_fwd_launch<8>(x, ld_x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, stream);
 }
 
-extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma,
+extern "C" int b200_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, long long ld_x, const float* gamma,
                                   const float* mean, const float* rstd, const float* dres, float* dx_out,
                                   long long ld_dx, void* dx_bf16, float* dgb_part, int max_parts, int* nparts_out,
                                   int rows, int dim, int dx_colsum, cudaStream_t stream) {
@@ -593,6 +602,8 @@ extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long
     if (ld_x % 4 != 0 || ld_dx % 4 != 0) return set_error(B200_ERR_ALIGN, "layernorm_bwd: ld % 4 != 0");
     if (max_parts < 1) return set_error(B200_ERR_ARG, "layernorm_bwd: max_parts < 1");
     if (dx_colsum && dx_bf16 == nullptr) return set_error(B200_ERR_ARG, "layernorm_bwd: dx_colsum needs dx_bf16");
+    if (dx_colsum && dy_is_f32) return set_error(B200_ERR_ARG, "layernorm_bwd: dx_colsum is not offered with an fp32 dy");
+    const bool dyf = dy_is_f32 != 0;
     const bool dxs = dx_colsum != 0;
     int nparts = num_sms() * 2  /* two resident 256-thread blocks per SM: one wave */;
     const int need = (rows + 7) / 8;
@@ -600,9 +611,9 @@ extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long
     if (nparts > max_parts) nparts = max_parts;
     if (nparts_out) *nparts_out = nparts;
     const int nv = (dim + 127) / 128;
-    if (nv <= 4) return ln_bwd_launch<4>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
-    if (nv <= 6) return ln_bwd_launch<6>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
-    return ln_bwd_launch<8>(dy_bf16, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, stream);
+    if (nv <= 4) return ln_bwd_launch<4>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, dyf, stream);
+    if (nv <= 6) return ln_bwd_launch<6>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, dyf, stream);
+    return ln_bwd_launch<8>(dy, x, ld_x, gamma, mean, rstd, dres, dx_out, ld_dx, dx_bf16, dgb_part, nparts, rows, dim, dxs, dyf, stream);
 }
 
 extern "C" int b200_colsum_bf16(const void* x_bf16, long long ld, int rows, int cols, float* part, int max_parts,

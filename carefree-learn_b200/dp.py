@@ -53,10 +53,13 @@ class GradBucketReducer:
                 n *= s
             return lo, hi + (n + 63) // 64 * 64
 
-        self.buckets["stem"] = span(lambda k: k.startswith("to_patches") or k in ("encoder.head_token", "encoder.pos_encoding.pos_encoding"))
+        self.buckets["stem"] = span(lambda k: k.startswith("to_patches") or k.startswith("encoder.embedding_norm.")
+                                    or k in ("encoder.head_token", "encoder.pos_encoding.pos_encoding"))
         for i in range(num_layers):
             self.buckets[i] = span(lambda k, i=i: k.startswith(f"encoder.mixing_blocks.{i}."))
-        self.buckets["tail"] = span(lambda k: k.startswith("encoder.head.") or k.startswith("head.linear"))
+        self.buckets["tail"] = span(lambda k: k.startswith("encoder.head.") or k.startswith("encoder.head_norm.") or k.startswith("head.linear"))
+        if "output_projection" in offs:  # a parameter of the encoder itself: first in state_dict order, written with the tail
+            self.buckets["proj"] = span(lambda k: k == "output_projection")
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._pending: List = []
         self.use_backend_avg = True
@@ -70,6 +73,8 @@ class GradBucketReducer:
         """Bucket ``key`` of the gradient arena ``grad`` is complete on the current stream: start reducing it."""
         if self.world == 1:
             return
+        if key == "tail" and "proj" in self.buckets:
+            self.ready("proj", grad)
         lo, hi = self.buckets[key]
         if grad is None:
             grad = self.arena.grad

@@ -20,6 +20,8 @@ EPI_BIAS_GELU_BF16 = 1
 EPI_BIAS_RESID_F32 = 2
 EPI_DGELU_BF16 = 3
 EPI_PARTIAL_F32 = 4
+EPI_BIAS_QGELU_BF16 = 5  # QuickGELU (CLIP towers) flavours of 1 and 3
+EPI_DQGELU_BF16 = 6
 
 _MAX_PARTS = 1024
 
@@ -159,7 +161,7 @@ def layernorm_bwd(
     part = WORKSPACE.get(x.device, 3 * _MAX_PARTS * dim, "lnbwd")
     nparts = ctypes.c_int(0)
     call(
-        "b200_layernorm_bwd", dy.data_ptr(), x.data_ptr(), ld_x, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+        "b200_layernorm_bwd", dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(), ld_x, gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
         _ptr(dres), dx_out.data_ptr(), ld_dx, _ptr(dx_bf16), part.data_ptr(), _MAX_PARTS,
         ctypes.byref(nparts), rows, dim, int(dx_colsum is not None), _stream(),
     )

@@ -124,7 +124,9 @@ def _register_dotted(root: nn.Module, key: str, param: nn.Parameter) -> None:
 # -----------------------------------------------------------------------------------------------------------------
 class ViTGeometry:
     def __init__(self, *, img_size: int, patch_size: int, in_channels: int, latent_dim: int, num_layers: int,
-                 ff_ratio: float, eps: float, num_classes: Optional[int]):
+                 ff_ratio: float, eps: float, num_classes: Optional[int], conv_bias: bool = True,
+                 embedding_norm_eps: Optional[float] = None, norm_after_head: bool = False,
+                 output_dim: Optional[int] = None, activation: str = "GELU"):
         if latent_dim % 64 != 0:
             raise NotImplementedError("latent_dim must be a multiple of 64 (head dim 64, transformer.py:61)")
         if patch_size % 16 != 0 or img_size % patch_size != 0:
@@ -136,15 +138,35 @@ class ViTGeometry:
         self.T = self.np + 1
         self.eps = eps
         self.C = num_classes
+        # the options CLIP's vision tower switches on (multimodal/clip.py:121-135)
+        self.conv_bias = conv_bias                    # to_patches_config={"bias": False}
+        self.emb_eps = embedding_norm_eps             # embedding_norm=nn.LayerNorm(D, eps): LN right after cls + pos-enc
+        self.norm_after_head = norm_after_head        # head_norm applied to the cls token (same maths, other key names)
+        self.out_dim = output_dim                     # `net @ output_projection`  [D, out_dim], no bias
+        self.quick_gelu = activation == "quick_gelu"  # feedforward_kwargs={"activation": "quick_gelu"}
+        if activation not in ("GELU", "quick_gelu"):
+            raise NotImplementedError(f"FeedForward activation {activation!r} is outside the fused path (GELU, quick_gelu)")
+        if output_dim is not None and (output_dim % 8 != 0 or num_classes is not None):
+            raise NotImplementedError("output_dim must be a multiple of 8 and cannot be combined with a classifier head")
         if self.T > 256:
             raise NotImplementedError("sequence length > 256 tokens is not supported by the fused attention yet")
 
+    @property
+    def head_norm_key(self) -> str:  # mixed_stacks/api.py:383-395: PreNorm(head) vs head then head_norm
+        return "encoder.head_norm." if self.norm_after_head else "encoder.head.norms.0."
+
     def spec(self, with_head: bool) -> List[Tuple[str, Tuple[int, ...]]]:
         d, p, c, ff = self.D, self.patch, self.cin, self.FF
-        out: List[Tuple[str, Tuple[int, ...]]] = [
-            ("to_patches.projection.weight", (d, c, p, p)), ("to_patches.projection.bias", (d,)),
-            ("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, self.T, d)),
-        ]
+        # (key order = the reference's state_dict order: a module's own parameters precede its sub-modules')
+        out: List[Tuple[str, Tuple[int, ...]]] = []
+        if self.out_dim is not None:
+            out.append(("output_projection", (d, self.out_dim)))
+        out.append(("to_patches.projection.weight", (d, c, p, p)))
+        if self.conv_bias:
+            out.append(("to_patches.projection.bias", (d,)))
+        out += [("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, self.T, d))]
+        if self.emb_eps is not None:
+            out += [("encoder.embedding_norm.weight", (d,)), ("encoder.embedding_norm.bias", (d,))]
         for i in range(self.L):
             b = f"encoder.mixing_blocks.{i}."
             out += [
@@ -155,7 +177,7 @@ class ViTGeometry:
                 (b + "channel_mixing.net.0.linear.weight", (ff, d)), (b + "channel_mixing.net.0.linear.bias", (ff,)),
                 (b + "channel_mixing.net.3.linear.weight", (d, ff)), (b + "channel_mixing.net.3.linear.bias", (d,)),
             ]
-        out += [("encoder.head.norms.0.weight", (d,)), ("encoder.head.norms.0.bias", (d,))]
+        out += [(self.head_norm_key + "weight", (d,)), (self.head_norm_key + "bias", (d,))]
         if with_head:
             out += [("head.linear.weight", (self.C, d)), ("head.linear.bias", (self.C,))]
         return out
@@ -166,6 +188,8 @@ def _init_param(key: str, shape: Tuple[int, ...]) -> Tensor:
     attentions.py:108-110), zero biases, LayerNorm 1/0, xavier_normal(gain/sqrt 2) conv (convs/basic.py:94-97)."""
     if key.endswith("norm.weight") or key.endswith("norms.0.weight"):
         return torch.ones(shape)
+    if key == "output_projection":  # cv/encoder/transformer.py:81-82
+        return (shape[0] ** -0.5) * torch.randn(shape)
     if key.endswith("bias"):
         return torch.zeros(shape)
     if key == "to_patches.projection.weight":
@@ -179,7 +203,7 @@ def _init_param(key: str, shape: Tuple[int, ...]) -> Tensor:
 # the engine: forward / backward of the whole stack on raw buffers
 # -----------------------------------------------------------------------------------------------------------------
 class _Saved:
-    __slots__ = ("B", "cols", "blocks", "net_last", "head_mean", "head_rstd", "enc_bf16")
+    __slots__ = ("B", "cols", "blocks", "net_last", "head_mean", "head_rstd", "enc_bf16", "emb_in", "emb_mean", "emb_rstd")
 
 
 class ViTEngine:
@@ -221,9 +245,17 @@ class ViTEngine:
         sv = _Saved()
         sv.B = B
         cols = ops.patch_im2col(x, g.patch)
-        patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1), bias=A.w("to_patches.projection.bias"))
+        patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
+                         bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
         net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(M, D)
+        sv.emb_in = None
+        if g.emb_eps is not None:  # embedding_norm (api.py:433-434): its fp32 output IS the residual stream
+            normed = torch.empty_like(net)
+            _, sv.emb_mean, sv.emb_rstd = ops.layernorm_fwd(net, A.p("encoder.embedding_norm.weight"), A.p("encoder.embedding_norm.bias"),
+                                                            g.emb_eps, rows=M, dim=D, ld_x=D, y_f32=normed)
+            sv.emb_in, net = net, normed
         sv.cols = cols
+        epi_act = ops.EPI_BIAS_QGELU_BF16 if g.quick_gelu else ops.EPI_BIAS_GELU_BF16
         sv.blocks = []
         for i in range(g.L):
             b = f"encoder.mixing_blocks.{i}."
@@ -235,14 +267,14 @@ class ViTEngine:
             ln2, mean2, rstd2 = ops.layernorm_fwd(mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
             act = torch.empty((M, g.FF), dtype=torch.bfloat16, device=x.device)
             h = ops.gemm(ln2, A.w(b + "channel_mixing.net.0.linear.weight"), bias=A.w(b + "channel_mixing.net.0.linear.bias"),
-                         epilogue=ops.EPI_BIAS_GELU_BF16, out1=act)
+                         epilogue=epi_act, out1=act)
             out = ops.gemm(act, A.w(b + "channel_mixing.net.3.linear.weight"), bias=A.w(b + "channel_mixing.net.3.linear.bias"),
                            epilogue=ops.EPI_BIAS_RESID_F32, aux=mid)
             sv.blocks.append((net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act))
             net = out
         enc_f32 = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_f32 else None
         # head = LayerNorm over all tokens then token 0 (api.py:365,397-402): only row 0 of each image is needed
-        enc_bf16, hm, hr = ops.layernorm_fwd(net, A.p("encoder.head.norms.0.weight"), A.p("encoder.head.norms.0.bias"), g.eps,
+        enc_bf16, hm, hr = ops.layernorm_fwd(net, A.p(g.head_norm_key + "weight"), A.p(g.head_norm_key + "bias"), g.eps,
                                              rows=B, dim=D, ld_x=T * D, y_f32=enc_f32)
         sv.net_last, sv.head_mean, sv.head_rstd, sv.enc_bf16 = net, hm, hr, enc_bf16
         return enc_bf16, enc_f32, sv
@@ -250,6 +282,16 @@ class ViTEngine:
     def head_forward(self, enc_bf16: Tensor) -> Tensor:
         A = self.arena
         return ops.gemm(enc_bf16, A.w("head.linear.weight"), bias=A.w("head.linear.bias"))
+
+    # ---- `net @ output_projection` (cv/encoder/transformer.py:93-94): a bf16 matmul under autocast ----------------
+    def projection_forward(self, enc_bf16: Tensor) -> Tensor:
+        return ops.gemm(enc_bf16, self.arena.w("output_projection"), b_mn_major=True)  # [B, D] . [D, out] -> bf16 [B, out]
+
+    def projection_backward(self, sv: _Saved, d_out: Tensor, G: Tensor) -> Tensor:
+        A = self.arena
+        d_enc = ops.gemm(d_out, A.w("output_projection"))                      # [B, out] . [D, out]^T -> bf16 [B, D]
+        ops.wgrad(sv.enc_bf16, d_out, A.g("output_projection", G))             # enc^T . d_out -> [D, out]
+        return d_enc
 
     # ---- backward -----------------------------------------------------------------------------------------
     def head_backward(self, sv: _Saved, dlogits: Tensor, G: Tensor) -> Tensor:
@@ -267,9 +309,9 @@ class ViTEngine:
         red = self.reducer
         dnet = torch.empty((M, D), dtype=torch.float32, device=dev)
         ops.fill_f32(dnet, 0.0)
-        ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p("encoder.head.norms.0.weight"), sv.head_mean, sv.head_rstd,
+        ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p(g.head_norm_key + "weight"), sv.head_mean, sv.head_rstd,
                           rows=B, dim=D, ld_x=T * D, dres=None, dx_out=dnet, ld_dx=T * D, dx_bf16=None,
-                          dgamma=A.g("encoder.head.norms.0.weight", G), dbeta=A.g("encoder.head.norms.0.bias", G))
+                          dgamma=A.g(g.head_norm_key + "weight", G), dbeta=A.g(g.head_norm_key + "bias", G))
         dnet_bf = ops.cast_bf16(dnet)
         # bias gradient of the last block's FF2 (dY = dnet_bf); every other Linear whose dY comes out of a LayerNorm
         # backward gets its bias gradient from that kernel (dx_colsum)
@@ -280,7 +322,8 @@ class ViTEngine:
             b = f"encoder.mixing_blocks.{i}."
             net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act = sv.blocks[i]
             # FeedForward: net_out = mid + W2 gelu(W1 ln2 + b1) + b2
-            dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=h)
+            dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True,
+                          epilogue=ops.EPI_DQGELU_BF16 if g.quick_gelu else ops.EPI_DGELU_BF16, aux=h)
             ops.wgrad(dnet_bf, act, A.g(b + "channel_mixing.net.3.linear.weight", G))
             dln2 = ops.gemm(dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
             ops.wgrad(dh, ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
@@ -305,10 +348,17 @@ class ViTEngine:
             sv.blocks[i] = None  # release this block's activations
             if red is not None:
                 red.ready(i, G)
+        if sv.emb_in is not None:  # embedding_norm backward: dy is the fp32 residual-stream gradient
+            dpre = torch.empty_like(dnet)
+            ops.layernorm_bwd(dnet, sv.emb_in, A.p("encoder.embedding_norm.weight"), sv.emb_mean, sv.emb_rstd, rows=M, dim=D, ld_x=D,
+                              dres=None, dx_out=dpre, ld_dx=D, dx_bf16=None,
+                              dgamma=A.g("encoder.embedding_norm.weight", G), dbeta=A.g("encoder.embedding_norm.bias", G))
+            dnet = dpre
         # tokens = cat(cls, patches) + pos ; patches = conv(x)
         dpatch = ops.assemble_tokens_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), A.g("encoder.head_token", G), B, g.np, D)
         ops.wgrad(dpatch, sv.cols, A.g("to_patches.projection.weight", G).view(D, -1))
-        self._bias_grad(dpatch, A.g("to_patches.projection.bias", G))
+        if g.conv_bias:
+            self._bias_grad(dpatch, A.g("to_patches.projection.bias", G))
         self._join_side()
         if red is not None:
             red.ready("stem", G)
@@ -347,8 +397,11 @@ def _pick_grad_arena(arena: ParamArena, keys: List[str]) -> Tensor:
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx: Any, module: "ViTEncoderB200", x: Tensor, *params: Tensor) -> Tensor:
-        enc_bf16, enc_f32, sv = module.engine.encoder_forward(x, want_f32=True)
+        proj = module.geo.out_dim is not None
+        enc_bf16, enc_f32, sv = module.engine.encoder_forward(x, want_f32=not proj)
         ctx.module, ctx.sv = module, sv
+        if proj:  # `net @ output_projection` is a bf16 matmul under autocast: the encoder returns bf16 [B, output_dim]
+            return module.engine.projection_forward(enc_bf16)
         return enc_f32
 
     @staticmethod
@@ -358,7 +411,9 @@ class _EncoderFn(torch.autograd.Function):
         keys = module.encoder_keys
         G = _pick_grad_arena(arena, keys)
         # under autocast the encoder output feeds a bf16 matmul, so its gradient is bf16-representable
-        d_bf = ops.cast_bf16(d_enc.contiguous().float())
+        d_bf = d_enc.contiguous() if d_enc.dtype == torch.bfloat16 else ops.cast_bf16(d_enc.contiguous().float())
+        if module.geo.out_dim is not None:
+            d_bf = eng.projection_backward(sv, d_bf, G)
         eng.encoder_backward(sv, d_bf, G)
         if eng.reducer is not None:
             eng.reducer.finish()
@@ -427,9 +482,8 @@ def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
 # modules (the plug-in surface)
 # -----------------------------------------------------------------------------------------------------------------
 def _check_supported(**kw: Any) -> None:
-    expected = dict(to_patches_type="vanilla", dropout=0.0, drop_path_rate=0.0, norm_type="layer", embedding_norm=None,
-                    residual_after_norm=False, use_head_token=True, use_positional_encoding=True, norm_after_head=False,
-                    output_dim=None, feedforward_kwargs=None)
+    expected = dict(to_patches_type="vanilla", dropout=0.0, drop_path_rate=0.0, norm_type="layer",
+                    residual_after_norm=False, use_head_token=True, use_positional_encoding=True)
     for k, v in expected.items():
         if k in kw and kw[k] != v and not (kw[k] is None and v is None):
             raise NotImplementedError(
@@ -469,24 +523,37 @@ class ViTEncoderB200(nn.Module):
     ):
         super().__init__()
         _check_supported(to_patches_type=to_patches_type, dropout=dropout, drop_path_rate=drop_path_rate, norm_type=norm_type,
-                         embedding_norm=embedding_norm, residual_after_norm=residual_after_norm, use_head_token=use_head_token,
-                         use_positional_encoding=use_positional_encoding, norm_after_head=norm_after_head, output_dim=output_dim,
-                         feedforward_kwargs=feedforward_kwargs)
+                         residual_after_norm=residual_after_norm, use_head_token=use_head_token,
+                         use_positional_encoding=use_positional_encoding)
+        fk = dict(feedforward_kwargs or {})
+        if set(fk) - {"activation"}:
+            raise NotImplementedError(f"unsupported feedforward_kwargs: {sorted(set(fk) - {'activation'})}")
+        emb_eps: Optional[float] = None
+        if embedding_norm is not None:  # clip.py:131: nn.LayerNorm(latent_dim, eps)
+            if not isinstance(embedding_norm, nn.LayerNorm) or tuple(embedding_norm.normalized_shape) != (latent_dim,) \
+                    or not embedding_norm.elementwise_affine or embedding_norm.bias is None:
+                raise NotImplementedError("embedding_norm must be an affine nn.LayerNorm(latent_dim)")
+            emb_eps = float(embedding_norm.eps)
+        tpc = dict(to_patches_config or {})
+        if set(tpc) - {"bias"}:
+            raise NotImplementedError(f"unsupported to_patches_config: {sorted(set(tpc) - {'bias'})}")
         ak = dict(attention_kwargs or {})
         if ak.get("num_heads", latent_dim // 64) != latent_dim // 64 or not ak.get("bias", True):
             raise NotImplementedError("ViTEncoderB200 supports the default attention_kwargs only (bias=True, head dim 64)")
         if set(ak) - {"num_heads", "bias"}:
             raise NotImplementedError(f"unsupported attention_kwargs: {sorted(set(ak) - {'num_heads', 'bias'})}")
-        if to_patches_config:
-            raise NotImplementedError("to_patches_config extras are outside the fused path")
         eps = float((norm_kwargs or {}).get("eps", 1e-6))  # norms.py:118-119 default, clip.py:128 overrides to 1e-5
         self.geo = ViTGeometry(img_size=img_size, patch_size=patch_size, in_channels=in_channels, latent_dim=latent_dim,
-                               num_layers=num_layers, ff_ratio=feedforward_dim_ratio, eps=eps, num_classes=_num_classes)
+                               num_layers=num_layers, ff_ratio=feedforward_dim_ratio, eps=eps, num_classes=_num_classes,
+                               conv_bias=bool(tpc.get("bias", True)), embedding_norm_eps=emb_eps, norm_after_head=bool(norm_after_head),
+                               output_dim=output_dim, activation=fk.get("activation", "GELU"))
         spec = self.geo.spec(with_head=_num_classes is not None)
         self.arena = ParamArena(spec)
         params: Dict[str, nn.Parameter] = {}
         for key, shape in spec:
             p = nn.Parameter(_init_param(key, shape))
+            if embedding_norm is not None and key.startswith("encoder.embedding_norm."):
+                p.data.copy_(getattr(embedding_norm, key.rsplit(".", 1)[1]).data)  # the instance handed in is adopted
             params[key] = p
             _register_dotted(self, key, p)
         self.arena.attach(params)

@@ -44,7 +44,10 @@ enum {
     B200_EPI_BIAS_GELU_BF16 = 1, /* out0 = h = bf16(acc + bias); out1 = bf16(gelu_erf(h))                        */
     B200_EPI_BIAS_RESID_F32 = 2, /* out0[f32] = aux[f32] + float(bf16(acc + bias))   (aux may alias out0)         */
     B200_EPI_DGELU_BF16 = 3,     /* out0[bf16] = bf16(float(bf16(acc)) * gelu_erf'(aux[bf16]))                   */
-    B200_EPI_PARTIAL_F32 = 4     /* out0[f32][split, M, N] = partial accumulators (split-K)                      */
+    B200_EPI_PARTIAL_F32 = 4,    /* out0[f32][split, M, N] = partial accumulators (split-K)                      */
+    B200_EPI_BIAS_QGELU_BF16 = 5, /* like 1 with QuickGELU x * sigmoid(1.702 x) (CLIP, activations.py:151-153), rounded to
+                                    bf16 after each of eager's three elementwise ops                              */
+    B200_EPI_DQGELU_BF16 = 6      /* like 3: autograd of those three ops with eager's bf16 rounding after each kernel */
 };
 
 int b200_abi_version(void);
@@ -92,10 +95,11 @@ int b200_layernorm_fwd(const float* x, long long ld_x, const float* gamma, const
  * dy: bf16 [rows, dim].  dx_bf16 (optional) receives bf16(dx_out) -- the gradient the preceding bf16 matmul
  * output sees under autocast.  dgb_part: f32 [nparts, 2*dim] workspace ([.., 0:dim] dgamma partials, [.., dim:2dim]
  * dbeta partials), reduced by b200_colsum_finish.  Returns nparts through *nparts_out (host int).
- * dx_colsum != 0 (needs dx_bf16): the part rows are 3*dim wide and columns [2*dim, 3*dim) hold the column sums of
+ * dy is bf16 [rows, dim], or fp32 when dy_is_f32 != 0 (a LayerNorm whose output is the fp32 residual stream itself:
+ * CLIP's embedding_norm, mixed_stacks/api.py:433-434).  dx_colsum != 0 (needs dx_bf16, bf16 dy): the part rows are 3*dim wide and columns [2*dim, 3*dim) hold the column sums of
  * the bf16-rounded dx rows, i.e. the bias gradient of the Linear layer whose output gradient this dx is (the
  * separate b200_colsum_bf16 pass over dx_bf16 is then not needed). */
-int b200_layernorm_bwd(const void* dy_bf16, const float* x, long long ld_x, const float* gamma, const float* mean,
+int b200_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, long long ld_x, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx_out, long long ld_dx, void* dx_bf16,
                        float* dgb_part, int max_parts, int* nparts_out, int rows, int dim, int dx_colsum,
                        cudaStream_t stream);

@@ -69,6 +69,42 @@ def pin(name, batch, autocast_bf16):
     return cfg, sd, x, y, r_enc, r_logits, r_loss, r_grads
 
 
+def reference_clip_vision(cfg):
+    """The ViTEncoder that CLIP._init_vision builds (multimodal/clip.py:121-135), from the unmodified reference."""
+    load_reference_modules()
+    from cflearn.modules.cv.encoder.transformer import ViTEncoder
+
+    d = cfg["latent_dim"]
+    return ViTEncoder(img_size=cfg["img_size"], patch_size=cfg["patch_size"], in_channels=cfg["in_channels"], latent_dim=d,
+                      to_patches_config={"bias": False}, num_layers=cfg["num_layers"], norm_kwargs={"eps": cfg["eps"]},
+                      embedding_norm=torch.nn.LayerNorm(d, cfg["eps"]), attention_kwargs={"num_heads": d // 64},
+                      feedforward_kwargs={"activation": "quick_gelu"}, norm_after_head=True, output_dim=cfg["output_dim"])
+
+
+def pin_clip_vision(name, batch, autocast_bf16):
+    """Encoder-only pin (the reference defines no loss for CLIP): output and every gradient for a seeded
+    upstream gradient must be bit-identical between the oracle and the reference module."""
+    cfg = vo.vit_config(name)
+    enc = reference_clip_vision(cfg)
+    assert [(k, tuple(v.shape)) for k, v in enc.state_dict().items()] == vo.state_dict_spec(cfg), "state_dict keys / order / shapes"
+    sd = vo.init_state_dict(cfg, seed=0)
+    enc.load_state_dict(sd, strict=True)
+    enc.train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, cfg["in_channels"], cfg["img_size"], cfg["img_size"], generator=g)
+    up = torch.randn(batch, cfg["output_dim"], generator=g)
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast_bf16):
+        out = enc(x)
+    (out.float() * up).sum().backward()
+    r_grads = {k: p.grad for k, p in enc.named_parameters()}
+    o_out, o_grads, _ = vo.encoder_train_step(sd, x, up, cfg, autocast_bf16=autocast_bf16)
+    assert torch.equal(o_out, out.detach()), "encoder output differs from the reference"
+    for k in r_grads:
+        assert torch.equal(o_grads[k], r_grads[k]), f"grad {k} differs from the reference"
+    print(f"pinned {name} B={batch} {'bf16' if autocast_bf16 else 'fp32'}: {len(r_grads)} grads bit-identical to the reference")
+    return cfg, x, up, out.detach(), r_grads
+
+
 def known_answer_attention():
     """tests/test_blocks.py:147-176 logic, pointed at the oracle's attention(): == nn.MultiheadAttention, atol 1e-4."""
     torch.manual_seed(0)
@@ -115,6 +151,17 @@ def main():
 
     with open(os.path.join(GOLDEN, "vit_b16_state_dict_keys.json"), "w") as f:
         json.dump({"num_params": sum(p.numel() for p in big.parameters()), "keys": keys}, f, indent=1)
+    # CLIP's vision tower: real ViT-B/32 shapes pinned once, a tiny one stored as a fixture
+    pin_clip_vision("clip_vision_b32", 2, True)
+    ref = {}
+    for mode in (False, True):
+        cfg, x, up, r_out, r_grads = pin_clip_vision("clip_vision_tiny", 3, mode)
+        ref["bf16" if mode else "fp32"] = {"out": r_out, "grads": {k: v.clone() for k, v in r_grads.items()}}
+    torch.save({"config_name": "clip_vision_tiny", "weights_seed": 0, "x": x, "upstream": up, "reference": ref},
+               os.path.join(GOLDEN, "clip_vision_tiny_reference.pt"))
+    tiny = reference_clip_vision(vo.vit_config("clip_vision_tiny"))
+    with open(os.path.join(GOLDEN, "clip_vision_tiny_keys.json"), "w") as f:
+        json.dump({"keys": [[k, list(v.shape)] for k, v in tiny.state_dict().items()]}, f, indent=1)
     print("wrote", os.listdir(GOLDEN))
 
 

@@ -32,6 +32,14 @@ def vit_config(name: str = "vit_b16") -> Dict[str, int]:
         "vit_b16": dict(img_size=224, patch_size=16, in_channels=3, latent_dim=768, num_layers=12, num_classes=1000),
         "vit_tiny": dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, num_layers=2, num_classes=10),
         "vit_small": dict(img_size=64, patch_size=16, in_channels=3, latent_dim=256, num_layers=3, num_classes=24),
+        # the ViTEncoder CLIP._init_vision builds (multimodal/clip.py:121-135; SURVEY.md 8a row a16, vision half): no conv bias,
+        # embedding_norm, QuickGELU, LayerNorm eps 1e-5, head_norm after the cls pick, output_projection [D, latent_dim]
+        "clip_vision_b32": dict(img_size=224, patch_size=32, in_channels=3, latent_dim=768, num_layers=12, conv_bias=False,
+                                emb_norm=True, norm_after_head=True, output_dim=512, activation="quick_gelu", eps=1e-5),
+        "clip_vision_tiny": dict(img_size=64, patch_size=32, in_channels=3, latent_dim=128, num_layers=2, conv_bias=False,
+                                 emb_norm=True, norm_after_head=True, output_dim=64, activation="quick_gelu", eps=1e-5),
+        "clip_vision_small": dict(img_size=96, patch_size=32, in_channels=3, latent_dim=256, num_layers=3, conv_bias=False,
+                                  emb_norm=True, norm_after_head=True, output_dim=128, activation="quick_gelu", eps=1e-5),
     }
     return dict(table[name])
 
@@ -41,12 +49,15 @@ def state_dict_spec(cfg: Dict[str, int]) -> List[Tuple[str, Tuple[int, ...]]]:
     d, p, c = cfg["latent_dim"], cfg["patch_size"], cfg["in_channels"]
     n_tok = (cfg["img_size"] // p) ** 2 + 1
     ff = 4 * d
-    spec: List[Tuple[str, Tuple[int, ...]]] = [
-        ("to_patches.projection.weight", (d, c, p, p)),
-        ("to_patches.projection.bias", (d,)),
-        ("encoder.head_token", (1, 1, d)),
-        ("encoder.pos_encoding.pos_encoding", (1, n_tok, d)),
-    ]
+    spec: List[Tuple[str, Tuple[int, ...]]] = []
+    if cfg.get("output_dim") is not None:  # ViTEncoder's own parameter: first in state_dict order (transformer.py:78-82)
+        spec.append(("output_projection", (d, cfg["output_dim"])))
+    spec.append(("to_patches.projection.weight", (d, c, p, p)))
+    if cfg.get("conv_bias", True):
+        spec.append(("to_patches.projection.bias", (d,)))
+    spec += [("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, n_tok, d))]
+    if cfg.get("emb_norm", False):
+        spec += [("encoder.embedding_norm.weight", (d,)), ("encoder.embedding_norm.bias", (d,))]
     for i in range(cfg["num_layers"]):
         b = f"encoder.mixing_blocks.{i}."
         spec += [
@@ -57,8 +68,10 @@ def state_dict_spec(cfg: Dict[str, int]) -> List[Tuple[str, Tuple[int, ...]]]:
             (b + "channel_mixing.net.0.linear.weight", (ff, d)), (b + "channel_mixing.net.0.linear.bias", (ff,)),
             (b + "channel_mixing.net.3.linear.weight", (d, ff)), (b + "channel_mixing.net.3.linear.bias", (d,)),
         ]
-    spec += [("encoder.head.norms.0.weight", (d,)), ("encoder.head.norms.0.bias", (d,))]
-    spec += [("head.linear.weight", (cfg["num_classes"], d)), ("head.linear.bias", (cfg["num_classes"],))]
+    hn = "encoder.head_norm." if cfg.get("norm_after_head", False) else "encoder.head.norms.0."
+    spec += [(hn + "weight", (d,)), (hn + "bias", (d,))]
+    if cfg.get("num_classes") is not None:
+        spec += [("head.linear.weight", (cfg["num_classes"], d)), ("head.linear.bias", (cfg["num_classes"],))]
     return spec
 
 
@@ -73,6 +86,8 @@ def init_state_dict(cfg: Dict[str, int], seed: int = 0, *, perturb: bool = True)
             t = torch.ones(shape) + (0.1 * torch.randn(shape, generator=g) if perturb else 0)
         elif key.endswith("bias"):
             t = 0.02 * torch.randn(shape, generator=g) if perturb else torch.zeros(shape)
+        elif key == "output_projection":
+            t = (shape[0] ** -0.5) * torch.randn(shape, generator=g)  # transformer.py:81
         elif key == "to_patches.projection.weight":
             fan_in = shape[1] * shape[2] * shape[3]
             fan_out = shape[0] * shape[2] * shape[3]
@@ -99,18 +114,21 @@ def patch_embed(sd: StateDict, x: Tensor) -> Tensor:
     (convs/basic.py:155-174), then _flatten (high_level.py:143-149): [B,C,h,w] -> [B, h*w, C] contiguous."""
     w = sd["to_patches.projection.weight"]
     p = w.shape[-1]
-    net = F.conv2d(x, w, sd["to_patches.projection.bias"], stride=p, padding=0)
+    net = F.conv2d(x, w, sd.get("to_patches.projection.bias"), stride=p, padding=0)
     b, c, h, ww = net.shape
     return net.view(b, c, h * ww).transpose(1, 2).contiguous()
 
 
-def pre_process(sd: StateDict, patches: Tensor) -> Tensor:
+def pre_process(sd: StateDict, patches: Tensor, emb_eps: float = 1e-5) -> Tensor:
     """MixedStackedEncoder.pre_process (mixed_stacks/api.py:419-438): cat head token, add learned positional
     encoding (PositionalEncoding.forward early-return path, api.py:209-228,244-245).  Dropout(0) is the identity."""
     n = patches.shape[0]
     head_tokens = sd["encoder.head_token"].repeat([n, 1, 1])
     net = torch.cat([head_tokens, patches], dim=1)
-    return net + sd["encoder.pos_encoding.pos_encoding"]
+    net = net + sd["encoder.pos_encoding.pos_encoding"]
+    if "encoder.embedding_norm.weight" in sd:  # api.py:433-434 (CLIP: nn.LayerNorm(D, 1e-5), clip.py:131)
+        net = F.layer_norm(net, (net.shape[-1],), sd["encoder.embedding_norm.weight"], sd["encoder.embedding_norm.bias"], emb_eps)
+    return net
 
 
 def attention(sd: StateDict, prefix: str, net: Tensor, num_heads: int, causal: bool = False) -> Tensor:
@@ -129,38 +147,48 @@ def attention(sd: StateDict, prefix: str, net: Tensor, num_heads: int, causal: b
     return F.linear(out, sd[prefix + "out_linear.linear.weight"], sd[prefix + "out_linear.linear.bias"])
 
 
-def feed_forward(sd: StateDict, prefix: str, net: Tensor) -> Tensor:
-    """FeedForward (mixed_stacks/channel_mixers.py:29-36): Linear -> nn.GELU() (exact erf) -> Dropout(0) -> Linear."""
+def feed_forward(sd: StateDict, prefix: str, net: Tensor, activation: str = "GELU") -> Tensor:
+    """FeedForward (mixed_stacks/channel_mixers.py:29-36): Linear -> nn.GELU() (exact erf) -> Dropout(0) -> Linear;
+    activation "quick_gelu" = QuickGELU, ``net * torch.sigmoid(1.702 * net)`` (core/activations.py:151-153)."""
     h = F.linear(net, sd[prefix + "0.linear.weight"], sd[prefix + "0.linear.bias"])
-    return F.linear(F.gelu(h), sd[prefix + "3.linear.weight"], sd[prefix + "3.linear.bias"])
+    a = h * torch.sigmoid(1.702 * h) if activation == "quick_gelu" else F.gelu(h)
+    return F.linear(a, sd[prefix + "3.linear.weight"], sd[prefix + "3.linear.bias"])
 
 
-def mixing_block(sd: StateDict, i: int, net: Tensor, num_heads: int, eps: float) -> Tensor:
+def mixing_block(sd: StateDict, i: int, net: Tensor, num_heads: int, eps: float, activation: str = "GELU") -> Tensor:
     """MixingBlock._pre_norm_forward (mixed_stacks/api.py:130-158); DropPath / Dropout are identities at rate 0."""
     b = f"encoder.mixing_blocks.{i}."
     d = net.shape[-1]
     t = F.layer_norm(net, (d,), sd[b + "token_norm.weight"], sd[b + "token_norm.bias"], eps)
     net = net + attention(sd, b + "token_mixing.net.", t, num_heads)
     c = F.layer_norm(net, (d,), sd[b + "channel_norm.weight"], sd[b + "channel_norm.bias"], eps)
-    return net + feed_forward(sd, b + "channel_mixing.net.", c)
+    return net + feed_forward(sd, b + "channel_mixing.net.", c, activation)
 
 
 def encoder_forward(sd: StateDict, x: Tensor, cfg: Dict[str, int], taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """ViTEncoder.forward (modules/cv/encoder/transformer.py:88-100) -> [B, latent_dim]."""
     d = cfg["latent_dim"]
     heads = d // 64  # transformer.py:61
-    eps = 1e-6  # norms.py:118-119
-    net = pre_process(sd, patch_embed(sd, x))
+    eps = cfg.get("eps", 1e-6)  # norms.py:118-119; CLIP passes norm_kwargs={"eps": 1e-5} (clip.py:130)
+    act = cfg.get("activation", "GELU")
+    net = pre_process(sd, patch_embed(sd, x), eps)
     if taps is not None:
         taps["tokens"] = net
     for i in range(cfg["num_layers"]):
-        net = mixing_block(sd, i, net, heads, eps)
+        net = mixing_block(sd, i, net, heads, eps, act)
         if taps is not None:
             taps[f"block{i}"] = net
     # head = PreNorm(LayerNorm, Lambda(x[:, 0])) (api.py:365,397-402; high_level.py:42-45): normalise ALL tokens, take token 0
-    net = F.layer_norm(net, (d,), sd["encoder.head.norms.0.weight"], sd["encoder.head.norms.0.bias"], eps)[:, 0]
+    if cfg.get("norm_after_head", False):  # api.py:391-393,440-444: head (cls pick) first, then head_norm
+        net = F.layer_norm(net[:, 0], (d,), sd["encoder.head_norm.weight"], sd["encoder.head_norm.bias"], eps)
+    else:
+        net = F.layer_norm(net, (d,), sd["encoder.head.norms.0.weight"], sd["encoder.head.norms.0.bias"], eps)[:, 0]
     if taps is not None:
         taps["encoded"] = net
+    if cfg.get("output_dim") is not None:  # transformer.py:93-94
+        net = net @ sd["output_projection"]
+        if taps is not None:
+            taps["projected"] = net
     return net
 
 
@@ -194,3 +222,15 @@ def train_step(sd: StateDict, x: Tensor, labels: Tensor, cfg: Dict[str, int], *,
     loss.backward()
     grads = {k: v.grad for k, v in params.items()}
     return loss.detach(), grads, {k: v.detach() for k, v in taps.items()}
+
+
+def encoder_train_step(sd: StateDict, x: Tensor, upstream: Tensor, cfg: Dict[str, int], *, autocast_bf16: bool,
+                       want_taps: bool = False) -> Tuple[Tensor, StateDict, Dict[str, Tensor]]:
+    """Forward + backward of the bare encoder (e.g. CLIP's vision tower, which has no loss of its own in the reference):
+    the scalar is ``sum(out * upstream)``, i.e. ``upstream`` [B, out] is the gradient arriving at the encoder output."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    taps: Dict[str, Tensor] = {}
+    with torch.autocast(x.device.type, dtype=torch.bfloat16, enabled=autocast_bf16):
+        out = encoder_forward(params, x, cfg, taps if want_taps else None)
+    (out.float() * upstream).sum().backward()
+    return out.detach(), {k: v.grad for k, v in params.items()}, {k: v.detach() for k, v in taps.items()}

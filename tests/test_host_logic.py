@@ -1,5 +1,6 @@
 """CPU tests (no GPU, no compute calls into the CUDA library): C-ABI export table, registry / module surface,
 parameter arena, data-parallel bucket layout and the world_size=2 gloo run of the bucket reducer."""
+import json
 import os
 import re
 import sys
@@ -62,7 +63,9 @@ def test_registry_semantics_mirror_reference():
     fake_reference_dict = {"encoders.vit": object, "cv_clf": object}
     replaced = registry.install_into(fake_reference_dict)
     assert fake_reference_dict["encoders.vit"] is vit.ViTEncoderB200 and replaced["cv_clf"] is object
-    for bad in (dict(dropout=0.1), dict(drop_path_rate=0.1), dict(norm_type="batch"), dict(output_dim=512)):
+    for bad in (dict(dropout=0.1), dict(drop_path_rate=0.1), dict(norm_type="batch"), dict(output_dim=100),
+                dict(feedforward_kwargs={"activation": "geglu"}), dict(to_patches_config={"padding": 1}),
+                dict(embedding_norm=torch.nn.BatchNorm1d(128))):
         with pytest.raises(NotImplementedError):
             registry.build_module("encoders.vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, **bad))
 
@@ -81,6 +84,18 @@ def test_fcnn_surface_mirrors_reference():
             registry.build_module("fcnn", input_dim=10, output_dim=1, **bad)
     with pytest.raises(cflearn_b200.B200Error):
         m(torch.randn(4, 10))  # CPU tensor: no fallback
+
+
+def test_clip_vision_tower_options_mirror_reference_keys():
+    # the ViTEncoder that CLIP._init_vision builds (multimodal/clip.py:121-135): key names AND order of the real reference
+    with open(os.path.join(ROOT, "tests", "golden", "clip_vision_tiny_keys.json")) as f:
+        golden = json.load(f)
+    m = registry.build_module("encoders.vit", config=dict(
+        img_size=64, patch_size=32, in_channels=3, latent_dim=128, to_patches_config={"bias": False}, num_layers=2,
+        norm_kwargs={"eps": 1e-5}, embedding_norm=torch.nn.LayerNorm(128, 1e-5), attention_kwargs={"num_heads": 2},
+        feedforward_kwargs={"activation": "quick_gelu"}, norm_after_head=True, output_dim=64))
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == golden["keys"]
+    assert m.geo.quick_gelu and m.geo.emb_eps == 1e-5 and m.geo.eps == 1e-5 and not m.geo.conv_bias
 
 
 def test_param_arena_views_and_state_dict_roundtrip():

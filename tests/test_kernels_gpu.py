@@ -370,3 +370,44 @@ def test_attention_bwd(B, T, H, causal):
     ref_b = dqkv.double().sum(0)
     assert (dbias.double() - ref_b).abs().max().item() <= 2.0 ** -8 * ref_b.abs().max().item() + 1e-6
     assert torch.equal(dbias, dbias.to(torch.bfloat16).float())
+
+
+def test_gemm_quick_gelu_epilogues_follow_eager_rounding():
+    """QuickGELU (CLIP towers): forward and backward must reproduce eager's op-by-op bf16 rounding
+    (``net * torch.sigmoid(1.702 * net)`` is three elementwise kernels on a bf16 tensor)."""
+    M, N, K = 1024, 1024, 256
+    a, b, a_arg, b_arg = _operands(M, N, K, False, False, seed=61)
+    bias = _rand_bf16(N, seed=62)
+    g = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    h = ops.gemm(a_arg, b_arg, bias=bias, epilogue=ops.EPI_BIAS_QGELU_BF16, out1=g)
+    torch.cuda.synchronize()
+    _assert_bf16_close(h, a.float() @ b.float().t() + bias.float(), "quick-gelu epilogue: h")
+    hh = h.clone().requires_grad_(True)
+    ref = hh * torch.sigmoid(1.702 * hh)  # eager, bf16 tensors
+    assert (g != ref.detach()).float().mean().item() < 2e-3  # identical up to ulp flips of the approximate sigmoid
+    _assert_bf16_close(g, ref.detach().float(), "quick-gelu epilogue: act")
+    # backward: dh = autograd of the three bf16 ops; dY . W with W MN-major as in the FF2 dgrad
+    dy = _rand_bf16(M, K, seed=63)
+    w2 = _rand_bf16(K, N, seed=64)
+    dact = (dy.float() @ w2.float()).to(torch.bfloat16)
+    ref.backward(dact)
+    dh = ops.gemm(dy, w2, b_mn_major=True, epilogue=ops.EPI_DQGELU_BF16, aux=h)
+    torch.cuda.synchronize()
+    assert (dh != hh.grad).float().mean().item() < 2e-2
+    _assert_bf16_close(dh, hh.grad.float(), "quick-gelu backward epilogue")
+
+
+@pytest.mark.parametrize("rows,dim", [(1000, 768), (77, 512)])
+def test_layernorm_bwd_fp32_upstream(rows, dim):
+    """LayerNorm whose output is the fp32 residual stream (CLIP's embedding_norm): dy arrives in fp32."""
+    torch.manual_seed(3)
+    x = (torch.randn(rows, dim, device=DEV) * 1.3 - 0.2).requires_grad_(True)
+    g = torch.randn(dim, device=DEV, requires_grad=True)
+    b = torch.randn(dim, device=DEV, requires_grad=True)
+    dy = torch.randn(rows, dim, device=DEV)
+    F.layer_norm(x, (dim,), g, b, 1e-5).backward(dy)
+    _, mean, rstd = ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-5, rows=rows, dim=dim, ld_x=dim)
+    dx, dg, db = torch.empty(rows, dim, device=DEV), torch.empty(dim, device=DEV), torch.empty(dim, device=DEV)
+    ops.layernorm_bwd(dy, x.detach(), g.detach(), mean, rstd, rows=rows, dim=dim, ld_x=dim, dres=None, dx_out=dx, ld_dx=dim,
+                      dx_bf16=None, dgamma=dg, dbeta=db)
+    assert _relerr(dx, x.grad) < 1e-5 and _relerr(dg, g.grad) < 1e-5 and _relerr(db, b.grad) < 1e-5

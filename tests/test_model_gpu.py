@@ -275,3 +275,58 @@ def test_fcnn_step_matches_reference_golden_and_oracle():
     assert rel(pred, ref_pred.detach()) < 1e-5 and abs(loss.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
     for k, p in m2.named_parameters():
         assert rel(p.grad, params[k].grad) < 2e-5, k
+
+
+# ---- CLIP vision tower: the ViTEncoder CLIP._init_vision builds (multimodal/clip.py:121-135) --------------------------
+def _clip_vision_module(cfg, sd):
+    d = cfg["latent_dim"]
+    m = registry.build_module("encoders.vit", config=dict(
+        img_size=cfg["img_size"], patch_size=cfg["patch_size"], in_channels=cfg["in_channels"], latent_dim=d,
+        to_patches_config={"bias": False}, num_layers=cfg["num_layers"], norm_kwargs={"eps": cfg["eps"]},
+        embedding_norm=torch.nn.LayerNorm(d, cfg["eps"]), attention_kwargs={"num_heads": d // 64},
+        feedforward_kwargs={"activation": "quick_gelu"}, norm_after_head=True, output_dim=cfg["output_dim"]))
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name,batch", [("clip_vision_tiny", 3), ("clip_vision_small", 5), ("clip_vision_b32", 8)])
+def test_clip_vision_tower_parity(name, batch):
+    """Same three-way criterion as the classifier: ours vs the oracle eagerly on this GPU under bf16 autocast, both against
+    the fp32 oracle; the scalar is sum(out * upstream) (the reference defines no loss for CLIP)."""
+    cfg = vo.vit_config(name)
+    sd = vo.init_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, cfg["in_channels"], cfg["img_size"], cfg["img_size"], generator=g).to(DEV)
+    up = torch.randn(batch, cfg["output_dim"], generator=g).to(DEV)
+    m = _clip_vision_module(cfg, sd)
+    out = m(x)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (batch, cfg["output_dim"])
+    (out.float() * up).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    e_out, e_grads, _ = vo.encoder_train_step(sdg, x, up, cfg, autocast_bf16=True)
+    f_out, f_grads, _ = vo.encoder_train_step(sdg, x, up, cfg, autocast_bf16=False)
+    floor = rel(e_out, f_out)
+    assert rel(out, e_out) < VS_EAGER_FACTOR * floor + SLACK and rel(out, f_out) < VS_FP32_FACTOR * floor + SLACK
+    assert set(grads) == set(e_grads)
+    worst = 0.0
+    for k in sorted(grads):
+        ours_vs_eager, ours_vs_fp32, eager_vs_fp32 = rel(grads[k], e_grads[k]), rel(grads[k], f_grads[k]), rel(e_grads[k], f_grads[k])
+        worst = max(worst, ours_vs_fp32 / max(eager_vs_fp32, 1e-12))
+        assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
+        assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
+    print(f"{name}: out vs eager {rel(out, e_out):.2e} (bf16 floor {floor:.2e}); worst grad err ratio {worst:.2f}")
+
+
+def test_clip_vision_against_reference_golden_vectors():
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "clip_vision_tiny_reference.pt"), weights_only=False)
+    cfg = vo.vit_config(fx["config_name"])
+    m = _clip_vision_module(cfg, vo.init_state_dict(cfg, seed=fx["weights_seed"]))
+    out = m(fx["x"].to(DEV))
+    (out.float() * fx["upstream"].to(DEV)).sum().backward()
+    ref_bf16, ref_fp32 = fx["reference"]["bf16"], fx["reference"]["fp32"]
+    assert rel(out.cpu(), ref_fp32["out"]) < max(2.0 * rel(ref_bf16["out"], ref_fp32["out"]), 5e-3)
+    for k, p in m.named_parameters():
+        ours = rel(p.grad.cpu(), ref_fp32["grads"][k])
+        theirs = rel(ref_bf16["grads"][k], ref_fp32["grads"][k])
+        assert ours < max(2.0 * theirs, 5e-3), (k, ours, theirs)

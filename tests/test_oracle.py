@@ -89,3 +89,31 @@ def test_fcnn_live_pin_against_reference(tmp_path, monkeypatch):
 
     monkeypatch.setattr(make_golden_fcnn, "GOLDEN", str(tmp_path))
     make_golden_fcnn.main()
+
+
+# ---- CLIP vision tower (vision half) ------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_clip_vision_oracle_matches_reference_golden(mode):
+    """The oracle with CLIP._init_vision's options (no conv bias, embedding_norm, QuickGELU, eps 1e-5, head_norm after the
+    cls pick, output_projection) vs the fixture written from the REAL reference ViTEncoder."""
+    fx = torch.load(os.path.join(GOLDEN, "clip_vision_tiny_reference.pt"), weights_only=False)
+    with open(os.path.join(GOLDEN, "clip_vision_tiny_keys.json")) as f:
+        keys = json.load(f)["keys"]
+    cfg = vo.vit_config(fx["config_name"])
+    assert [[k, list(s)] for k, s in vo.state_dict_spec(cfg)] == keys
+    sd = vo.init_state_dict(cfg, seed=fx["weights_seed"])
+    out, grads, _ = vo.encoder_train_step(sd, fx["x"], fx["upstream"], cfg, autocast_bf16=(mode == "bf16"))
+    ref = fx["reference"][mode]
+    tol = dict(rtol=1e-5, atol=1e-6) if mode == "fp32" else dict(rtol=2e-2, atol=2e-3)
+    assert out.dtype == ref["out"].dtype and torch.allclose(out.float(), ref["out"].float(), **tol)
+    for k, g in ref["grads"].items():
+        err = (grads[k] - g).norm() / g.norm().clamp_min(1e-20)
+        assert err < (1e-4 if mode == "fp32" else 2e-2), (k, err.item())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_clip_vision_live_pin_against_reference():
+    import make_golden
+
+    make_golden.pin_clip_vision("clip_vision_tiny", 2, False)
+    make_golden.pin_clip_vision("clip_vision_tiny", 2, True)
