@@ -389,11 +389,12 @@ def test_gemm_quick_gelu_epilogues_follow_eager_rounding():
     # backward: dh = autograd of the three bf16 ops; dY . W with W MN-major as in the FF2 dgrad
     dy = _rand_bf16(M, K, seed=63)
     w2 = _rand_bf16(K, N, seed=64)
-    dact = (dy.float() @ w2.float()).to(torch.bfloat16)
+    dact = ops.gemm(dy, w2, b_mn_major=True)  # bf16(acc) exactly as the fused kernel sees it (same main loop)
+    _assert_bf16_close(dact, dy.float() @ w2.float(), "quick-gelu backward: dact")
     ref.backward(dact)
     dh = ops.gemm(dy, w2, b_mn_major=True, epilogue=ops.EPI_DQGELU_BF16, aux=h)
     torch.cuda.synchronize()
-    assert (dh != hh.grad).float().mean().item() < 2e-2
+    assert (dh != hh.grad).float().mean().item() < 5e-3  # same five roundings as autograd's kernels; only the sigmoid differs
     _assert_bf16_close(dh, hh.grad.float(), "quick-gelu backward epilogue")
 
 
