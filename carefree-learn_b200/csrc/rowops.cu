@@ -404,6 +404,29 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, 
     *reinterpret_cast<float4*>(o + 4) = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
 }
 
+// text tower input stage (TeTEncoder: no head token): net[b, t, :] = x[b, t, :] + pos[t, :], fp32
+__global__ void add_pos_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ net, long long n4,
+                               int td4) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 p = reinterpret_cast<const float4*>(pos)[i % td4];
+    reinterpret_cast<float4*>(net)[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+// dpos[t, :] = sum_b dnet[b, t, :] (thread = 4 columns of (t, d), loops over the batch in a fixed order)
+__global__ void add_pos_bwd_kernel(const float* __restrict__ dnet, float* __restrict__ dpos, int B, int td4, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= td4) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+        const float4 v = reinterpret_cast<const float4*>(dnet)[static_cast<long long>(b) * td4 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(dpos) + i;
+    if (accumulate) { const float4 old = *o; s.x += old.x; s.y += old.y; s.z += old.z; s.w += old.w; }
+    *o = s;
+}
+
 // thread = (t, d4): loops over the batch; dpos[t] = sum_b dnet[b,t]; dpatch = bf16(dnet[:,1:]); dcls = dpos[0]
 __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dnet, __nv_bfloat16* __restrict__ dpatch,
                                            float* __restrict__ dpos, float* __restrict__ dcls, int B, int np, int D,
@@ -673,6 +696,20 @@ extern "C" int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, fl
     const int total = (np + 1) * (D / 4);
     assemble_tokens_bwd_kernel<<<(total + 127) / 128, 128, 0, stream>>>(dnet, reinterpret_cast<__nv_bfloat16*>(dpatch_bf16), dpos, dcls, B, np, D, accumulate);
     return check_launch("assemble_tokens_bwd");
+}
+
+extern "C" int b200_add_pos(const float* x, const float* pos, float* net, int B, int T, int D, cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || D <= 0 || D % 4 != 0) return set_error(B200_ERR_ARG, "add_pos: D % 4 != 0");
+    const long long n4 = static_cast<long long>(B) * T * (D / 4);
+    add_pos_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(x, pos, net, n4, T * (D / 4));
+    return check_launch("add_pos");
+}
+
+extern "C" int b200_add_pos_bwd(const float* dnet, float* dpos, int B, int T, int D, int accumulate, cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || D <= 0 || D % 4 != 0) return set_error(B200_ERR_ARG, "add_pos_bwd: D % 4 != 0");
+    const int td4 = T * (D / 4);
+    add_pos_bwd_kernel<<<(td4 + 127) / 128, 128, 0, stream>>>(dnet, dpos, B, td4, accumulate);
+    return check_launch("add_pos_bwd");
 }
 
 extern "C" int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels,

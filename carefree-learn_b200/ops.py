@@ -225,6 +225,18 @@ def patch_im2col(x: Tensor, patch: int) -> Tensor:
     return cols
 
 
+def add_pos(x: Tensor, pos: Tensor, B: int, T: int, D: int) -> Tensor:
+    """net[b, t, :] = x[b, t, :] + pos[t, :] (fp32): the text tower's input stage."""
+    _need_cuda(x, pos)
+    net = torch.empty((B, T, D), dtype=torch.float32, device=x.device)
+    call("b200_add_pos", x.data_ptr(), pos.data_ptr(), net.data_ptr(), B, T, D, _stream())
+    return net
+
+
+def add_pos_bwd(dnet: Tensor, dpos: Tensor, B: int, T: int, D: int, accumulate: bool = False) -> None:
+    call("b200_add_pos_bwd", dnet.data_ptr(), dpos.data_ptr(), B, T, D, int(accumulate), _stream())
+
+
 def assemble_tokens(patch: Tensor, cls: Tensor, pos: Tensor, B: int, np_: int, D: int) -> Tensor:
     net = torch.empty((B, np_ + 1, D), dtype=torch.float32, device=patch.device)
     call("b200_assemble_tokens", patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), net.data_ptr(), B, np_, D, _stream())

@@ -126,16 +126,21 @@ class ViTGeometry:
     def __init__(self, *, img_size: int, patch_size: int, in_channels: int, latent_dim: int, num_layers: int,
                  ff_ratio: float, eps: float, num_classes: Optional[int], conv_bias: bool = True,
                  embedding_norm_eps: Optional[float] = None, norm_after_head: bool = False,
-                 output_dim: Optional[int] = None, activation: str = "GELU"):
+                 output_dim: Optional[int] = None, activation: str = "GELU",
+                 context_length: Optional[int] = None, causal: bool = False):
         if latent_dim % 64 != 0:
             raise NotImplementedError("latent_dim must be a multiple of 64 (head dim 64, transformer.py:61)")
-        if patch_size % 16 != 0 or img_size % patch_size != 0:
+        # token mode (TeTEncoder, nlp/encoder/transformer.py:16-99): the input is an embedded sequence [B, T, D]; no patch
+        # stem, no head token; the head is PreNorm(Identity) = LayerNorm over every token
+        self.tokens = context_length is not None
+        self.causal = causal
+        if not self.tokens and (patch_size % 16 != 0 or img_size % patch_size != 0):
             raise NotImplementedError("patch_size must be a multiple of 16 dividing img_size")
         self.img, self.patch, self.cin, self.D, self.L = img_size, patch_size, in_channels, latent_dim, num_layers
         self.H = latent_dim // 64
         self.FF = int(round(latent_dim * ff_ratio))
-        self.np = (img_size // patch_size) ** 2
-        self.T = self.np + 1
+        self.np = 0 if self.tokens else (img_size // patch_size) ** 2
+        self.T = int(context_length) if self.tokens else self.np + 1
         self.eps = eps
         self.C = num_classes
         # the options CLIP's vision tower switches on (multimodal/clip.py:121-135)
@@ -161,10 +166,13 @@ class ViTGeometry:
         out: List[Tuple[str, Tuple[int, ...]]] = []
         if self.out_dim is not None:
             out.append(("output_projection", (d, self.out_dim)))
-        out.append(("to_patches.projection.weight", (d, c, p, p)))
-        if self.conv_bias:
-            out.append(("to_patches.projection.bias", (d,)))
-        out += [("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, self.T, d))]
+        if self.tokens:
+            out.append(("encoder.pos_encoding.pos_encoding", (1, self.T, d)))
+        else:
+            out.append(("to_patches.projection.weight", (d, c, p, p)))
+            if self.conv_bias:
+                out.append(("to_patches.projection.bias", (d,)))
+            out += [("encoder.head_token", (1, 1, d)), ("encoder.pos_encoding.pos_encoding", (1, self.T, d))]
         if self.emb_eps is not None:
             out += [("encoder.embedding_norm.weight", (d,)), ("encoder.embedding_norm.bias", (d,))]
         for i in range(self.L):
@@ -211,6 +219,7 @@ class ViTEngine:
         self.geo = geo
         self.arena = arena
         self.reducer = None  # set by dp.attach_reducer
+        self.d_input: Optional[Tensor] = None  # token mode: gradient w.r.t. the embedded input of the last backward
         # B200_SIDE_COLSUM=1 puts the HBM-bound bias-gradient column sums on a side stream (a parallel branch of the
         # captured graph).  Off by default: measured neutral (38.4 vs 38.5 ms / step) -- the persistent GEMM holds
         # 224 KB of shared memory on every SM, so no other CTA can become resident next to it.
@@ -237,17 +246,24 @@ class ViTEngine:
         g, A = self.geo, self.arena
         if not x.is_cuda:
             raise B200Error("ViTEncoderB200 runs on CUDA only: there is no CPU fallback")
-        if x.dim() != 4 or x.shape[1] != g.cin or x.shape[2] != g.img or x.shape[3] != g.img:
+        if g.tokens:
+            if x.dim() != 3 or x.shape[1] != g.T or x.shape[2] != g.D:
+                raise ValueError(f"expected embedded tokens [B, {g.T}, {g.D}], got {tuple(x.shape)}")
+        elif x.dim() != 4 or x.shape[1] != g.cin or x.shape[2] != g.img or x.shape[3] != g.img:
             raise ValueError(f"expected input [B, {g.cin}, {g.img}, {g.img}], got {tuple(x.shape)}")
         x = x.contiguous().float()
         A.refresh_bf16()
         B, T, D, M = x.shape[0], g.T, g.D, x.shape[0] * g.T
         sv = _Saved()
         sv.B = B
-        cols = ops.patch_im2col(x, g.patch)
-        patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
-                         bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
-        net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(M, D)
+        if g.tokens:  # TeTEncoder.forward -> pre_process (api.py:419-438 without head token): x + pos
+            cols = None
+            net = ops.add_pos(x, A.p("encoder.pos_encoding.pos_encoding"), B, T, D).view(M, D)
+        else:
+            cols = ops.patch_im2col(x, g.patch)
+            patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
+                             bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
+            net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(M, D)
         sv.emb_in = None
         if g.emb_eps is not None:  # embedding_norm (api.py:433-434): its fp32 output IS the residual stream
             normed = torch.empty_like(net)
@@ -261,7 +277,7 @@ class ViTEngine:
             b = f"encoder.mixing_blocks.{i}."
             ln1, mean1, rstd1 = ops.layernorm_fwd(net, A.p(b + "token_norm.weight"), A.p(b + "token_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
             qkv = ops.gemm(ln1, A.w(b + "token_mixing.net.in_w"), bias=A.w(b + "token_mixing.net.qkv_bias"))
-            attn, lse = ops.attention_fwd(qkv, B, T, g.H)
+            attn, lse = ops.attention_fwd(qkv, B, T, g.H, causal=g.causal)
             mid = ops.gemm(attn, A.w(b + "token_mixing.net.out_linear.linear.weight"), bias=A.w(b + "token_mixing.net.out_linear.linear.bias"),
                            epilogue=ops.EPI_BIAS_RESID_F32, aux=net)
             ln2, mean2, rstd2 = ops.layernorm_fwd(mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
@@ -272,10 +288,12 @@ class ViTEngine:
                            epilogue=ops.EPI_BIAS_RESID_F32, aux=mid)
             sv.blocks.append((net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act))
             net = out
-        enc_f32 = torch.empty((B, D), dtype=torch.float32, device=x.device) if want_f32 else None
-        # head = LayerNorm over all tokens then token 0 (api.py:365,397-402): only row 0 of each image is needed
+        hrows, hld = (M, D) if g.tokens else (B, T * D)
+        enc_f32 = torch.empty((hrows, D), dtype=torch.float32, device=x.device) if want_f32 else None
+        # head = LayerNorm over all tokens then token 0 (api.py:365,397-402): only row 0 of each image is needed;
+        # token mode: head = PreNorm(Identity), every token is an output row
         enc_bf16, hm, hr = ops.layernorm_fwd(net, A.p(g.head_norm_key + "weight"), A.p(g.head_norm_key + "bias"), g.eps,
-                                             rows=B, dim=D, ld_x=T * D, y_f32=enc_f32)
+                                             rows=hrows, dim=D, ld_x=hld, y_f32=enc_f32)
         sv.net_last, sv.head_mean, sv.head_rstd, sv.enc_bf16 = net, hm, hr, enc_bf16
         return enc_bf16, enc_f32, sv
 
@@ -302,17 +320,25 @@ class ViTEngine:
         return d_enc
 
     def encoder_backward(self, sv: _Saved, d_enc_bf16: Tensor, G: Tensor) -> None:
-        """Writes every encoder parameter gradient into the flat arena ``G`` (overwrite semantics)."""
+        """Writes every encoder parameter gradient into the flat arena ``G`` (overwrite semantics).  ``d_enc_bf16``: the
+        gradient of the head LayerNorm's output -- bf16 [B, D] (vision: it feeds a bf16 matmul) or, in token mode,
+        fp32 [B*T, D] (the LayerNorm output itself is what the module returns)."""
         g, A = self.geo, self.arena
         B, T, D, M = sv.B, g.T, g.D, sv.B * g.T
         dev = d_enc_bf16.device
         red = self.reducer
         dnet = torch.empty((M, D), dtype=torch.float32, device=dev)
-        ops.fill_f32(dnet, 0.0)
-        ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p(g.head_norm_key + "weight"), sv.head_mean, sv.head_rstd,
-                          rows=B, dim=D, ld_x=T * D, dres=None, dx_out=dnet, ld_dx=T * D, dx_bf16=None,
-                          dgamma=A.g(g.head_norm_key + "weight", G), dbeta=A.g(g.head_norm_key + "bias", G))
-        dnet_bf = ops.cast_bf16(dnet)
+        if g.tokens:
+            dnet_bf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p(g.head_norm_key + "weight"), sv.head_mean, sv.head_rstd,
+                              rows=M, dim=D, ld_x=D, dres=None, dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,
+                              dgamma=A.g(g.head_norm_key + "weight", G), dbeta=A.g(g.head_norm_key + "bias", G))
+        else:
+            ops.fill_f32(dnet, 0.0)
+            ops.layernorm_bwd(d_enc_bf16, sv.net_last, A.p(g.head_norm_key + "weight"), sv.head_mean, sv.head_rstd,
+                              rows=B, dim=D, ld_x=T * D, dres=None, dx_out=dnet, ld_dx=T * D, dx_bf16=None,
+                              dgamma=A.g(g.head_norm_key + "weight", G), dbeta=A.g(g.head_norm_key + "bias", G))
+            dnet_bf = ops.cast_bf16(dnet)
         # bias gradient of the last block's FF2 (dY = dnet_bf); every other Linear whose dY comes out of a LayerNorm
         # backward gets its bias gradient from that kernel (dx_colsum)
         self._bias_grad(dnet_bf, A.g(f"encoder.mixing_blocks.{g.L - 1}.channel_mixing.net.3.linear.bias", G))
@@ -337,7 +363,7 @@ class ViTEngine:
             # attention: mid = net + Wo attn + bo
             dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
             ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
-            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H, dbias=A.g(b + "token_mixing.net.qkv_bias", G))
+            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H, causal=g.causal, dbias=A.g(b + "token_mixing.net.qkv_bias", G))
             dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
             ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
             self._join_side()  # dnet_bf is overwritten below, and this block's bias gradients must be complete
@@ -354,6 +380,12 @@ class ViTEngine:
                               dres=None, dx_out=dpre, ld_dx=D, dx_bf16=None,
                               dgamma=A.g("encoder.embedding_norm.weight", G), dbeta=A.g("encoder.embedding_norm.bias", G))
             dnet = dpre
+        if g.tokens:  # net = x + pos: the input gradient is dnet itself
+            ops.add_pos_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), B, T, D)
+            self.d_input = dnet.view(B, T, D)
+            if red is not None:
+                red.ready("stem", G)
+            return
         # tokens = cat(cls, patches) + pos ; patches = conv(x)
         dpatch = ops.assemble_tokens_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), A.g("encoder.head_token", G), B, g.np, D)
         ops.wgrad(dpatch, sv.cols, A.g("to_patches.projection.weight", G).view(D, -1))
@@ -573,6 +605,89 @@ class ViTEncoderB200(nn.Module):
 
     def encode(self, net: Tensor) -> Tensor:  # IEncoder.encode, cv/common.py:42-50
         return self.forward(net)
+
+
+class _TokenEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, module: "TeTEncoderB200", x: Tensor, *params: Tensor) -> Tensor:
+        _, enc_f32, sv = module.engine.encoder_forward(x, want_f32=True)
+        ctx.module, ctx.sv = module, sv
+        return enc_f32.view(x.shape[0], module.geo.T, module.geo.D)
+
+    @staticmethod
+    def backward(ctx: Any, d_out: Tensor) -> Tuple[Any, ...]:
+        module, sv = ctx.module, ctx.sv
+        arena, eng = module.arena, module.engine
+        keys = module.all_keys
+        G = _pick_grad_arena(arena, keys)
+        eng.encoder_backward(sv, d_out.contiguous().float().view(-1, module.geo.D), G)  # fp32: the LN output is the module output
+        if eng.reducer is not None:
+            eng.reducer.finish()
+        _publish_grads(arena, G, keys)
+        ctx.sv = None
+        d_in, eng.d_input = eng.d_input, None
+        return (None, d_in) + (None,) * len(keys)
+
+
+class TeTEncoderB200(nn.Module):
+    """Drop-in for ``TeTEncoder`` (registered as ``tet``, cflearn/modules/nlp/encoder/transformer.py:16-99): the text
+    tower's transformer stack on an already embedded sequence [B, T, D] -> LayerNorm-ed tokens [B, T, D] (fp32).
+    Same kernels as the ViT blocks with the causal flag of the attention kernels (``use_triu_attn_mask``); the
+    ``attention_mask`` buffer is kept so that ``state_dict`` keys match the reference's."""
+
+    def __init__(self, latent_dim: int = 384, context_length: int = 77, *, use_triu_attn_mask: bool = False, num_layers: int = 12,
+                 dropout: float = 0.0, drop_path_rate: float = 0.0, norm_position: str = "pre_norm",
+                 norm_type: Optional[str] = "layer", norm_kwargs: Optional[Dict[str, Any]] = None,
+                 embedding_norm: Optional[nn.Module] = None, embedding_dropout: Optional[float] = None,
+                 residual_after_norm: bool = False, feedforward_dim_ratio: float = 4.0,
+                 attention_kwargs: Optional[Dict[str, Any]] = None, feedforward_kwargs: Optional[Dict[str, Any]] = None,
+                 use_positional_encoding: bool = True, head_pooler: Optional[str] = None, no_head_norm: Optional[bool] = None,
+                 norm_after_head: bool = False):
+        super().__init__()
+        if dropout != 0.0 or drop_path_rate != 0.0 or norm_position != "pre_norm" or norm_type != "layer" or residual_after_norm \
+                or embedding_dropout not in (None, 0.0) or not use_positional_encoding or head_pooler is not None \
+                or no_head_norm not in (None, False) or norm_after_head:
+            raise NotImplementedError("TeTEncoderB200 implements the configuration CLIP's text tower uses (pre-norm LayerNorm, "
+                                      "no dropout / drop-path, learned positions, head_pooler=None)")
+        ak = dict(attention_kwargs or {})
+        if ak.get("num_heads", 6) != latent_dim // 64 or not ak.get("bias", True) or set(ak) - {"num_heads", "bias"}:
+            raise NotImplementedError("TeTEncoderB200 needs attention_kwargs num_heads = latent_dim // 64 (head dim 64) and bias=True")
+        fk = dict(feedforward_kwargs or {})
+        if set(fk) - {"activation"}:
+            raise NotImplementedError(f"unsupported feedforward_kwargs: {sorted(set(fk) - {'activation'})}")
+        emb_eps: Optional[float] = None
+        if embedding_norm is not None:
+            if not isinstance(embedding_norm, nn.LayerNorm) or tuple(embedding_norm.normalized_shape) != (latent_dim,) \
+                    or not embedding_norm.elementwise_affine or embedding_norm.bias is None:
+                raise NotImplementedError("embedding_norm must be an affine nn.LayerNorm(latent_dim)")
+            emb_eps = float(embedding_norm.eps)
+        if use_triu_attn_mask:  # transformer.py:42-48
+            self.register_buffer("attention_mask", torch.ones(context_length, context_length, dtype=torch.bool).triu_(1))
+        else:
+            self.attention_mask = None
+        eps = float((norm_kwargs or {}).get("eps", 1e-6))
+        self.geo = ViTGeometry(img_size=0, patch_size=16, in_channels=0, latent_dim=latent_dim, num_layers=num_layers,
+                               ff_ratio=feedforward_dim_ratio, eps=eps, num_classes=None, embedding_norm_eps=emb_eps,
+                               activation=fk.get("activation", "GELU"), context_length=context_length, causal=bool(use_triu_attn_mask))
+        spec = self.geo.spec(with_head=False)
+        self.arena = ParamArena(spec)
+        params: Dict[str, nn.Parameter] = {}
+        for key, shape in spec:
+            p = nn.Parameter(_init_param(key, shape))
+            if embedding_norm is not None and key.startswith("encoder.embedding_norm."):
+                p.data.copy_(getattr(embedding_norm, key.rsplit(".", 1)[1]).data)
+            params[key] = p
+            _register_dotted(self, key, p)
+        self.arena.attach(params)
+        self.engine = ViTEngine(self.geo, self.arena)
+        self.all_keys = [k for k, _ in spec]
+        self.latent_dim = latent_dim
+
+    def forward(self, net: Tensor, mask: Optional[Tensor] = None, *, apply_head: bool = True, clip_skip: int = 0, **kwargs: Any) -> Tensor:
+        if mask is not None or not apply_head or clip_skip != 0:
+            raise NotImplementedError("TeTEncoderB200: custom masks, apply_head=False and clip_skip are outside the fused path")
+        self.arena.ensure()
+        return _TokenEncoderFn.apply(self, net, *[self.arena.params[k] for k in self.all_keys])
 
 
 class VanillaClassifierB200(ViTEncoderB200):

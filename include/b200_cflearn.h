@@ -155,6 +155,10 @@ int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* 
                          int D, cudaStream_t stream);
 int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, float* dcls, int B, int np, int D,
                              int accumulate, cudaStream_t stream);
+/* Text-tower input stage (TeTEncoder, cflearn/modules/nlp/encoder/transformer.py:92 -> mixed_stacks/api.py:419-438 without
+ * a head token): net f32 [B, T, D] = x f32 [B, T, D] + pos f32 [T, D];  backward: dpos = sum over the batch of dnet. */
+int b200_add_pos(const float* x, const float* pos, float* net, int B, int T, int D, cudaStream_t stream);
+int b200_add_pos_bwd(const float* dnet, float* dpos, int B, int T, int D, int accumulate, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Cross entropy with integer labels (cflearn/losses/basic.py:137-141: -log_softmax(logits,1).gather(1,labels),

@@ -105,6 +105,36 @@ def pin_clip_vision(name, batch, autocast_bf16):
     return cfg, x, up, out.detach(), r_grads
 
 
+def pin_tet(name, batch, autocast_bf16):
+    """Text tower stack: the oracle vs the reference's TeTEncoder as CLIP._init_text configures it (clip.py:175-188)."""
+    load_reference_modules()
+    from cflearn.modules.nlp.encoder.transformer import TeTEncoder
+
+    cfg = vo.tet_config(name)
+    d, t = cfg["latent_dim"], cfg["context_length"]
+    enc = TeTEncoder(d, t, use_triu_attn_mask=True, num_layers=cfg["num_layers"], norm_kwargs={"eps": cfg["eps"]},
+                     attention_kwargs={"num_heads": d // 64}, feedforward_kwargs={"activation": "quick_gelu"}, head_pooler=None)
+    keys = [(k, tuple(v.shape)) for k, v in enc.state_dict().items()]
+    assert keys[0] == ("attention_mask", (t, t)) and keys[1:] == vo.tet_state_dict_spec(cfg), "state_dict keys / order / shapes"
+    sd = vo.tet_init_state_dict(cfg, seed=0)
+    enc.load_state_dict(sd, strict=False)
+    enc.train()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, t, d, generator=g) * 0.5
+    up = torch.randn(batch, t, d, generator=g)
+    xin = x.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast_bf16):
+        out = enc(xin)
+    (out.float() * up).sum().backward()
+    r_grads = {k: p.grad for k, p in enc.named_parameters()}
+    o_out, o_dx, o_grads = vo.tet_train_step(sd, x, up, cfg, autocast_bf16=autocast_bf16)
+    assert torch.equal(o_out, out.detach()) and torch.equal(o_dx, xin.grad), "output / input gradient differ from the reference"
+    for k in r_grads:
+        assert torch.equal(o_grads[k], r_grads[k]), f"grad {k} differs from the reference"
+    print(f"pinned {name} B={batch} {'bf16' if autocast_bf16 else 'fp32'}: {len(r_grads)} grads + dx bit-identical to the reference")
+    return cfg, x, up, out.detach(), xin.grad.detach(), r_grads
+
+
 def known_answer_attention():
     """tests/test_blocks.py:147-176 logic, pointed at the oracle's attention(): == nn.MultiheadAttention, atol 1e-4."""
     torch.manual_seed(0)
@@ -162,6 +192,14 @@ def main():
     tiny = reference_clip_vision(vo.vit_config("clip_vision_tiny"))
     with open(os.path.join(GOLDEN, "clip_vision_tiny_keys.json"), "w") as f:
         json.dump({"keys": [[k, list(v.shape)] for k, v in tiny.state_dict().items()]}, f, indent=1)
+    # CLIP's text tower stack (TeTEncoder): real shape pinned once, a tiny one stored
+    pin_tet("clip_text", 2, True)
+    ref = {}
+    for mode in (False, True):
+        cfg, x, up, r_out, r_dx, r_grads = pin_tet("clip_text_tiny", 3, mode)
+        ref["bf16" if mode else "fp32"] = {"out": r_out, "dx": r_dx, "grads": {k: v.clone() for k, v in r_grads.items()}}
+    torch.save({"config_name": "clip_text_tiny", "weights_seed": 0, "x": x, "upstream": up, "reference": ref},
+               os.path.join(GOLDEN, "clip_text_tiny_reference.pt"))
     print("wrote", os.listdir(GOLDEN))
 
 

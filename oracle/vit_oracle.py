@@ -234,3 +234,79 @@ def encoder_train_step(sd: StateDict, x: Tensor, upstream: Tensor, cfg: Dict[str
         out = encoder_forward(params, x, cfg, taps if want_taps else None)
     (out.float() * upstream).sum().backward()
     return out.detach(), {k: v.grad for k, v in params.items()}, {k: v.detach() for k, v in taps.items()}
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# text tower: TeTEncoder (nlp/encoder/transformer.py:16-99) as CLIP._init_text builds it (multimodal/clip.py:175-188)
+# -----------------------------------------------------------------------------------------------------------------
+def tet_config(name: str = "clip_text") -> Dict[str, int]:
+    table = {
+        # CLIP defaults (clip.py:47-62): width 512, 8 heads, 12 layers, context 77, causal mask, QuickGELU, eps 1e-5
+        "clip_text": dict(latent_dim=512, context_length=77, num_layers=12, causal=True, activation="quick_gelu", eps=1e-5),
+        "clip_text_tiny": dict(latent_dim=128, context_length=12, num_layers=2, causal=True, activation="quick_gelu", eps=1e-5),
+        "clip_text_small": dict(latent_dim=256, context_length=77, num_layers=3, causal=True, activation="quick_gelu", eps=1e-5),
+    }
+    return dict(table[name])
+
+
+def tet_state_dict_spec(cfg: Dict[str, int]) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Parameters of TeTEncoder in state_dict order (the persistent bool buffer ``attention_mask`` [T, T] comes first in
+    the reference's state_dict when use_triu_attn_mask=True, transformer.py:42-48; it is not a parameter)."""
+    d, t = cfg["latent_dim"], cfg["context_length"]
+    ff = 4 * d
+    spec: List[Tuple[str, Tuple[int, ...]]] = [("encoder.pos_encoding.pos_encoding", (1, t, d))]
+    for i in range(cfg["num_layers"]):
+        b = f"encoder.mixing_blocks.{i}."
+        spec += [
+            (b + "token_norm.weight", (d,)), (b + "token_norm.bias", (d,)),
+            (b + "token_mixing.net.in_w", (3 * d, d)), (b + "token_mixing.net.qkv_bias", (3 * d,)),
+            (b + "token_mixing.net.out_linear.linear.weight", (d, d)), (b + "token_mixing.net.out_linear.linear.bias", (d,)),
+            (b + "channel_norm.weight", (d,)), (b + "channel_norm.bias", (d,)),
+            (b + "channel_mixing.net.0.linear.weight", (ff, d)), (b + "channel_mixing.net.0.linear.bias", (ff,)),
+            (b + "channel_mixing.net.3.linear.weight", (d, ff)), (b + "channel_mixing.net.3.linear.bias", (d,)),
+        ]
+    spec += [("encoder.head.norms.0.weight", (d,)), ("encoder.head.norms.0.bias", (d,))]
+    return spec
+
+
+def tet_init_state_dict(cfg: Dict[str, int], seed: int = 0) -> StateDict:
+    g = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for key, shape in tet_state_dict_spec(cfg):
+        if key.endswith("norm.weight") or key.endswith("norms.0.weight"):
+            t = torch.ones(shape) + 0.1 * torch.randn(shape, generator=g)
+        elif key.endswith("bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif key.endswith("pos_encoding"):
+            t = 0.01 * torch.randn(shape, generator=g)  # clip.py:196
+        else:
+            t = torch.randn(shape, generator=g) * (shape[-1] ** -0.5) * 0.7  # clip.py:197-206 scales, roughly
+        sd[key] = t.float()
+    return sd
+
+
+def tet_forward(sd: StateDict, net: Tensor, cfg: Dict[str, int]) -> Tensor:
+    """TeTEncoder.forward (transformer.py:77-99) on an embedded sequence [B, T, D]: pre_process = + positional encoding
+    (api.py:419-438, no head token), pre-norm blocks with the upper-triangular mask (:42-48 -> attentions.py:246-253),
+    post_process = PreNorm(Identity): LayerNorm over every token (api.py:383-402)."""
+    d = cfg["latent_dim"]
+    heads = d // 64
+    eps, act = cfg["eps"], cfg["activation"]
+    net = net + sd["encoder.pos_encoding.pos_encoding"]
+    for i in range(cfg["num_layers"]):
+        b = f"encoder.mixing_blocks.{i}."
+        t = F.layer_norm(net, (d,), sd[b + "token_norm.weight"], sd[b + "token_norm.bias"], eps)
+        net = net + attention(sd, b + "token_mixing.net.", t, heads, causal=cfg["causal"])
+        c = F.layer_norm(net, (d,), sd[b + "channel_norm.weight"], sd[b + "channel_norm.bias"], eps)
+        net = net + feed_forward(sd, b + "channel_mixing.net.", c, act)
+    return F.layer_norm(net, (d,), sd["encoder.head.norms.0.weight"], sd["encoder.head.norms.0.bias"], eps)
+
+
+def tet_train_step(sd: StateDict, x: Tensor, upstream: Tensor, cfg: Dict[str, int], *, autocast_bf16: bool):
+    """Forward + backward with ``upstream`` [B, T, D] as the gradient of the output; returns (out, dx, grads)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    xin = x.detach().clone().requires_grad_(True)
+    with torch.autocast(x.device.type, dtype=torch.bfloat16, enabled=autocast_bf16):
+        out = tet_forward(params, xin, cfg)
+    (out.float() * upstream).sum().backward()
+    return out.detach(), xin.grad, {k: v.grad for k, v in params.items()}

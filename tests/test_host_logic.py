@@ -98,6 +98,27 @@ def test_clip_vision_tower_options_mirror_reference_keys():
     assert m.geo.quick_gelu and m.geo.emb_eps == 1e-5 and m.geo.eps == 1e-5 and not m.geo.conv_bias
 
 
+def test_tet_encoder_surface_mirrors_reference():
+    # key names / order pinned by oracle/make_golden.py::pin_tet against the real TeTEncoder (buffer first, then parameters)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vit_oracle as vo
+
+    cfg = vo.tet_config("clip_text_tiny")
+    m = registry.build_module("tet", config=dict(latent_dim=128, context_length=12, use_triu_attn_mask=True, num_layers=2,
+                                                 norm_kwargs={"eps": 1e-5}, attention_kwargs={"num_heads": 2},
+                                                 feedforward_kwargs={"activation": "quick_gelu"}, head_pooler=None))
+    sd = m.state_dict()
+    assert list(sd)[0] == "attention_mask" and sd["attention_mask"].dtype == torch.bool
+    assert torch.equal(sd["attention_mask"], torch.ones(12, 12, dtype=torch.bool).triu(1))
+    assert [(k, tuple(v.shape)) for k, v in list(sd.items())[1:]] == vo.tet_state_dict_spec(cfg)
+    assert m.geo.causal and m.geo.tokens and m.geo.quick_gelu
+    for bad in (dict(head_pooler="mean"), dict(dropout=0.1), dict(norm_position="post_norm"), dict(attention_kwargs={"num_heads": 6})):
+        with pytest.raises(NotImplementedError):
+            registry.build_module("tet", latent_dim=128, context_length=12, **bad)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 12, 128), mask=torch.zeros(12, 12, dtype=torch.bool))
+
+
 def test_param_arena_views_and_state_dict_roundtrip():
     m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=16, img_size=32, latent_dim=128, encoder="vit",
                                                     encoder_config=dict(patch_size=16, num_layers=2)))

@@ -384,7 +384,8 @@ def test_gemm_quick_gelu_epilogues_follow_eager_rounding():
     _assert_bf16_close(h, a.float() @ b.float().t() + bias.float(), "quick-gelu epilogue: h")
     hh = h.clone().requires_grad_(True)
     ref = hh * torch.sigmoid(1.702 * hh)  # eager, bf16 tensors
-    assert (g != ref.detach()).float().mean().item() < 2e-3  # identical up to ulp flips of the approximate sigmoid
+    fl = (g != ref.detach()).float().mean().item()
+    assert fl < 2e-3, f"forward flips {fl}"  # identical up to ulp flips of the approximate sigmoid
     _assert_bf16_close(g, ref.detach().float(), "quick-gelu epilogue: act")
     # backward: dh = autograd of the three bf16 ops; dY . W with W MN-major as in the FF2 dgrad
     dy = _rand_bf16(M, K, seed=63)
@@ -394,7 +395,9 @@ def test_gemm_quick_gelu_epilogues_follow_eager_rounding():
     ref.backward(dact)
     dh = ops.gemm(dy, w2, b_mn_major=True, epilogue=ops.EPI_DQGELU_BF16, aux=h)
     torch.cuda.synchronize()
-    assert (dh != hh.grad).float().mean().item() < 5e-3  # same five roundings as autograd's kernels; only the sigmoid differs
+    fl = (dh != hh.grad).float().mean().item()
+    big = ((dh.float() - hh.grad.float()).abs() > 0.02 * hh.grad.float().abs().clamp_min(1e-3)).float().mean().item()
+    assert fl < 5e-3, f"backward flips {fl}, beyond one ulp {big}"  # same five roundings as autograd's kernels; only the sigmoid differs
     _assert_bf16_close(dh, hh.grad.float(), "quick-gelu backward epilogue")
 
 

@@ -330,3 +330,39 @@ def test_clip_vision_against_reference_golden_vectors():
         ours = rel(p.grad.cpu(), ref_fp32["grads"][k])
         theirs = rel(ref_bf16["grads"][k], ref_fp32["grads"][k])
         assert ours < max(2.0 * theirs, 5e-3), (k, ours, theirs)
+
+
+# ---- CLIP text tower stack: TeTEncoder (nlp/encoder/transformer.py) with the causal mask -----------------------------
+@pytest.mark.parametrize("name,batch", [("clip_text_tiny", 3), ("clip_text_small", 4), ("clip_text", 8)])
+def test_clip_text_stack_parity(name, batch):
+    cfg = vo.tet_config(name)
+    d, t = cfg["latent_dim"], cfg["context_length"]
+    sd = vo.tet_init_state_dict(cfg, seed=0)
+    m = registry.build_module("tet", config=dict(latent_dim=d, context_length=t, use_triu_attn_mask=True, num_layers=cfg["num_layers"],
+                                                 norm_kwargs={"eps": cfg["eps"]}, attention_kwargs={"num_heads": d // 64},
+                                                 feedforward_kwargs={"activation": "quick_gelu"}, head_pooler=None))
+    assert list(m.state_dict().keys())[0] == "attention_mask"
+    m.load_state_dict(sd, strict=False)
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(batch, t, d, generator=g) * 0.5).to(DEV)
+    up = torch.randn(batch, t, d, generator=g).to(DEV)
+    xin = x.clone().requires_grad_(True)
+    out = m(xin)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (batch, t, d)
+    (out * up).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    e_out, e_dx, e_grads = vo.tet_train_step(sdg, x, up, cfg, autocast_bf16=True)
+    f_out, f_dx, f_grads = vo.tet_train_step(sdg, x, up, cfg, autocast_bf16=False)
+    floor = rel(e_out, f_out)
+    assert rel(out, e_out) < VS_EAGER_FACTOR * floor + SLACK and rel(out, f_out) < VS_FP32_FACTOR * floor + SLACK
+    assert rel(xin.grad, e_dx) < VS_EAGER_FACTOR * rel(e_dx, f_dx) + SLACK and rel(xin.grad, f_dx) < VS_FP32_FACTOR * rel(e_dx, f_dx) + SLACK
+    assert set(grads) == set(e_grads)
+    worst = 0.0
+    for k in sorted(grads):
+        ours_vs_eager, ours_vs_fp32, eager_vs_fp32 = rel(grads[k], e_grads[k]), rel(grads[k], f_grads[k]), rel(e_grads[k], f_grads[k])
+        worst = max(worst, ours_vs_fp32 / max(eager_vs_fp32, 1e-12))
+        assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
+        assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
+    print(f"{name}: out vs eager {rel(out, e_out):.2e} (bf16 floor {floor:.2e}); worst grad err ratio {worst:.2f}")

@@ -117,3 +117,27 @@ def test_clip_vision_live_pin_against_reference():
 
     make_golden.pin_clip_vision("clip_vision_tiny", 2, False)
     make_golden.pin_clip_vision("clip_vision_tiny", 2, True)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_clip_text_stack_oracle_matches_reference_golden(mode):
+    """TeTEncoder as CLIP._init_text builds it (causal mask, QuickGELU, eps 1e-5): oracle vs the real-reference fixture."""
+    fx = torch.load(os.path.join(GOLDEN, "clip_text_tiny_reference.pt"), weights_only=False)
+    cfg = vo.tet_config(fx["config_name"])
+    sd = vo.tet_init_state_dict(cfg, seed=fx["weights_seed"])
+    out, dx, grads = vo.tet_train_step(sd, fx["x"], fx["upstream"], cfg, autocast_bf16=(mode == "bf16"))
+    ref = fx["reference"][mode]
+    tol = dict(rtol=1e-5, atol=1e-6) if mode == "fp32" else dict(rtol=2e-2, atol=2e-3)
+    assert torch.allclose(out, ref["out"], **tol)
+    assert (dx - ref["dx"]).norm() / ref["dx"].norm() < (1e-4 if mode == "fp32" else 2e-2)
+    for k, g in ref["grads"].items():
+        err = (grads[k] - g).norm() / g.norm().clamp_min(1e-20)
+        assert err < (1e-4 if mode == "fp32" else 2e-2), (k, err.item())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_clip_text_stack_live_pin_against_reference():
+    import make_golden
+
+    make_golden.pin_tet("clip_text_tiny", 2, False)
+    make_golden.pin_tet("clip_text_tiny", 2, True)
