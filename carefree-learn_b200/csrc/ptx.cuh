@@ -449,7 +449,8 @@ __device__ __forceinline__ float quick_gelu_bf16(float x) {  // x: a bf16 value
 }
 // autograd of the same three ops, with eager's bf16 rounding after every backward kernel (dy, x: bf16 values):
 //   mul:      d_net1 = bf16(dy * s),  d_s = bf16(dy * x)            s = bf16(sigmoid(t)), t = bf16(1.702 x)
-//   sigmoid:  d_t = bf16(d_s * (1 - s) * s)
+//   sigmoid:  d_t = bf16(bf16(d_s * bf16(1 - s)) * s)   -- ATen's CUDA sigmoid_backward evaluates `a * (1 - b) * b` in the
+//             tensor's own type (c10::BFloat16 arithmetic rounds after every operator), unlike its opmath forward kernels
 //   scale:    d_net2 = bf16(d_t * 1.702)
 //   sum:      bf16(d_net1 + d_net2)   (the caller rounds the sum)
 __device__ __forceinline__ float quick_gelu_bf16_grad(float x, float dy) {
@@ -457,7 +458,7 @@ __device__ __forceinline__ float quick_gelu_bf16_grad(float x, float dy) {
     const float sg = bf16_round(fast_sigmoid(t));
     const float d1 = bf16_round(dy * sg);
     const float ds = bf16_round(dy * x);
-    const float dt = bf16_round(ds * (1.0f - sg) * sg);
+    const float dt = bf16_round(bf16_round(ds * bf16_round(1.0f - sg)) * sg);
     const float d2 = bf16_round(dt * 1.702f);
     return d1 + d2;
 }

@@ -397,7 +397,9 @@ def test_gemm_quick_gelu_epilogues_follow_eager_rounding():
     torch.cuda.synchronize()
     fl = (dh != hh.grad).float().mean().item()
     big = ((dh.float() - hh.grad.float()).abs() > 0.02 * hh.grad.float().abs().clamp_min(1e-3)).float().mean().item()
-    assert fl < 5e-3, f"backward flips {fl}, beyond one ulp {big}"  # same five roundings as autograd's kernels; only the sigmoid differs
+    # same rounding points as autograd's CUDA kernels (incl. the per-operator bf16 rounding inside sigmoid_backward);
+    # what is left are flips from the approximate sigmoid propagating through the five roundings
+    assert fl < 1e-2 and big < 1e-3, f"backward flips {fl}, beyond one ulp {big}"
     _assert_bf16_close(dh, hh.grad.float(), "quick-gelu backward epilogue")
 
 
