@@ -151,7 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tma_prefetch_desc(&tmKV);
             mbar_init(bar_load, 1);
             mbar_init(bar_s, 1);
-            mbar_init(bar_p, 256);
+            mbar_init(bar_p, 8);  // one arrival per softmax warp (256 per-thread arrivals serialise on the barrier word)
             mbar_init(bar_o, 1);
             fence_mbar_init();
             // issue the loads right away: they overlap the TMEM allocation and the CTA-wide sync below
@@ -258,7 +258,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         xch_sum[half * 128 + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(bar_p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         sum = xch_sum[r] + xch_sum[128 + r];
         // O = P V
@@ -349,9 +350,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             mbar_init(bar_kvload, 1);
             mbar_init(bar_s, 1);
             mbar_init(bar_sdp, 1);
-            mbar_init(bar_pds, 256);
+            mbar_init(bar_pds, 8);     // one arrival per compute warp
             mbar_init(bar_kv, 1);
-            mbar_init(bar_kvfree, 256);
+            mbar_init(bar_kvfree, 8);
             fence_mbar_init();
             mbar_expect_tx(bar_qdo, static_cast<uint32_t>(n_mt) * 2u * 16384u);
             for (int mt = 0; mt < n_mt; ++mt) {
@@ -517,7 +518,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 fence_proxy_async_smem();
                 tc_fence_before_sync();
-                mbar_arrive(bar_pds);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pds);
                 if (mt == n_mt - 1) {
                     // dK / dV of this key tile are complete (and, on the last key tile, so are all dQ); every MMA that read
                     // sP / sDS has retired, so sP doubles as the staging area of the coalesced stores
@@ -529,7 +531,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     if (ch == 0) store_rows_coalesced<4, true>(stage, g0 + p.D, D3, taddr + TM_DK, p.scale, p.T - key0, lane, cs);
                     else         store_rows_coalesced<4, true>(stage, g0 + 2 * p.D, D3, taddr + TM_DV, 1.0f, p.T - key0, lane, cs);
                     tc_fence_before_sync();
-                    mbar_arrive(bar_kvfree);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_kvfree);
                     // the next key tile's P / dS chunks of another warp may land in this warp's staging rows
                     if (kt + 1 < n_kt) asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
