@@ -1,9 +1,11 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (fp32 accumulate in TMEM)
 //
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages of 48 KB)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma 128x256x16)
-//   warps 2..9  : epilogue (tcgen05.ld -> registers -> swizzled smem transpose -> fused math -> coalesced 16-byte
-//                 global stores; aux operands by coalesced global loads issued one chunk ahead)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring: 6 stages of 32 KB in the default
+//                 cta_group::2 mode, where each CTA of a pair stores its A rows and half of B; 4 stages of 48 KB otherwise)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma: 256x256x16 per CTA pair, or 128x256x16)
+//   warps 2..   : epilogue, 8 warps (bias-only, split-K) or 16 (GELU / dGELU / fp32-residual variants): tcgen05.ld ->
+//                 registers -> swizzled smem transpose -> fused math -> coalesced 16-byte global stores; aux operands by
+//                 coalesced global loads issued ahead of use
 //
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
