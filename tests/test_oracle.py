@@ -141,3 +141,43 @@ def test_clip_text_stack_live_pin_against_reference():
 
     make_golden.pin_tet("clip_text_tiny", 2, False)
     make_golden.pin_tet("clip_text_tiny", 2, True)
+
+
+# ---- full CLIP forward (both towers + embedding / arg-max pooling / projection / l2-normalise / logits) ---------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_clip_oracle_matches_reference_golden(mode):
+    """oracle/clip_oracle.py vs the fixture written from the REAL reference CLIP module (oracle/make_golden_clip.py);
+    the token-embedding gather and the arg-max token pooling are integer ops: their gradients land on exactly the
+    rows that were looked up."""
+    import clip_oracle as co
+
+    fx = torch.load(os.path.join(GOLDEN, "clip_tiny_reference.pt"), weights_only=False)
+    cfg = co.clip_config(fx["config_name"])
+    sd = co.init_state_dict(cfg, seed=fx["weights_seed"])
+    x, ids = co.synthetic_batch(cfg, fx["x"].shape[0], seed=3)
+    assert torch.equal(x, fx["x"]) and torch.equal(ids, fx["ids"])
+    logits, grads = co.train_step(sd, x, ids, fx["upstream"], cfg, autocast_bf16=(mode == "bf16"))
+    ref = fx["reference"][mode]
+    tol = dict(rtol=1e-5, atol=1e-6) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    assert logits.dtype == ref["logits"].dtype and torch.allclose(logits.float(), ref["logits"].float(), **tol)
+    for k, g in ref["grads"].items():
+        err = (grads[k] - g).norm() / g.norm().clamp_min(1e-20)
+        assert err < (1e-4 if mode == "fp32" else 3e-2), (k, err.item())
+    # integer paths: exactly the embedding rows looked up at positions <= the pooled (arg-max) position receive gradient --
+    # the causal mask keeps later tokens out of the pooled feature -- and never the padding row 0
+    ge = grads["token_embedding.weight"]
+    used = torch.zeros(cfg["vocab_size"], dtype=torch.bool)
+    pooled = ids.argmax(-1)
+    for b in range(ids.shape[0]):
+        used[ids[b, : pooled[b] + 1]] = True
+    assert torch.equal(ge.abs().sum(1) > 0, used & (torch.arange(cfg["vocab_size"]) != 0))
+    assert (ids.argmax(-1) >= 1).all() and (ids.max(-1).values == cfg["vocab_size"] - 1).all()
+    assert abs(co.symmetric_cross_entropy(torch.zeros(5, 5)).item() - torch.log(torch.tensor(5.0)).item()) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_clip_live_pin_against_reference():
+    import make_golden_clip
+
+    make_golden_clip.pin("clip_tiny", 3, False)
+    make_golden_clip.pin("clip_tiny", 3, True)
