@@ -52,6 +52,10 @@ SIGNATURES: Dict[str, Any] = {
     "b200_patch_im2col": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_embedding_fwd": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P]),
+    "b200_embedding_bwd": (c_int, [_P, _P, _P, _LL, c_int, c_int, c_int, _P]),
+    "b200_argmax_gather_rows": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "b200_scatter_rows": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_add_pos": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_add_pos_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),

@@ -427,6 +427,57 @@ __global__ void add_pos_bwd_kernel(const float* __restrict__ dnet, float* __rest
     *o = s;
 }
 
+// ---- CLIP text glue: integer-indexed row moves (bit-exact copies) ------------------------------------------------------
+// out[n, :] = W[ids[n], :]   (nn.Embedding forward, clip.py:235); ids outside [0, V) raise the flag and read row 0
+__global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ W, float* __restrict__ out,
+                                     long long n4_total, int d4, int V, int* __restrict__ bad) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4_total) return;
+    const long long n = i / d4;
+    const int c = static_cast<int>(i % d4);
+    long long id = ids[n];
+    if (id < 0 || id >= V) { if (c == 0) atomicExch(bad, 1); id = 0; }
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(W)[id * d4 + c];
+}
+// dW[ids[n], :] += dnet[n, :] for ids[n] != padding_idx (embedding_dense_backward; fp32 atomics: the summation order over
+// repeated tokens is not fixed, the set of rows touched is exact)
+__global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dnet, float* __restrict__ dW,
+                                     long long n_total, int D, int V, int padding_idx) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const long long n = i / D;
+    const int c = static_cast<int>(i % D);
+    const long long id = ids[n];
+    if (id < 0 || id >= V || id == padding_idx) return;
+    const float v = dnet[i];
+    if (v != 0.f) atomicAdd(dW + id * D + c, v);
+}
+// pos[b] = first arg-max of ids[b, :] (clip.py:250); out[b, :] = x[b, pos[b], :].  One block per sample.
+__global__ void argmax_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ x, float* __restrict__ out,
+                                     int* __restrict__ pos_out, int T, int D) {
+    __shared__ int spos;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        long long best = ids[static_cast<long long>(b) * T];
+        int bp = 0;
+        for (int t = 1; t < T; ++t) {
+            const long long v = ids[static_cast<long long>(b) * T + t];
+            if (v > best) { best = v; bp = t; }
+        }
+        spos = bp;
+        pos_out[b] = bp;
+    }
+    __syncthreads();
+    const float* src = x + (static_cast<long long>(b) * T + spos) * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) out[static_cast<long long>(b) * D + c] = src[c];
+}
+// dx[b, pos[b], :] = dout[b, :] (dx zero-filled by the caller)
+__global__ void scatter_rows_kernel(const float* __restrict__ dout, const int* __restrict__ pos, float* __restrict__ dx, int T, int D) {
+    const int b = blockIdx.x;
+    float* dst = dx + (static_cast<long long>(b) * T + pos[b]) * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = dout[static_cast<long long>(b) * D + c];
+}
+
 // thread = (t, d4): loops over the batch; dpos[t] = sum_b dnet[b,t]; dpatch = bf16(dnet[:,1:]); dcls = dpos[0]
 __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dnet, __nv_bfloat16* __restrict__ dpatch,
                                            float* __restrict__ dpos, float* __restrict__ dcls, int B, int np, int D,
@@ -696,6 +747,35 @@ extern "C" int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, fl
     const int total = (np + 1) * (D / 4);
     assemble_tokens_bwd_kernel<<<(total + 127) / 128, 128, 0, stream>>>(dnet, reinterpret_cast<__nv_bfloat16*>(dpatch_bf16), dpos, dcls, B, np, D, accumulate);
     return check_launch("assemble_tokens_bwd");
+}
+
+extern "C" int b200_embedding_fwd(const long long* ids, const float* weight, float* out, long long n, int D, int V,
+                                  int* bad_index_flag, cudaStream_t stream) {
+    if (n <= 0 || D <= 0 || D % 4 != 0 || V <= 0 || bad_index_flag == nullptr) return set_error(B200_ERR_ARG, "embedding_fwd: need D % 4 == 0 and a flag");
+    const long long total = n * (D / 4);
+    embedding_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ids, weight, out, total, D / 4, V, bad_index_flag);
+    return check_launch("embedding_fwd");
+}
+
+extern "C" int b200_embedding_bwd(const long long* ids, const float* dnet, float* dweight, long long n, int D, int V,
+                                  int padding_idx, cudaStream_t stream) {
+    if (n <= 0 || D <= 0 || V <= 0) return set_error(B200_ERR_ARG, "embedding_bwd: bad size");
+    const long long total = n * D;
+    embedding_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ids, dnet, dweight, total, D, V, padding_idx);
+    return check_launch("embedding_bwd");
+}
+
+extern "C" int b200_argmax_gather_rows(const long long* ids, const float* x, float* out, int* pos, int B, int T, int D,
+                                       cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || D <= 0) return set_error(B200_ERR_ARG, "argmax_gather_rows: bad size");
+    argmax_gather_kernel<<<B, 128, 0, stream>>>(ids, x, out, pos, T, D);
+    return check_launch("argmax_gather_rows");
+}
+
+extern "C" int b200_scatter_rows(const float* dout, const int* pos, float* dx, int B, int T, int D, cudaStream_t stream) {
+    if (B <= 0 || T <= 0 || D <= 0) return set_error(B200_ERR_ARG, "scatter_rows: bad size");
+    scatter_rows_kernel<<<B, 128, 0, stream>>>(dout, pos, dx, T, D);
+    return check_launch("scatter_rows");
 }
 
 extern "C" int b200_add_pos(const float* x, const float* pos, float* net, int B, int T, int D, cudaStream_t stream) {

@@ -17,6 +17,7 @@ from typing import Any, Callable, Dict, Optional, Type, Union
 
 import torch.nn as nn
 
+from .clip import CLIPB200
 from .fcnn import FCNNB200
 from .vit import TeTEncoderB200, VanillaClassifierB200, ViTEncoderB200
 
@@ -90,6 +91,8 @@ register_module("cv_clf")(VanillaClassifierB200)
 register_module("fcnn_b200")(FCNNB200)
 register_module("tet_b200")(TeTEncoderB200)
 register_module("tet")(TeTEncoderB200)  # cflearn/modules/nlp/encoder/transformer.py:16
+register_module("clip_b200")(CLIPB200)
+register_module("clip")(CLIPB200)  # cflearn/modules/multimodal/clip.py:21
 register_module("fcnn")(FCNNB200)  # cflearn/modules/ml/fcnn.py:12
 
 
@@ -99,7 +102,7 @@ def install_into(reference_module_dict: Dict[str, Any], *, override: bool = True
     ``register_core``'s duplicate policy is unverified, so we assign directly.  Returns the entries
     that were replaced so a caller can restore them."""
     replaced = {}
-    for name in ("encoders.vit_b200", "cv_clf_b200", "fcnn_b200", "tet_b200") + (("encoders.vit", "cv_clf", "fcnn", "tet") if override else ()):
+    for name in ("encoders.vit_b200", "cv_clf_b200", "fcnn_b200", "tet_b200", "clip_b200") + (("encoders.vit", "cv_clf", "fcnn", "tet", "clip") if override else ()):
         if name in reference_module_dict:
             replaced[name] = reference_module_dict[name]
         reference_module_dict[name] = module_dict[name]

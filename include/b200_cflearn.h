@@ -160,6 +160,18 @@ int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, 
 int b200_add_pos(const float* x, const float* pos, float* net, int B, int T, int D, cudaStream_t stream);
 int b200_add_pos_bwd(const float* dnet, float* dpos, int B, int T, int D, int accumulate, cudaStream_t stream);
 
+/* CLIP text glue (cflearn/modules/multimodal/clip.py:235,248-250): integer-indexed row moves, bit-exact.
+ *   embedding_fwd : out f32 [n, D] = weight f32 [V, D][ids[n]]; ids outside [0, V) set *bad_index_flag (device int)
+ *   embedding_bwd : dweight[ids[n]] += dnet[n] for ids[n] != padding_idx (dweight zeroed by the caller; fp32 atomics)
+ *   argmax_gather : pos[b] = first arg-max of ids[b, :]; out f32 [B, D] = x f32 [B, T, D][b, pos[b]]
+ *   scatter_rows  : dx[b, pos[b], :] = dout[b, :]   (dx zero-filled by the caller) */
+int b200_embedding_fwd(const long long* ids, const float* weight, float* out, long long n, int D, int V, int* bad_index_flag,
+                       cudaStream_t stream);
+int b200_embedding_bwd(const long long* ids, const float* dnet, float* dweight, long long n, int D, int V, int padding_idx,
+                       cudaStream_t stream);
+int b200_argmax_gather_rows(const long long* ids, const float* x, float* out, int* pos, int B, int T, int D, cudaStream_t stream);
+int b200_scatter_rows(const float* dout, const int* pos, float* dx, int B, int T, int D, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Cross entropy with integer labels (cflearn/losses/basic.py:137-141: -log_softmax(logits,1).gather(1,labels),
  * mean over the batch via ILoss._reduce, cflearn/schema.py:767-810).  logits bf16 [B, C] (ld = ldl),

@@ -366,3 +366,56 @@ def test_clip_text_stack_parity(name, batch):
         assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
         assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
     print(f"{name}: out vs eager {rel(out, e_out):.2e} (bf16 floor {floor:.2e}); worst grad err ratio {worst:.2f}")
+
+
+# ---- full CLIP: both towers + embedding / arg-max pooling / text_projection / l2-normalise / logits --------------------
+def _clip_module(cfg, sd):
+    v, t = cfg["vision"], cfg["text"]
+    m = registry.build_module("clip", config=dict(
+        img_size=v["img_size"], latent_dim=cfg["latent_dim"], in_channels=v["in_channels"], vision_latent_dim=v["latent_dim"],
+        vision_patch_size=v["patch_size"], vision_num_heads=v["latent_dim"] // 64, vision_num_layers=v["num_layers"],
+        vocab_size=cfg["vocab_size"], context_length=t["context_length"], text_latent_dim=t["latent_dim"],
+        text_num_heads=t["latent_dim"] // 64, text_num_layers=t["num_layers"]))
+    missing = m.load_state_dict(sd, strict=False)
+    assert missing.missing_keys == ["text_transformer.attention_mask"] and not missing.unexpected_keys
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name,batch", [("clip_tiny", 4), ("clip", 8)])
+def test_clip_forward_backward_parity(name, batch):
+    """``CLIP.forward`` (logits_per_image) and every parameter gradient for a seeded upstream gradient: ours vs the oracle
+    eagerly on this GPU under bf16 autocast, both against the fp32 oracle.  The embedding gather / scatter and the arg-max
+    pooling are integer-indexed copies: the gradient of the token embedding is non-zero on exactly the rows eager touches."""
+    import clip_oracle as co
+
+    cfg = co.clip_config(name)
+    sd = co.init_state_dict(cfg, seed=0)
+    x, ids = co.synthetic_batch(cfg, batch, seed=3)
+    up = torch.randn(batch, batch, generator=torch.Generator().manual_seed(9))
+    x, ids, up = x.to(DEV), ids.to(DEV), up.to(DEV)
+    m = _clip_module(cfg, sd)
+    logits = m(x, ids)
+    assert logits.dtype == torch.bfloat16 and tuple(logits.shape) == (batch, batch)
+    (logits.float() * up).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    e_logits, e_grads = co.train_step(sdg, x, ids, up, cfg, autocast_bf16=True)
+    f_logits, f_grads = co.train_step(sdg, x, ids, up, cfg, autocast_bf16=False)
+    assert e_logits.dtype == torch.bfloat16
+    floor = rel(e_logits, f_logits)
+    assert rel(logits, e_logits) < VS_EAGER_FACTOR * floor + SLACK and rel(logits, f_logits) < VS_FP32_FACTOR * floor + SLACK
+    assert set(grads) == set(e_grads)
+    for k in sorted(grads):
+        ours_vs_eager, ours_vs_fp32, eager_vs_fp32 = rel(grads[k], e_grads[k]), rel(grads[k], f_grads[k]), rel(e_grads[k], f_grads[k])
+        assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
+        assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
+    ge, ee = grads["token_embedding.weight"], e_grads["token_embedding.weight"]
+    assert torch.equal(ge.abs().sum(1) > 0, ee.abs().sum(1) > 0) and ge[0].abs().sum().item() == 0.0  # padding row untouched
+    # integer ops alone: gather and arg-max pooling are bit-exact copies
+    from cflearn_b200.clip import _ArgmaxPoolFn, _EmbeddingFn
+
+    w = sdg["token_embedding.weight"]
+    assert torch.equal(_EmbeddingFn.apply(ids, w, 0), torch.nn.functional.embedding(ids, w))
+    seq = torch.randn(batch, ids.shape[1], 64, device=DEV)
+    assert torch.equal(_ArgmaxPoolFn.apply(seq, ids), seq[torch.arange(batch, device=DEV), ids.argmax(-1)])
+    print(f"{name}: logits vs eager {rel(logits, e_logits):.2e} (bf16 floor {floor:.2e})")
