@@ -182,7 +182,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import cflearn_b200  # noqa: F401
-    from cflearn_b200 import _cabi, dp, ops, registry, vit
+    from cflearn_b200 import _cabi, dp, ops, registry
     from cflearn_b200.optim import ArenaAdam
 
     if not torch.cuda.is_available():
