@@ -181,3 +181,35 @@ def test_clip_live_pin_against_reference():
 
     make_golden_clip.pin("clip_tiny", 3, False)
     make_golden_clip.pin("clip_tiny", 3, True)
+
+
+# ---- SD-v1.5 UNet (BASELINE.json configs[4]; oracle prepared ahead of the kernels) ---------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_unet_oracle_matches_reference_golden(mode):
+    """oracle/unet_oracle.py (structure read off the state_dict keys) vs the fixture written from the REAL reference
+    UNetDiffuser (oracle/make_golden_unet.py)."""
+    import unet_oracle as uo
+
+    fx = torch.load(os.path.join(GOLDEN, "unet_tiny_reference.pt"), weights_only=False)
+    cfg = uo.unet_config(fx["config_name"])
+    sd = uo.synthetic_state_dict([(k, tuple(s)) for k, s in fx["shapes"]], seed=fx["weights_seed"])
+    out, grads = uo.train_step(sd, fx["x"], fx["timesteps"], fx["context"], fx["upstream"], cfg, autocast_bf16=(mode == "bf16"))
+    ref = fx["reference"][mode]
+    tol = dict(rtol=1e-5, atol=1e-5) if mode == "fp32" else dict(rtol=3e-2, atol=3e-2)
+    assert out.dtype == ref["out"].dtype and torch.allclose(out.float(), ref["out"].float(), **tol)
+    for k, g in ref["grads"].items():
+        # (absolute floor: e.g. the last ResBlock's conv2.bias feeds a per-channel GroupNorm, its true gradient is 0 and
+        # the fp32 value is rounding noise ~1e-6 that changes with the thread count)
+        diff = (grads[k] - g).norm().item()
+        assert diff < (1e-4 if mode == "fp32" else 3e-2) * g.norm().item() + 1e-5 * g.numel() ** 0.5, (k, diff, g.norm().item())
+    # timestep embedding known answer (unet.py:53-77): cos block first, then sin; t = 0 -> (1, ..., 1, 0, ..., 0)
+    e = uo.timestep_embedding(torch.tensor([0, 7]), 8, torch.float32)
+    assert torch.equal(e[0], torch.tensor([1.0, 1, 1, 1, 0, 0, 0, 0])) and abs(e[1, 0].item() - torch.cos(torch.tensor(7.0)).item()) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cflearn"), reason="reference tree only exists in the build container")
+def test_unet_live_pin_against_reference():
+    import make_golden_unet
+
+    make_golden_unet.pin("unet_tiny", 2, 8, 3, False)
+    make_golden_unet.pin("unet_tiny", 2, 8, 3, True)
