@@ -119,6 +119,30 @@ def test_tet_encoder_surface_mirrors_reference():
         m(torch.zeros(1, 12, 128), mask=torch.zeros(12, 12, dtype=torch.bool))
 
 
+def test_clip_module_surface_mirrors_reference():
+    # CLIP.__init__ keywords, state_dict keys / order (pinned to the real reference CLIP by oracle/make_golden_clip.py)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import clip_oracle as co
+
+    cfg = co.clip_config("clip_tiny")
+    v, t = cfg["vision"], cfg["text"]
+    m = registry.build_module("clip", config=dict(
+        img_size=v["img_size"], latent_dim=cfg["latent_dim"], vision_latent_dim=v["latent_dim"], vision_patch_size=v["patch_size"],
+        vision_num_heads=2, vision_num_layers=v["num_layers"], vocab_size=cfg["vocab_size"], context_length=t["context_length"],
+        text_latent_dim=t["latent_dim"], text_num_heads=2, text_num_layers=t["num_layers"]))
+    keys = [(k, tuple(p.shape)) for k, p in m.state_dict().items()]
+    i = [k for k, _ in keys].index("text_transformer.attention_mask")
+    assert keys[i - 1][0] == "token_embedding.weight"  # the buffer sits where the reference has it
+    assert [kv for kv in keys if kv[0] != "text_transformer.attention_mask"] == co.state_dict_spec(cfg)
+    assert abs(m.logit_scale.item() - 2.6592600) < 1e-5 and m.token_embedding.padding_idx == 0
+    for bad in (dict(use_text=False), dict(token_type_size=2), dict(text_dropout=0.1), dict(text_head_pooler="mean")):
+        with pytest.raises(NotImplementedError):
+            registry.build_module("clip", img_size=64, latent_dim=64, vision_latent_dim=128, text_latent_dim=128, text_num_heads=2,
+                                  vision_num_heads=2, **bad)
+    with pytest.raises(cflearn_b200.B200Error):
+        m(torch.zeros(1, 3, v["img_size"], v["img_size"]), torch.ones(1, t["context_length"], dtype=torch.long))  # CPU: no fallback
+
+
 def test_param_arena_views_and_state_dict_roundtrip():
     m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=16, img_size=32, latent_dim=128, encoder="vit",
                                                     encoder_config=dict(patch_size=16, num_layers=2)))
