@@ -60,8 +60,15 @@ SIGNATURES: Dict[str, Any] = {
     "b200_add_pos_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
     "b200_adam_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P, _P]),
+    "b200_adam_step_dev": (c_int, [_P, _P, _P, _P, _LL, _P, _P, c_int, _P]),
     "b200_cast_f32_to_bf16": (c_int, [_P, _P, _LL, _P]),
     "b200_fill_f32": (c_int, [_P, c_float, _LL, _P]),
+    "b200_comm_unique_id": (c_int, [_P]),
+    "b200_comm_init": (c_int, [_P, c_int, c_int, POINTER(c_void_p)]),
+    "b200_comm_allreduce_bucket": (c_int, [_P, _P, _LL, c_int, _P]),
+    "b200_comm_async_error": (c_int, [_P]),
+    "b200_comm_finalize": (c_int, [_P, c_int]),
+    "b200_comm_nccl_version": (c_int, []),
 }
 
 _lib: Optional[ctypes.CDLL] = None

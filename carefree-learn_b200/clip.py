@@ -175,9 +175,27 @@ class CLIPB200(nn.Module):
             attention_kwargs={"num_heads": text_num_heads}, feedforward_kwargs={"activation": text_feedforward_activation},
             head_pooler=text_head_pooler)
         self.text_projection = nn.Linear(text_latent_dim, latent_dim)
-        with torch.no_grad():  # clip.py:190-207 (the towers keep the encoder's own initialisation)
+        self.text_latent_dim, self.text_num_layers = text_latent_dim, text_num_layers
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        """clip.py:188-207: the text tower is re-initialised with CLIP's own standard deviations (the vision tower keeps the
+        encoder's trunc_normal(0.02) initialisation, as in the reference)."""
+        tld = self.text_latent_dim
+        proj_std = (tld ** -0.5) * ((2 * self.text_num_layers) ** -0.5)
+        attn_std = tld ** -0.5
+        fc_std = (2 * tld) ** -0.5
+        P = self.text_transformer.arena.params
+        with torch.no_grad():
             nn.init.normal_(self.token_embedding.weight, std=0.02)
-            nn.init.normal_(self.text_projection.weight, std=text_latent_dim ** -0.5)
+            nn.init.normal_(P["encoder.pos_encoding.pos_encoding"], std=0.01)
+            for i in range(self.text_num_layers):
+                b = f"encoder.mixing_blocks.{i}."
+                nn.init.normal_(P[b + "token_mixing.net.in_w"], std=attn_std)
+                nn.init.normal_(P[b + "token_mixing.net.out_linear.linear.weight"], std=proj_std)
+                nn.init.normal_(P[b + "channel_mixing.net.0.linear.weight"], std=fc_std)
+                nn.init.normal_(P[b + "channel_mixing.net.3.linear.weight"], std=proj_std)
+            nn.init.normal_(self.text_projection.weight, std=tld ** -0.5)
             nn.init.zeros_(self.text_projection.bias)
 
     def encode_image(self, image: Tensor) -> Tensor:  # clip.py:209-216

@@ -589,11 +589,12 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
     uint32_t boxkv[3] = {64, static_cast<uint32_t>(tp), 1};
     if ((rc = make_tmap(&tmQ, qkv_bf16, 2, 3, dims, strides, boxq, 128)) != 0) return rc;
     if ((rc = make_tmap(&tmKV, qkv_bf16, 2, 3, dims, strides, boxkv, 128)) != 0) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};  // per device: the attribute belongs to the (function, device) pair
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
-        configured = true;
+        configured[dev] = true;
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = tp; p.scale = scale; p.causal = causal;
@@ -621,11 +622,12 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
         uint32_t box[3] = {64, 128, 1};
         if ((rc = make_tmap(&tmDO, dout_bf16, 2, 3, dims, strides, box, 128)) != 0) return rc;
     }
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
-        configured = true;
+        configured[dev] = true;
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;

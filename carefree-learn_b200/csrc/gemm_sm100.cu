@@ -772,6 +772,12 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
     return 0;
 }
 
+int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -790,12 +796,13 @@ static int g_gemm_multicast = 2;  // 0: one CTA per tile; 1: CTA pairs + TMA mul
 template <int EPI, bool TWO_SM, bool QUICK>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBh,
                        const GemmParams& p, int grid, cudaStream_t stream) {
-    static bool configured = false;  // per-process; attribute is per-function (all devices share the module image)
+    static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
     cudaError_t e;
-    if (!configured) {
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI, TWO_SM, QUICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
-        configured = true;
+        configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));

@@ -619,6 +619,40 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 __global__ void increment_kernel(int* counter) { counter[0] += 1; }
 
+// Same update with EVERY hyper-parameter read from device memory (hyper = {lr, beta1, beta2, eps, weight_decay, grad_scale}):
+// a captured CUDA graph then follows a learning-rate schedule (the reference's default scheduler is "warmup",
+// cflearn/pipeline/blocks/basic.py:334-352) by rewriting 24 bytes between replays.  grad_scale multiplies the gradient
+// first (1 / world_size after a SUM all-reduce, or a clip coefficient, cflearn/schema.py:981-982).
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n4, const float* __restrict__ hyper,
+                                const int* __restrict__ step_dev) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
+    const float t = static_cast<float>(step_dev[0]);
+    const float bc1 = 1.0f - powf(b1, t);
+    const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float step = lr / bc1;
+    auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+        gw = gw * gs + wd * pw;
+        mw += (gw - mw) * (1.0f - b1);
+        vw = vw * b2 + (1.0f - b2) * gw * gw;
+        const float denom = sqrtf(vw) / bc2_sqrt + eps;
+        pw -= step * (mw / denom);
+    };
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+}
+
 template <int NV>
 static int ln_fwd_launch(const float* x, long long ld_x, const float* gamma, const float* beta, void* y, float* y32,
                          float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t st) {
@@ -832,6 +866,19 @@ extern "C" int b200_adam_step(float* params, const float* grads, float* exp_avg,
     adam_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n4, lr, beta1,
                                                                           beta2, eps, weight_decay, bc1, bc2_sqrt, step_dev);
     return check_launch("adam_step");
+}
+extern "C" int b200_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                                  const float* hyper_dev, int* step_dev, int increment, cudaStream_t stream) {
+    if (n <= 0 || n % 4 != 0) return set_error(B200_ERR_ARG, "adam_step_dev: n must be a positive multiple of 4");
+    if (hyper_dev == nullptr || step_dev == nullptr) return set_error(B200_ERR_ARG, "adam_step_dev: hyper_dev and step_dev are required");
+    if (increment) {
+        increment_kernel<<<1, 1, 0, stream>>>(step_dev);
+        int rc = check_launch("adam_step_increment");
+        if (rc) return rc;
+    }
+    const long long n4 = n / 4;
+    adam_dev_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n4, hyper_dev, step_dev);
+    return check_launch("adam_step_dev");
 }
 extern "C" int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream) {
     if (n <= 0) return set_error(B200_ERR_ARG, "fill: n <= 0");

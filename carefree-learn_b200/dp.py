@@ -13,11 +13,14 @@ finding 3: the reference defines multi-GPU parity only mathematically).
 """
 from __future__ import annotations
 
+import ctypes
 import os
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch
 import torch.distributed as dist
+
+from . import _cabi
 
 BucketKey = Union[int, str]
 
@@ -102,6 +105,110 @@ class GradBucketReducer:
         self._pending.clear()
         if not on_host:
             torch.cuda.current_stream().wait_stream(self._stream())
+
+
+class NativeComm:
+    """The library's own NCCL communicator (C-ABI ``b200_comm_*``, csrc/comm.cu): one per process / GPU.
+
+    Unlike ``torch.distributed``'s ProcessGroup, its all-reduce is a plain stream operation -- no Work object, no
+    watchdog thread -- so it can be captured into the CUDA graph of the training step and forked onto a side stream.
+    The 128-byte NCCL unique id is created by rank 0 and handed to the other ranks through whatever process group
+    already exists (``bootstrap_group``; gloo or nccl), exactly once."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, bootstrap_group: Any = None):
+        if not dist.is_initialized():
+            raise RuntimeError("NativeComm needs an initialised torch.distributed group to ship the NCCL unique id")
+        # NCCL kernels and the persistent GEMMs of the backward share the SMs: cap the channels NCCL may use so that the
+        # engine can leave exactly that many SMs free while a bucket is in flight (B200_COMM_CTAS, default 16)
+        self.ctas = int(os.environ.get("B200_COMM_CTAS", "16"))
+        os.environ.setdefault("NCCL_MAX_CTAS", str(self.ctas))
+        self.rank, self.world, self.device = rank, world, device
+        lib = _cabi.lib()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _cabi.check(lib.b200_comm_unique_id(buf), "b200_comm_unique_id")
+        backend = dist.get_backend(bootstrap_group)
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if backend == "nccl":
+            t = t.to(device)
+        dist.broadcast(t, src=0, group=bootstrap_group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _cabi.check(lib.b200_comm_init(raw, rank, world, ctypes.byref(handle)), "b200_comm_init")
+        self._h = handle
+        self.nccl_version = int(lib.b200_comm_nccl_version())
+
+    def allreduce_(self, t: torch.Tensor, *, average: bool = True) -> None:
+        """In-place fp32 all-reduce of a contiguous tensor on the CURRENT stream."""
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise _cabi.B200Error("NativeComm.allreduce_: contiguous fp32 CUDA tensor required")
+        _cabi.call("b200_comm_allreduce_bucket", self._h, t.data_ptr(), t.numel(), int(average), torch.cuda.current_stream().cuda_stream)
+
+    def check(self) -> None:
+        """Raises if NCCL recorded an asynchronous error on the communicator (dead peer, failed transport): the caller
+        aborts instead of waiting on a collective that will never finish."""
+        _cabi.call("b200_comm_async_error", self._h)
+
+    def close(self, abort: bool = False) -> None:
+        if self._h is not None and self._h.value:
+            _cabi.lib().b200_comm_finalize(self._h, int(abort))
+            self._h = None
+
+
+class NativeBucketReducer(GradBucketReducer):
+    """Same bucket protocol as ``GradBucketReducer`` over a ``NativeComm``: works eagerly AND under stream capture.
+
+    ``ready(key)`` forks the communication stream off the compute stream (event) and enqueues the bucket's all-reduce
+    there; ``finish()`` joins.  While a bucket is in flight the engine launches its next GEMM on ``148 - comm.ctas`` SMs
+    (``engine.shrink_next``): the persistent GEMM statically assigns its tiles to its CTAs, so CTAs that cannot start
+    because NCCL holds their SM would otherwise stretch the kernel by the whole duration of the all-reduce."""
+
+    def __init__(self, arena, num_layers: int, comm: NativeComm, engine: Any = None):
+        super().__init__(arena, num_layers, process_group=None)
+        self.comm = comm
+        self.world = comm.world
+        self.engine = engine
+        self._launched = False
+
+    def ready(self, key: BucketKey, grad: Optional[torch.Tensor] = None) -> None:
+        if self.world == 1:
+            return
+        if key == "tail" and "proj" in self.buckets:
+            self.ready("proj", grad)
+        lo, hi = self.buckets[key]
+        if grad is None:
+            grad = self.arena.grad
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cs = self._stream()
+        cs.wait_event(ev)
+        with torch.cuda.stream(cs):
+            self.comm.allreduce_(grad[lo:hi], average=True)
+        self._launched = True
+        if self.engine is not None and key != "stem":
+            self.engine.shrink_next = self.comm.ctas
+
+    def finish(self) -> None:
+        if self.world == 1 or not self._launched:
+            return
+        torch.cuda.current_stream().wait_stream(self._stream())
+        self._launched = False
+
+    def _stream(self) -> torch.cuda.Stream:
+        if self.comm_stream is None:
+            # high priority: at a kernel boundary the NCCL CTAs are placed before the next GEMM's
+            self.comm_stream = torch.cuda.Stream(priority=-1)
+        return self.comm_stream
+
+
+def attach_native_reducer(module, comm: NativeComm) -> NativeBucketReducer:
+    """Overlapped, capturable gradient averaging for a ViTEncoderB200 / VanillaClassifierB200."""
+    module.arena.ensure()
+    red = NativeBucketReducer(module.arena, module.geo.L, comm, module.engine)
+    module.engine.reducer = red
+    return red
 
 
 def allreduce_flat_cpu(grad: torch.Tensor, buckets: List[Tuple[int, int]], group=None) -> None:

@@ -7,7 +7,7 @@ ATen fallback.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -108,6 +108,16 @@ def gemm(
         M, N, K, epilogue, _ptr(bias), out0.data_ptr(), _ptr(out1), _ptr(aux), ldo, splits, max_ctas, _stream(),
     )
     return out0
+
+
+_NUM_SMS: Dict[int, int] = {}
+
+
+def num_sms() -> int:
+    dev = torch.cuda.current_device()
+    if dev not in _NUM_SMS:
+        _NUM_SMS[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _NUM_SMS[dev]
 
 
 def pick_splits(M: int, N: int, K: int) -> int:

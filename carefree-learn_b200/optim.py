@@ -2,16 +2,20 @@
 
 ``ArenaAdam`` mirrors ``torch.optim.Adam`` (the reference's default optimizer ``"adam"``, cflearn/optimizers.py:29-32,
 built by BuildOptimizersBlock at cflearn/pipeline/blocks/basic.py:385-558 and stepped in cflearn/schema.py:983-984):
-one kernel per step instead of one per tensor.  With ``capturable=True`` the step counter lives on the device so
-the update can be replayed from a CUDA graph.
+one kernel per step instead of one per tensor.  With ``capturable=True`` the step counter AND every hyper-parameter
+live on the device, so the update can be replayed from a CUDA graph while a scheduler keeps changing the learning rate
+(``param_groups[0]["lr"]`` is what ``torch.optim.lr_scheduler`` classes write; the reference's default scheduler is
+``warmup``, basic.py:334-352).
 
-``GraphedTrainStep`` captures ``zero_grad -> forward -> cross-entropy -> backward (-> bucketed all-reduce) -> Adam``
-(IDLModel.train, cflearn/schema.py:1174-1294, minus its per-step host work) into ONE CUDA graph: ~410 kernel launches
-per ViT-B/16 step stop costing host time, so the GPU is never waiting on Python.
+``GraphedTrainStep`` captures ``zero_grad -> forward -> cross-entropy -> backward -> bucketed gradient all-reduce ->
+Adam`` (IDLModel.train, cflearn/schema.py:1174-1294, minus its per-step host work) into ONE CUDA graph.  With more
+than one rank the all-reduces are nodes of the same graph: each transformer block's bucket is reduced on a forked
+communication stream through the library's own NCCL communicator (``dp.NativeComm``) while the backward of the
+earlier blocks is still running.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 from torch import Tensor
@@ -24,29 +28,97 @@ class ArenaAdam:
     def __init__(self, module: Any, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  capturable: bool = False):
         self.module = module
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.capturable = capturable
+        # the torch.optim surface schedulers and checkpoints use: ONE group holding every parameter of the arena
+        self.param_groups: List[Dict[str, Any]] = [dict(params=list(module.parameters()), lr=float(lr), betas=tuple(betas),
+                                                        eps=float(eps), weight_decay=float(weight_decay), grad_scale=1.0)]
+        self.defaults = {k: v for k, v in self.param_groups[0].items() if k != "params"}
         self.step_count = 0
         self.step_dev: Optional[Tensor] = None
+        self.hyper_dev: Optional[Tensor] = None
+        self._hyper_host: Optional[Tensor] = None
+        self._hyper_sent: Optional[tuple] = None
         self.exp_avg: Optional[Tensor] = None
         self.exp_avg_sq: Optional[Tensor] = None
 
+    # ---- hyper-parameters ---------------------------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.param_groups[0]["lr"] = float(value)
+
+    def set_lr(self, value: float) -> None:
+        self.lr = value
+
+    @property
+    def betas(self):
+        return self.param_groups[0]["betas"]
+
+    @property
+    def eps(self) -> float:
+        return self.param_groups[0]["eps"]
+
+    @property
+    def weight_decay(self) -> float:
+        return self.param_groups[0]["weight_decay"]
+
+    def _hyper_tuple(self) -> tuple:
+        g = self.param_groups[0]
+        return (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                float(g.get("grad_scale", 1.0)))
+
+    def sync_hyper(self) -> None:
+        """Push the current ``param_groups`` values to the device buffer the captured kernels read (24 bytes, only when
+        something changed; pinned source, asynchronous on the current stream, ordered before the next replay)."""
+        if self.hyper_dev is None:
+            return
+        cur = self._hyper_tuple()
+        if cur == self._hyper_sent:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("ArenaAdam.sync_hyper() must run outside the capture (it is a host-to-device copy of new values)")
+        self._hyper_host.copy_(torch.tensor(cur, dtype=torch.float32))
+        self.hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        self._hyper_sent = cur
+
+    # ---- state --------------------------------------------------------------------------------------------------
     def _state(self) -> None:
         arena = self.module.arena
         arena.ensure()
         if self.exp_avg is None or self.exp_avg.device != arena.flat.device:
+            dev = arena.flat.device
             self.exp_avg = torch.zeros_like(arena.flat)
             self.exp_avg_sq = torch.zeros_like(arena.flat)
             if self.capturable:
-                self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=arena.flat.device)
+                self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=dev)
+                self.hyper_dev = torch.zeros(6, dtype=torch.float32, device=dev)
+                self._hyper_host = torch.zeros(6, dtype=torch.float32).pin_memory()
+                self._hyper_sent = None
+        if self.capturable and not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
 
-    def step(self) -> None:
+    def step(self, lo: int = 0, hi: Optional[int] = None, *, increment: bool = True) -> None:
+        """Update arena elements [lo, hi) (default: everything).  ``increment=False``: a further slice of the SAME
+        optimisation step (per-bucket updates); the step counter advances once per step."""
         self._state()
         arena = self.module.arena
-        self.step_count += 1
-        call("b200_adam_step", arena.flat.data_ptr(), arena.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-             arena.total, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
-             self.step_count, None if self.step_dev is None else self.step_dev.data_ptr(), ops._stream())
+        hi = arena.total if hi is None else hi
+        n = hi - lo
+        off = 4 * lo
+        if self.capturable:
+            call("b200_adam_step_dev", arena.flat.data_ptr() + off, arena.grad.data_ptr() + off, self.exp_avg.data_ptr() + off,
+                 self.exp_avg_sq.data_ptr() + off, n, self.hyper_dev.data_ptr(), self.step_dev.data_ptr(), int(increment), ops._stream())
+            return
+        if increment:
+            self.step_count += 1
+        lr, b1, b2, eps, wd, gs = self._hyper_tuple()
+        if gs != 1.0:
+            raise ValueError("grad_scale needs ArenaAdam(capturable=True)")
+        call("b200_adam_step", arena.flat.data_ptr() + off, arena.grad.data_ptr() + off, self.exp_avg.data_ptr() + off,
+             self.exp_avg_sq.data_ptr() + off, n, lr, b1, b2, eps, wd, self.step_count, None, ops._stream())
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if set_to_none:
@@ -55,34 +127,69 @@ class ArenaAdam:
 
     def state_dict(self) -> Dict[str, Any]:
         step = int(self.step_dev.item()) if self.step_dev is not None else self.step_count
-        return {"step": step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr,
-                "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        g = self.param_groups[0]
+        return {"step": step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": g["lr"],
+                "betas": g["betas"], "eps": g["eps"], "weight_decay": g["weight_decay"]}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        self._state()
+        g = self.param_groups[0]
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in sd:
+                g[k] = tuple(sd[k]) if k == "betas" else float(sd[k])
+        with torch.no_grad():
+            for name in ("exp_avg", "exp_avg_sq"):
+                if sd.get(name) is not None:
+                    getattr(self, name).copy_(sd[name].to(getattr(self, name).device))
+                else:
+                    getattr(self, name).zero_()
+            self.step_count = int(sd.get("step", 0))
+            if self.step_dev is not None:
+                self.step_dev.fill_(self.step_count)
+        if self.capturable:
+            self.sync_hyper()
 
 
 class GraphedTrainStep:
     """Whole training step of a ``VanillaClassifierB200`` as one CUDA graph with static input / loss buffers.
 
     ``step(x, labels)`` copies the batch into the static buffers (device->device or pinned-host->device, on the
-    current stream), replays the graph and returns the static loss tensor (fp32 scalar, on the device)."""
+    current stream), replays the graph and returns the static loss tensor (fp32 scalar, on the device).  The warm-up
+    runs needed before the capture leave NO trace: parameters, Adam moments and the step counter are restored.
 
-    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, process_group: Any = None):
+    Data parallel (``comm``: a ``dp.NativeComm``): the graph also holds the gradient exchange -- the model's bucket
+    reducer launches ``ncclAllReduce`` per transformer block on a forked stream as soon as that block's gradients are
+    complete -- and the Adam update behind the join."""
+
+    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, comm: Any = None):
         if not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs ArenaAdam(capturable=True)")
-        import torch.distributed as dist
+        from . import _cabi, dp
 
-        # data parallel: the graph holds zero_grad + forward + loss + backward; the gradient mean (one NCCL all-reduce of
-        # the flat arena) and Adam run right after each replay.  (Capturing NCCL inside the graph hung on this stack.)
-        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.group = process_group
-        if self.world > 1 and model.engine.reducer is not None:
-            raise ValueError("detach the bucket reducer (model.engine.reducer = None) before graphing the DP step")
+        self.world = 1 if comm is None else comm.world
+        self.comm = comm
         g = model.geo
+        model.arena.ensure()
         dev = model.arena.flat.device
         self.model, self.optimizer = model, optimizer
+        if self.world > 1:
+            red = model.engine.reducer
+            if not isinstance(red, dp.NativeBucketReducer) or red.comm is not comm:
+                red = dp.attach_native_reducer(model, comm)
+            self.reducer = red
+        else:
+            if model.engine.reducer is not None:
+                raise ValueError("single-process graph: detach the bucket reducer first (model.engine.reducer = None)")
+            self.reducer = None
         self.x = torch.zeros((batch, g.cin, g.img, g.img), dtype=torch.float32, device=dev)
         self.labels = torch.zeros((batch, 1), dtype=torch.int64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        # warm up on a side stream (allocator pools, workspaces, lazy function attributes), then capture
+        self.bad_label = torch.zeros(1, dtype=torch.int32, device=dev)
+        optimizer._state()
+        arena = model.arena
+        # warm up on a side stream (allocator pools, workspaces, lazy function attributes, NCCL connections), then
+        # capture.  Warm-up steps run real Adam updates on an all-zero batch, so everything they touch is put back.
+        snap = [t.clone() for t in (arena.flat, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.step_dev)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -90,28 +197,34 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        from . import _cabi
-
         self.graph = torch.cuda.CUDAGraph()
         n0 = _cabi.launch_count()
         with torch.cuda.graph(self.graph):
             self._eager()
         self.launches_per_replay = _cabi.launch_count() - n0  # b200 kernels inside one replay of the graph
+        with torch.no_grad():
+            for dst, src in zip((arena.flat, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.step_dev), snap):
+                dst.copy_(src)
+        optimizer.step_count = int(snap[3].item())
+        torch.cuda.synchronize()
 
     def _eager(self) -> None:
         self.optimizer.zero_grad()
-        loss = self.model.train_step(self.x, self.labels)
-        if self.world == 1:
-            self.optimizer.step()
+        loss = self.model.train_step(self.x, self.labels)  # DP: the reducer all-reduces bucket by bucket inside backward
+        self.optimizer.step()
         self.loss.copy_(loss)
+        flag = getattr(self.model, "last_bad_flag", None)
+        if flag is not None:
+            self.bad_label.copy_(flag)
 
     def step(self, x: Tensor, labels: Tensor) -> Tensor:
+        self.optimizer.sync_hyper()  # lr schedule: 24 bytes host->device when (and only when) a value changed
         self.x.copy_(x, non_blocking=True)
         self.labels.copy_(labels.reshape(self.labels.shape), non_blocking=True)
         self.graph.replay()
-        if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(self.model.arena.grad, op=dist.ReduceOp.AVG, group=self.group)
-            self.optimizer.step()
         return self.loss
+
+    def check_labels(self) -> None:
+        """Synchronises and raises ``ValueError`` if the last replay saw a label outside [0, num_classes)."""
+        if int(self.bad_label.item()) != 0:
+            raise ValueError("cross_entropy: a label of the last step was outside [0, num_classes)")

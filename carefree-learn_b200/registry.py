@@ -10,7 +10,6 @@ the B200 modules into the reference's own dict when ``cflearn`` is importable, s
 """
 from __future__ import annotations
 
-import copy
 import inspect
 import json
 from typing import Any, Callable, Dict, Optional, Type, Union
@@ -42,16 +41,38 @@ def _safe_execute(fn: Callable, kwargs: Dict[str, Any]) -> Any:
     return fn(**{k: v for k, v in kwargs.items() if k in sig.parameters})
 
 
+def _copy_containers(d: Any) -> Any:
+    """``cftool.misc.shallow_copy_dict``: nested dict / list containers are copied, leaves shared
+    (an ``nn.Module`` passed as ``embedding_norm`` must stay the same object)."""
+    if isinstance(d, dict):
+        return {k: _copy_containers(v) for k, v in d.items()}
+    if isinstance(d, list):
+        return [_copy_containers(v) for v in d]
+    return d
+
+
+def _update_dict(src: Dict[str, Any], tgt: Dict[str, Any]) -> Dict[str, Any]:
+    """``cftool.misc.update_dict``: merge ``src`` INTO ``tgt`` recursively (src wins on leaves), return ``tgt``."""
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(tgt.get(k), dict):
+            _update_dict(v, tgt[k])
+        else:
+            tgt[k] = v
+    return tgt
+
+
 def build_module(name: str, *, config: Optional[Union[str, Dict[str, Any]]] = None, **kwargs: Any) -> nn.Module:
-    """Same contract as cflearn/modules/common.py:37-53: ``config`` may be a dict or a JSON path."""
+    """Same contract as cflearn/modules/common.py:37-53: ``config`` may be a dict or a JSON path; keyword arguments are
+    merged over it RECURSIVELY (``update_dict``), so ``encoder_config={"num_layers": 2}`` overrides one nested key and
+    keeps the others."""
     if config is None:
         kw: Dict[str, Any] = {}
     elif isinstance(config, dict):
-        kw = copy.deepcopy(config)
+        kw = _copy_containers(config)
     else:
         with open(config, "r") as f:
             kw = json.load(f)
-    kw.update(copy.deepcopy(kwargs))
+    _update_dict(_copy_containers(kwargs), kw)
     if name not in module_dict:
         raise KeyError(f"module '{name}' is not registered (available: {sorted(module_dict)})")
     return _safe_execute(module_dict[name], kw)

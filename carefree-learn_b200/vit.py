@@ -31,6 +31,22 @@ PREDICTIONS_KEY = "predictions"  # cflearn/constants.py:6
 LATENT_KEY = "latent"
 
 _ALIGN = 64  # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 arena
+_NVTX = os.environ.get("B200_NVTX", "0") == "1"
+
+
+class _nvtx:
+    """NVTX range per stage (B200_NVTX=1; off by default: a push / pop pair per stage costs host time on the eager path)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self) -> None:
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc: Any) -> None:
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -193,7 +209,8 @@ class ViTGeometry:
 
 def _init_param(key: str, shape: Tuple[int, ...]) -> Tensor:
     """Reference initialisation: trunc_normal(0.02) for Linear / in_w / cls / pos (mixed_stacks/api.py:205,405-417;
-    attentions.py:108-110), zero biases, LayerNorm 1/0, xavier_normal(gain/sqrt 2) conv (convs/basic.py:94-97)."""
+    attentions.py:108-110), zero biases, LayerNorm 1/0, xavier_normal conv with gain `gain / sqrt 2` where the Conv2d
+    default is gain = sqrt 2, i.e. 1.0 (convs/basic.py:56,94-97; pinned live by tests/test_host_logic.py)."""
     if key.endswith("norm.weight") or key.endswith("norms.0.weight"):
         return torch.ones(shape)
     if key == "output_projection":  # cv/encoder/transformer.py:81-82
@@ -202,7 +219,7 @@ def _init_param(key: str, shape: Tuple[int, ...]) -> Tensor:
         return torch.zeros(shape)
     if key == "to_patches.projection.weight":
         t = torch.empty(shape)
-        nn.init.xavier_normal_(t, 1.0 / math.sqrt(2.0))
+        nn.init.xavier_normal_(t, 1.0)
         return t
     return nn.init.trunc_normal_(torch.empty(shape), std=0.02)
 
@@ -218,7 +235,8 @@ class ViTEngine:
     def __init__(self, geo: ViTGeometry, arena: ParamArena):
         self.geo = geo
         self.arena = arena
-        self.reducer = None  # set by dp.attach_reducer
+        self.reducer = None  # set by dp.attach_reducer / dp.attach_native_reducer
+        self.shrink_next = 0  # SMs to leave free for an in-flight bucket all-reduce when launching the next GEMM (dp.py)
         self.d_input: Optional[Tensor] = None  # token mode: gradient w.r.t. the embedded input of the last backward
         # B200_SIDE_COLSUM=1 puts the HBM-bound bias-gradient column sums on a side stream (a parallel branch of the
         # captured graph).  Off by default: measured neutral (38.4 vs 38.5 ms / step) -- the persistent GEMM holds
@@ -241,6 +259,88 @@ class ViTEngine:
         if self.side_colsum and self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
 
+    # ---- stages (also the units of the teacher-forced parity tests, tests/test_taps_gpu.py) --------------------
+    def stem_forward(self, x: Tensor) -> Tuple[Optional[Tensor], Tensor]:
+        """image [B, C, S, S] fp32 (or embedded tokens [B, T, D]) -> (im2col matrix or None, fp32 tokens [B*T, D])."""
+        g, A = self.geo, self.arena
+        B, T, D = x.shape[0], g.T, g.D
+        if g.tokens:  # TeTEncoder.forward -> pre_process (api.py:419-438 without head token): x + pos
+            return None, ops.add_pos(x, A.p("encoder.pos_encoding.pos_encoding"), B, T, D).view(B * T, D)
+        cols = ops.patch_im2col(x, g.patch)
+        patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
+                         bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
+        net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(B * T, D)
+        return cols, net
+
+    def block_forward(self, i: int, net: Tensor, B: int) -> Tuple[Tensor, Tuple[Tensor, ...]]:
+        """MixingBlock._pre_norm_forward (mixed_stacks/api.py:130-158) on the fp32 residual stream [B*T, D]."""
+        g, A = self.geo, self.arena
+        T, D, M = g.T, g.D, B * g.T
+        b = f"encoder.mixing_blocks.{i}."
+        epi_act = ops.EPI_BIAS_QGELU_BF16 if g.quick_gelu else ops.EPI_BIAS_GELU_BF16
+        ln1, mean1, rstd1 = ops.layernorm_fwd(net, A.p(b + "token_norm.weight"), A.p(b + "token_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+        qkv = ops.gemm(ln1, A.w(b + "token_mixing.net.in_w"), bias=A.w(b + "token_mixing.net.qkv_bias"))
+        attn, lse = ops.attention_fwd(qkv, B, T, g.H, causal=g.causal)
+        mid = ops.gemm(attn, A.w(b + "token_mixing.net.out_linear.linear.weight"), bias=A.w(b + "token_mixing.net.out_linear.linear.bias"),
+                       epilogue=ops.EPI_BIAS_RESID_F32, aux=net)
+        ln2, mean2, rstd2 = ops.layernorm_fwd(mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+        act = torch.empty((M, g.FF), dtype=torch.bfloat16, device=net.device)
+        h = ops.gemm(ln2, A.w(b + "channel_mixing.net.0.linear.weight"), bias=A.w(b + "channel_mixing.net.0.linear.bias"),
+                     epilogue=epi_act, out1=act)
+        out = ops.gemm(act, A.w(b + "channel_mixing.net.3.linear.weight"), bias=A.w(b + "channel_mixing.net.3.linear.bias"),
+                       epilogue=ops.EPI_BIAS_RESID_F32, aux=mid)
+        return out, (net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act)
+
+    def block_backward(self, i: int, saved: Tuple[Tensor, ...], dnet: Tensor, dnet_bf: Tensor, G: Tensor, B: int,
+                       *, ff2_bias_done: bool = True, next_ff2_bias: bool = True) -> None:
+        """Backward of block ``i``.  ``dnet`` (fp32) / ``dnet_bf`` (its bf16 rounding) hold the gradient of the block's
+        output and are OVERWRITTEN with the gradient of its input.  ``ff2_bias_done``: this block's FF2 bias gradient was
+        already emitted by the producer of ``dnet_bf``; ``next_ff2_bias``: emit block ``i-1``'s from the last LayerNorm
+        backward here (both fusions remove a pass over the [M, D] gradient)."""
+        g, A = self.geo, self.arena
+        T, D, M = g.T, g.D, B * g.T
+        dev = dnet.device
+        b = f"encoder.mixing_blocks.{i}."
+        net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act = saved
+        if not ff2_bias_done:
+            self._bias_grad(dnet_bf, A.g(b + "channel_mixing.net.3.linear.bias", G))
+        # FeedForward: net_out = mid + W2 gelu(W1 ln2 + b1) + b2
+        ff1_bias = A.g(b + "channel_mixing.net.0.linear.bias", G)
+        shrink, self.shrink_next = self.shrink_next, 0  # the previous block's bucket is being all-reduced right now
+        dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True,
+                      epilogue=ops.EPI_DQGELU_BF16 if g.quick_gelu else ops.EPI_DGELU_BF16, aux=h,
+                      max_ctas=(ops.num_sms() - shrink) if shrink else 0)
+        ops.wgrad(dnet_bf, act, A.g(b + "channel_mixing.net.3.linear.weight", G))
+        dln2 = ops.gemm(dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
+        ops.wgrad(dh, ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
+        self._bias_grad(dh, ff1_bias)
+        dmid = torch.empty((M, D), dtype=torch.float32, device=dev)
+        dmid_bf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        ops.layernorm_bwd(dln2, mid, A.p(b + "channel_norm.weight"), mean2, rstd2, rows=M, dim=D, ld_x=D, dres=dnet,
+                          dx_out=dmid, ld_dx=D, dx_bf16=dmid_bf,
+                          dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G),
+                          dx_colsum=A.g(b + "token_mixing.net.out_linear.linear.bias", G))
+        # attention: mid = net + Wo attn + bo
+        dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
+        ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
+        dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H, causal=g.causal, dbias=A.g(b + "token_mixing.net.qkv_bias", G))
+        dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
+        ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
+        self._join_side()  # dnet_bf is overwritten below, and this block's bias gradients must be complete
+        ops.layernorm_bwd(dln1, net, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D, dres=dmid,
+                          dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,
+                          dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G),
+                          dx_colsum=A.g(f"encoder.mixing_blocks.{i - 1}.channel_mixing.net.3.linear.bias", G) if (i > 0 and next_ff2_bias) else None)
+
+    def stem_backward(self, sv: "_Saved", dnet: Tensor, G: Tensor) -> None:
+        """tokens = cat(cls, patches) + pos ; patches = conv(x): pos / cls / conv weight (+ bias) gradients."""
+        g, A = self.geo, self.arena
+        dpatch = ops.assemble_tokens_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), A.g("encoder.head_token", G), sv.B, g.np, g.D)
+        ops.wgrad(dpatch, sv.cols, A.g("to_patches.projection.weight", G).view(g.D, -1))
+        if g.conv_bias:
+            self._bias_grad(dpatch, A.g("to_patches.projection.bias", G))
+        self._join_side()
+
     # ---- forward ------------------------------------------------------------------------------------------
     def encoder_forward(self, x: Tensor, want_f32: bool) -> Tuple[Tensor, Optional[Tensor], _Saved]:
         g, A = self.geo, self.arena
@@ -256,14 +356,8 @@ class ViTEngine:
         B, T, D, M = x.shape[0], g.T, g.D, x.shape[0] * g.T
         sv = _Saved()
         sv.B = B
-        if g.tokens:  # TeTEncoder.forward -> pre_process (api.py:419-438 without head token): x + pos
-            cols = None
-            net = ops.add_pos(x, A.p("encoder.pos_encoding.pos_encoding"), B, T, D).view(M, D)
-        else:
-            cols = ops.patch_im2col(x, g.patch)
-            patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
-                             bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
-            net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(M, D)
+        with _nvtx("b200.stem.fwd"):
+            cols, net = self.stem_forward(x)
         sv.emb_in = None
         if g.emb_eps is not None:  # embedding_norm (api.py:433-434): its fp32 output IS the residual stream
             normed = torch.empty_like(net)
@@ -271,23 +365,11 @@ class ViTEngine:
                                                             g.emb_eps, rows=M, dim=D, ld_x=D, y_f32=normed)
             sv.emb_in, net = net, normed
         sv.cols = cols
-        epi_act = ops.EPI_BIAS_QGELU_BF16 if g.quick_gelu else ops.EPI_BIAS_GELU_BF16
         sv.blocks = []
         for i in range(g.L):
-            b = f"encoder.mixing_blocks.{i}."
-            ln1, mean1, rstd1 = ops.layernorm_fwd(net, A.p(b + "token_norm.weight"), A.p(b + "token_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
-            qkv = ops.gemm(ln1, A.w(b + "token_mixing.net.in_w"), bias=A.w(b + "token_mixing.net.qkv_bias"))
-            attn, lse = ops.attention_fwd(qkv, B, T, g.H, causal=g.causal)
-            mid = ops.gemm(attn, A.w(b + "token_mixing.net.out_linear.linear.weight"), bias=A.w(b + "token_mixing.net.out_linear.linear.bias"),
-                           epilogue=ops.EPI_BIAS_RESID_F32, aux=net)
-            ln2, mean2, rstd2 = ops.layernorm_fwd(mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
-            act = torch.empty((M, g.FF), dtype=torch.bfloat16, device=x.device)
-            h = ops.gemm(ln2, A.w(b + "channel_mixing.net.0.linear.weight"), bias=A.w(b + "channel_mixing.net.0.linear.bias"),
-                         epilogue=epi_act, out1=act)
-            out = ops.gemm(act, A.w(b + "channel_mixing.net.3.linear.weight"), bias=A.w(b + "channel_mixing.net.3.linear.bias"),
-                           epilogue=ops.EPI_BIAS_RESID_F32, aux=mid)
-            sv.blocks.append((net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act))
-            net = out
+            with _nvtx(f"b200.block{i}.fwd"):
+                net, saved = self.block_forward(i, net, B)
+            sv.blocks.append(saved)
         hrows, hld = (M, D) if g.tokens else (B, T * D)
         enc_f32 = torch.empty((hrows, D), dtype=torch.float32, device=x.device) if want_f32 else None
         # head = LayerNorm over all tokens then token 0 (api.py:365,397-402): only row 0 of each image is needed;
@@ -345,32 +427,8 @@ class ViTEngine:
         if red is not None:
             red.ready("tail", G)
         for i in reversed(range(g.L)):
-            b = f"encoder.mixing_blocks.{i}."
-            net, mean1, rstd1, ln1, qkv, attn, lse, mid, mean2, rstd2, ln2, h, act = sv.blocks[i]
-            # FeedForward: net_out = mid + W2 gelu(W1 ln2 + b1) + b2
-            dh = ops.gemm(dnet_bf, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True,
-                          epilogue=ops.EPI_DQGELU_BF16 if g.quick_gelu else ops.EPI_DGELU_BF16, aux=h)
-            ops.wgrad(dnet_bf, act, A.g(b + "channel_mixing.net.3.linear.weight", G))
-            dln2 = ops.gemm(dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
-            ops.wgrad(dh, ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
-            self._bias_grad(dh, A.g(b + "channel_mixing.net.0.linear.bias", G))
-            dmid = torch.empty((M, D), dtype=torch.float32, device=dev)
-            dmid_bf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-            ops.layernorm_bwd(dln2, mid, A.p(b + "channel_norm.weight"), mean2, rstd2, rows=M, dim=D, ld_x=D, dres=dnet,
-                              dx_out=dmid, ld_dx=D, dx_bf16=dmid_bf,
-                              dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G),
-                              dx_colsum=A.g(b + "token_mixing.net.out_linear.linear.bias", G))
-            # attention: mid = net + Wo attn + bo
-            dattn = ops.gemm(dmid_bf, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
-            ops.wgrad(dmid_bf, attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
-            dqkv = ops.attention_bwd(qkv, attn, dattn, lse, B, T, g.H, causal=g.causal, dbias=A.g(b + "token_mixing.net.qkv_bias", G))
-            dln1 = ops.gemm(dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
-            ops.wgrad(dqkv, ln1, A.g(b + "token_mixing.net.in_w", G))
-            self._join_side()  # dnet_bf is overwritten below, and this block's bias gradients must be complete
-            ops.layernorm_bwd(dln1, net, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D, dres=dmid,
-                              dx_out=dnet, ld_dx=D, dx_bf16=dnet_bf,
-                              dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G),
-                              dx_colsum=A.g(f"encoder.mixing_blocks.{i - 1}.channel_mixing.net.3.linear.bias", G) if i > 0 else None)
+            with _nvtx(f"b200.block{i}.bwd"):
+                self.block_backward(i, sv.blocks[i], dnet, dnet_bf, G, B)
             sv.blocks[i] = None  # release this block's activations
             if red is not None:
                 red.ready(i, G)
@@ -386,12 +444,8 @@ class ViTEngine:
             if red is not None:
                 red.ready("stem", G)
             return
-        # tokens = cat(cls, patches) + pos ; patches = conv(x)
-        dpatch = ops.assemble_tokens_bwd(dnet, A.g("encoder.pos_encoding.pos_encoding", G), A.g("encoder.head_token", G), B, g.np, D)
-        ops.wgrad(dpatch, sv.cols, A.g("to_patches.projection.weight", G).view(D, -1))
-        if g.conv_bias:
-            self._bias_grad(dpatch, A.g("to_patches.projection.bias", G))
-        self._join_side()
+        with _nvtx("b200.stem.bwd"):
+            self.stem_backward(sv, dnet, G)
         if red is not None:
             red.ready("stem", G)
 
@@ -487,12 +541,14 @@ class _ClassifierFn(torch.autograd.Function):
 class _SoftmaxXentFn(torch.autograd.Function):
     """CrossEntropyLoss (losses/basic.py:137-141) + mean reduction (schema.py:767-775) on bf16 logits."""
 
+    last_bad: Optional[Tensor] = None
+
     @staticmethod
     def forward(ctx: Any, logits: Tensor, labels: Tensor) -> Tensor:
         lab = labels.reshape(-1).contiguous()
         loss_mean, _, _, bad = ops.softmax_xent(logits, lab, need_grad=False)
         ctx.save_for_backward(logits, lab)
-        ctx.bad = bad
+        _SoftmaxXentFn.last_bad = bad  # int32[1] on the device: non-zero if a label was outside [0, C)
         return loss_mean.reshape(())
 
     @staticmethod
@@ -504,10 +560,16 @@ class _SoftmaxXentFn(torch.autograd.Function):
 
 
 def cross_entropy(logits: Tensor, labels: Tensor) -> Tensor:
-    """Mean softmax cross-entropy of bf16 ``logits`` [B, C] against int64 ``labels`` [B] or [B, 1]."""
+    """Mean softmax cross-entropy of bf16 ``logits`` [B, C] against int64 ``labels`` [B] or [B, 1].  Labels outside
+    [0, C) contribute nothing and set a device flag (``bad_label_flag()``); ``VanillaClassifierB200`` raises for it."""
     if logits.dtype != torch.bfloat16:
         raise B200Error("cross_entropy expects the bf16 logits produced by VanillaClassifierB200")
     return _SoftmaxXentFn.apply(logits, labels)  # keeps the logits' padded row stride (see ops.gemm)
+
+
+def bad_label_flag() -> Optional[Tensor]:
+    """int32[1] device tensor written by the most recent ``cross_entropy`` forward (non-zero: a label was out of range)."""
+    return _SoftmaxXentFn.last_bad
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -552,6 +614,7 @@ class ViTEncoderB200(nn.Module):
         norm_after_head: bool = False,
         output_dim: Optional[int] = None,
         _num_classes: Optional[int] = None,
+        _defer_head: bool = False,
     ):
         super().__init__()
         _check_supported(to_patches_type=to_patches_type, dropout=dropout, drop_path_rate=drop_path_rate, norm_type=norm_type,
@@ -587,12 +650,17 @@ class ViTEncoderB200(nn.Module):
             if embedding_norm is not None and key.startswith("encoder.embedding_norm."):
                 p.data.copy_(getattr(embedding_norm, key.rsplit(".", 1)[1]).data)  # the instance handed in is adopted
             params[key] = p
-            _register_dotted(self, key, p)
+            if not (_defer_head and key.startswith("head.linear")):  # the classifier registers its head itself
+                _register_dotted(self, key, p)
         self.arena.attach(params)
         self.engine = ViTEngine(self.geo, self.arena)
         self.all_keys = [k for k, _ in spec]
         self.encoder_keys = [k for k in self.all_keys if not k.startswith("head.linear")]
         self.latent_dim = latent_dim
+
+    def named_arena_parameters(self):
+        """(arena key, parameter) pairs: the reference ``ViTEncoder`` state_dict names (+ ``head.linear.*``)."""
+        return [(k, self.arena.params[k]) for k in self.all_keys]
 
     def _param_list(self, keys: List[str]) -> List[nn.Parameter]:
         return [self.arena.params[k] for k in keys]
@@ -690,15 +758,20 @@ class TeTEncoderB200(nn.Module):
         return _TokenEncoderFn.apply(self, net, *[self.arena.params[k] for k in self.all_keys])
 
 
-class VanillaClassifierB200(ViTEncoderB200):
+class VanillaClassifierB200(nn.Module):
     """Drop-in for ``cv_clf`` with ``encoder="vit"`` (cv/classifier/vanilla.py:16-66): ``{"predictions": logits}``.
 
-    ``state_dict`` keys: the encoder's keys under their reference names plus ``head.linear.{weight,bias}``; use
-    ``load_reference_state_dict`` for checkpoints saved from the reference ``cv_clf`` (keys prefixed ``encoder.``)."""
+    Module tree and ``state_dict`` layout are the reference's: the encoder is the sub-module ``encoder``
+    (``encoder.to_patches.*``, ``encoder.encoder.mixing_blocks.*`` ...) followed by ``head.linear.{weight,bias}``, so
+    checkpoints move between the reference ``cv_clf`` and this class with a plain ``load_state_dict(strict=True)``.
+    The head's parameters live in the same flat arena as the encoder's (one cast, one all-reduce, one Adam launch).
+    For convenience ``load_state_dict`` also accepts the encoder's keys WITHOUT the ``encoder.`` prefix (the layout of a
+    bare ``ViTEncoder`` checkpoint + head, which is what ``oracle/vit_oracle.py`` emits)."""
 
     def __init__(self, in_channels: int, num_classes: int, img_size: Optional[int] = None, latent_dim: int = 128,
                  aux_num_classes: Optional[Dict[str, int]] = None, *, encoder: str = "vit",
                  encoder_config: Optional[Dict[str, Any]] = None):
+        super().__init__()
         if aux_num_classes is not None:
             raise NotImplementedError("aux heads are outside the fused path")
         if encoder not in ("vit", "vit_b200"):
@@ -707,25 +780,94 @@ class VanillaClassifierB200(ViTEncoderB200):
         cfg.setdefault("img_size", img_size)
         cfg.setdefault("in_channels", in_channels)
         cfg.setdefault("latent_dim", latent_dim)
-        super().__init__(**cfg, _num_classes=num_classes)
+        self.img_size = img_size
+        self.encoder = ViTEncoderB200(**cfg, _num_classes=num_classes, _defer_head=True)
+        for key in ("head.linear.weight", "head.linear.bias"):  # registered after `encoder`: the reference's key order
+            _register_dotted(self, key, self.encoder.arena.params[key])
         self.num_classes = num_classes
+        self.last_bad_flag: Optional[Tensor] = None  # int32[1] on the device, written by the loss of the last train_step
+        self._bad_host: Optional[Tensor] = None
+        self._bad_event: Optional[torch.cuda.Event] = None
+        self._register_load_state_dict_pre_hook(self._accept_bare_encoder_keys)
 
-    def forward(self, net: Tensor, *, return_latent: bool = False) -> Dict[str, Tensor]:  # type: ignore[override]
+    # the engine, arena and geometry are the encoder's (they include the head's parameters)
+    @property
+    def arena(self) -> ParamArena:
+        return self.encoder.arena
+
+    @property
+    def engine(self) -> ViTEngine:
+        return self.encoder.engine
+
+    @property
+    def geo(self) -> ViTGeometry:
+        return self.encoder.geo
+
+    @property
+    def all_keys(self) -> List[str]:
+        return self.encoder.all_keys
+
+    @property
+    def encoder_keys(self) -> List[str]:
+        return self.encoder.encoder_keys
+
+    def named_arena_parameters(self):
+        """(arena key, parameter): ``ViTEncoder`` keys + ``head.linear.*`` -- the names ``oracle/vit_oracle.py`` uses."""
+        return self.encoder.named_arena_parameters()
+
+    def _accept_bare_encoder_keys(self, state_dict: Dict[str, Tensor], prefix: str, *args: Any) -> None:
+        enc = set(self.encoder_keys)
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix) and k[len(prefix):] in enc and (prefix + "encoder." + k[len(prefix):]) not in state_dict:
+                state_dict[prefix + "encoder." + k[len(prefix):]] = state_dict.pop(k)
+
+    def forward(self, net: Tensor, *, return_latent: bool = False) -> Dict[str, Tensor]:
+        self.check_labels()
         self.arena.ensure()
         if return_latent:
-            return {LATENT_KEY: _EncoderFn.apply(self, net, *self._param_list(self.encoder_keys))}
-        logits = _ClassifierFn.apply(self, net, *self._param_list(self.all_keys))
+            return {LATENT_KEY: _EncoderFn.apply(self.encoder, net, *self.encoder._param_list(self.encoder_keys))}
+        logits = _ClassifierFn.apply(self, net, *self.encoder._param_list(self.all_keys))
         return {PREDICTIONS_KEY: logits}
 
     def train_step(self, net: Tensor, labels: Tensor) -> Tensor:
-        """forward + CrossEntropyLoss + backward (IDLModel.train, schema.py:1266-1276,:980); returns the loss."""
-        loss = cross_entropy(self.forward(net)[PREDICTIONS_KEY], labels)
+        """forward + CrossEntropyLoss + backward (IDLModel.train, schema.py:1266-1276,:980); returns the loss.
+        An out-of-range label raises ``ValueError`` from a later call (see ``check_labels``): the flag travels to pinned
+        host memory asynchronously, so no step ever waits on the device for it."""
+        logits = self.forward(net)[PREDICTIONS_KEY]
+        loss = cross_entropy(logits, labels)
+        bad = _SoftmaxXentFn.last_bad
+        self.last_bad_flag = bad
+        if bad is not None and not torch.cuda.is_current_stream_capturing():
+            if self._bad_host is None:
+                self._bad_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            elif self._bad_event is not None:
+                self._bad_event.synchronize()  # the previous copy must have landed before its buffer is reused
+                self._raise_if_bad()
+            self._bad_host.copy_(bad, non_blocking=True)
+            self._bad_event = torch.cuda.Event()
+            self._bad_event.record()
         loss.backward()
         return loss.detach()
 
+    def _raise_if_bad(self) -> None:
+        if self._bad_host is not None and int(self._bad_host[0]) != 0:
+            self._bad_host.zero_()
+            self._bad_event = None
+            raise ValueError("cross_entropy: a label of an earlier train_step was outside [0, num_classes)")
+
+    def check_labels(self, sync: bool = False) -> None:
+        """Eager raises a device-side assert on an out-of-range class index (``gather`` in losses/basic.py:139); the fused
+        loss records a flag on the device instead.  This raises ``ValueError`` for it once the flag has reached the host
+        (``sync=True`` waits for it); ``forward`` calls it without waiting."""
+        ev = self._bad_event
+        if ev is None:
+            return
+        if sync:
+            ev.synchronize()
+        if ev.query():
+            self._bad_event = None
+            self._raise_if_bad()
+
     def load_reference_state_dict(self, sd: Dict[str, Tensor]) -> None:
-        """Accepts a reference ``cv_clf`` checkpoint (``encoder.<ViTEncoder keys>`` + ``head.linear.*``)."""
-        mapped = {}
-        for k, v in sd.items():
-            mapped[k[len("encoder."):] if k.startswith("encoder.to_patches") or k.startswith("encoder.encoder.") else k] = v
-        self.load_state_dict(mapped, strict=True)
+        """Reference ``cv_clf`` checkpoint (``encoder.<ViTEncoder keys>`` + ``head.linear.*``): same as ``load_state_dict``."""
+        self.load_state_dict(sd, strict=True)

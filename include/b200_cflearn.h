@@ -27,7 +27,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 enum {
     B200_OK = 0,
@@ -193,10 +193,34 @@ int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long
 int b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
                    cudaStream_t stream);
+/* The same update with every hyper-parameter in DEVICE memory: hyper_dev = {lr, beta1, beta2, eps, weight_decay,
+ * grad_scale} (6 floats; grad_scale multiplies the gradient first: 1/world after a SUM all-reduce, or the clip
+ * coefficient of cflearn/schema.py:981-982).  A captured CUDA graph therefore follows an LR scheduler
+ * (cflearn/pipeline/blocks/basic.py:334-352 "warmup" is the reference's default) without being re-captured.
+ * increment != 0: *step_dev += 1 first (pass 0 for all but the first slice when one step updates several slices). */
+int b200_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                       const float* hyper_dev, int* step_dev, int increment, cudaStream_t stream);
 
 /* element-wise helpers */
 int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStream_t stream);
 int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (replaces the DDP wrap of `accelerator.prepare`, cflearn/trainer.py:226-229,
+ * 266-273; the all-reduce sits between backward and optimizer.step, cflearn/schema.py:980-984).  One communicator per
+ * process / GPU over NCCL (libnccl.so.2 is dlopen'ed at first use).  b200_comm_unique_id: rank 0 creates the 128-byte
+ * id (HOST pointer) and ships it to the other ranks by any means; b200_comm_init is collective over all ranks and
+ * binds to the CURRENT device; b200_comm_allreduce_bucket enqueues an in-place fp32 all-reduce (average != 0: mean
+ * over ranks, else sum) of buf[0..n) on `stream` -- an ordinary stream operation, capturable in a CUDA graph;
+ * b200_comm_async_error polls the communicator (0 healthy, negative: abort the job); b200_comm_finalize destroys
+ * (abort != 0: ncclCommAbort) the communicator.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_comm_unique_id(void* id_out_128);
+int b200_comm_init(const void* id_128, int rank, int world, void** comm_out);
+int b200_comm_allreduce_bucket(void* comm, float* buf, long long n, int average, cudaStream_t stream);
+int b200_comm_async_error(void* comm);
+int b200_comm_finalize(void* comm, int abort);
+int b200_comm_nccl_version(void);
 
 #ifdef __cplusplus
 }

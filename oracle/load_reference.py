@@ -189,6 +189,18 @@ def load_reference_modules() -> types.ModuleType:
     return importlib.import_module("cflearn.modules")
 
 
+def load_modules() -> types.SimpleNamespace:
+    """The reference's registry entry points, imported where they lie: ``module_dict`` / ``build_module``
+    (cflearn/modules/common.py:30-53) and ``build_encoder`` (cflearn/modules/cv/common.py:286-292)."""
+    load_reference_modules()
+    import importlib
+
+    common = importlib.import_module("cflearn.modules.common")
+    cv_common = importlib.import_module("cflearn.modules.cv.common")
+    return types.SimpleNamespace(module_dict=common.module_dict, build_module=common.build_module,
+                                 build_encoder=cv_common.build_encoder, common=common)
+
+
 if __name__ == "__main__":
     m = load_reference_modules()
     from cflearn.modules.common import module_dict

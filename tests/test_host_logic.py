@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     exported = set(_cabi.exported_symbols())
     assert set(declared) == set(_cabi.SIGNATURES), (set(declared) ^ set(_cabi.SIGNATURES))
     assert not [n for n in declared if n not in exported]
-    assert _cabi.lib().b200_abi_version() == 2
+    assert _cabi.lib().b200_abi_version() == 3
     assert _cabi.lib().b200_gemm_pick_splits(768, 768, 50432) >= 1
 
 
@@ -147,22 +147,24 @@ def test_param_arena_views_and_state_dict_roundtrip():
     m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=16, img_size=32, latent_dim=128, encoder="vit",
                                                     encoder_config=dict(patch_size=16, num_layers=2)))
     a = m.arena
-    for k, p in m.named_parameters():
+    for k, p in m.named_arena_parameters():
         assert p.data_ptr() == a.flat.data_ptr() + 4 * a.offsets[k]
         assert a.offsets[k] % 64 == 0
+    # the module's own names are the reference cv_clf's: "encoder." + <ViTEncoder key>, then head.linear.*
+    assert [k for k, _ in m.named_parameters()] == [("encoder." + k if not k.startswith("head.linear") else k) for k, _ in m.named_arena_parameters()]
     sd = {k: torch.randn_like(v) for k, v in m.state_dict().items()}
     m.load_state_dict(sd)
     a.ensure()
-    for k in sd:
-        assert torch.equal(a.p(k), sd[k])  # load_state_dict copies in place: the arena sees the new values
+    bare = {(k[len("encoder."):] if k.startswith("encoder.") else k): v for k, v in sd.items()}
+    for k in bare:
+        assert torch.equal(a.p(k), bare[k])  # load_state_dict copies in place: the arena sees the new values
     m2 = m.double().float()  # _apply() re-allocates every parameter: views are broken, ensure() must repair them
     m2.arena.ensure()
-    for k, p in m2.named_parameters():
+    for k, p in m2.named_arena_parameters():
         assert p.data_ptr() == m2.arena.flat.data_ptr() + 4 * m2.arena.offsets[k]
-        assert torch.equal(p, sd[k])
-    # reference cv_clf checkpoints carry an "encoder." prefix on the encoder's keys
-    ref_sd = {("encoder." + k if not k.startswith("head.linear") else k): v for k, v in sd.items()}
-    m.load_reference_state_dict(ref_sd)
+        assert torch.equal(p, bare[k])
+    m.load_reference_state_dict(sd)  # reference cv_clf checkpoint layout == our own state_dict layout
+    m.load_state_dict(bare, strict=True)  # bare ViTEncoder keys + head.linear.* (what oracle/vit_oracle.py emits) are accepted too
 
 
 def test_bucket_layout_covers_arena_without_overlap():
@@ -213,3 +215,152 @@ def test_world2_gloo_bucket_allreduce_matches_mean():
     assert s0 == s1  # parameters identical after the broadcast
     expect = torch.arange(g0.numel(), dtype=torch.float32) * 1.5  # mean of 1x and 2x
     assert torch.equal(g0, g1) and torch.allclose(g0, expect)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# initialisation statistics and the optimizer's host surface
+# ------------------------------------------------------------------------------------------------------------------
+def _stats(t):
+    t = t.detach().float()
+    return t.mean().item(), t.std().item(), t.abs().max().item()
+
+
+def test_vit_init_statistics_follow_reference():
+    """mixed_stacks/api.py:405-417 (`_init_weights`: trunc_normal(0.02) Linear weights, zero biases, LayerNorm 1 / 0),
+    api.py:205 and :405 (pos-enc / head token trunc_normal(0.02)), attentions.py:108-110 (in_w trunc_normal(0.02), zero
+    qkv_bias), convs/basic.py:56,94-97 (xavier_normal, gain = sqrt 2 / sqrt 2 = 1 for the patch conv).  trunc_normal_ truncates at the
+    ABSOLUTE bounds [-2, 2], so with std 0.02 the sample std is 0.02 and |w| stays far below 2."""
+    torch.manual_seed(0)
+    m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=100, img_size=64, latent_dim=256, encoder="vit",
+                                                    encoder_config=dict(patch_size=16, num_layers=2)))
+    P = dict(m.named_arena_parameters())
+    for k, p in P.items():
+        mean, std, mx = _stats(p)
+        if k.endswith("norm.weight") or k.endswith("norms.0.weight"):
+            assert torch.equal(p.detach(), torch.ones_like(p)), k
+        elif k.endswith("bias"):
+            assert torch.equal(p.detach(), torch.zeros_like(p)), k
+        elif k == "to_patches.projection.weight":
+            fan_in, fan_out = 3 * 16 * 16, 256 * 16 * 16
+            want = (2.0 / (fan_in + fan_out)) ** 0.5
+            assert abs(std - want) < 0.03 * want and abs(mean) < 0.05 * want, (k, std, want)
+        else:  # Linear weights, in_w, head token, positional encoding
+            tol = 0.25 if p.numel() < 1000 else 0.05
+            assert abs(std - 0.02) < tol * 0.02 and abs(mean) < 0.004 and mx < 0.2, (k, mean, std, mx)
+
+
+def test_vit_init_matches_reference_distribution_live():
+    """Where /root/reference is importable: same statistics as the real ViTEncoder built under the same seed (not the same
+    values -- parity always injects identical weights -- but the same per-tensor std to a few percent)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import load_reference as lr
+
+    if not lr.reference_available():
+        pytest.skip("reference tree not present")
+    mods = lr.load_modules()
+    torch.manual_seed(0)
+    ref = mods.build_encoder("vit", config=dict(img_size=64, patch_size=16, in_channels=3, latent_dim=256, num_layers=2))
+    torch.manual_seed(1)
+    ours = registry.build_module("encoders.vit", config=dict(img_size=64, patch_size=16, in_channels=3, latent_dim=256, num_layers=2))
+    rsd, osd = ref.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        rm, rs, _ = _stats(rsd[k])
+        om, os_, _ = _stats(osd[k])
+        if rs == 0.0:
+            assert os_ == 0.0 and rm == om, k
+        else:
+            tol = 0.3 if rsd[k].numel() < 1000 else 0.06
+            assert abs(os_ - rs) < tol * rs, (k, os_, rs)
+
+
+def test_clip_text_tower_init_follows_reset_parameters():
+    """multimodal/clip.py:188-207: std 0.01 positions, d^-0.5 in_w, d^-0.5 (2L)^-0.5 out / mlp[3], (2d)^-0.5 mlp[0]."""
+    torch.manual_seed(0)
+    m = registry.build_module("clip", config=dict(img_size=64, latent_dim=64, vision_latent_dim=128, vision_patch_size=32,
+                                                  vision_num_heads=2, vision_num_layers=1, vocab_size=512, context_length=16,
+                                                  text_latent_dim=128, text_num_heads=2, text_num_layers=3))
+    P = m.text_transformer.arena.params
+    d, L = 128, 3
+    want = {"token_mixing.net.in_w": d ** -0.5, "token_mixing.net.out_linear.linear.weight": d ** -0.5 * (2 * L) ** -0.5,
+            "channel_mixing.net.0.linear.weight": (2 * d) ** -0.5, "channel_mixing.net.3.linear.weight": d ** -0.5 * (2 * L) ** -0.5}
+    for i in range(L):
+        for suffix, std in want.items():
+            _, s, _ = _stats(P[f"encoder.mixing_blocks.{i}.{suffix}"])
+            assert abs(s - std) < 0.05 * std, (i, suffix, s, std)
+    assert abs(_stats(P["encoder.pos_encoding.pos_encoding"])[1] - 0.01) < 0.002
+    assert abs(_stats(m.token_embedding.weight)[1] - 0.02) < 0.002
+    assert abs(_stats(m.text_projection.weight)[1] - d ** -0.5) < 0.05 * d ** -0.5 and torch.equal(m.text_projection.bias.detach(), torch.zeros(64))
+    # the vision tower keeps the encoder's trunc_normal(0.02)
+    assert abs(_stats(m.vit.arena.params["encoder.mixing_blocks.0.token_mixing.net.in_w"])[1] - 0.02) < 0.002
+
+
+def test_arena_adam_host_surface():
+    """param_groups / set_lr / state_dict round trip (what LR schedulers and checkpoints touch) -- no GPU involved."""
+    from cflearn_b200.optim import ArenaAdam
+
+    m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=8, img_size=32, latent_dim=64, encoder="vit",
+                                                    encoder_config=dict(patch_size=16, num_layers=1)))
+    opt = ArenaAdam(m, lr=1e-3, betas=(0.9, 0.99), weight_decay=0.01)
+    assert len(opt.param_groups) == 1 and len(opt.param_groups[0]["params"]) == len(list(m.parameters()))
+    opt.set_lr(5e-4)
+    assert opt.lr == 5e-4 and opt.param_groups[0]["lr"] == 5e-4
+    opt.param_groups[0]["lr"] = 2.5e-4  # how torch.optim.lr_scheduler writes it
+    assert opt.lr == 2.5e-4 and opt._hyper_tuple()[:5] == (2.5e-4, 0.9, 0.99, 1e-8, 0.01)
+
+
+def test_cv_clf_state_dict_layout_is_the_reference_cv_clf_layout():
+    """keys must be `encoder.<ViTEncoder keys>` + `head.linear.*`, in the reference's order."""
+    with open(os.path.join(ROOT, "tests", "golden", "cv_clf_vit_tiny_keys.json")) as f:
+        golden = json.load(f)["keys"]
+    m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=10, img_size=32, latent_dim=128, encoder="vit",
+                                                    encoder_config=dict(patch_size=16, num_layers=2)))
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == golden
+    assert [k for k, _ in m.named_parameters()] == [k for k, _ in golden]
+    # a bare-encoder-style checkpoint (ViTEncoder keys + head.linear.*) is accepted as well
+    bare = {(k[len("encoder."):] if k.startswith("encoder.") else k): v.clone() for k, v in m.state_dict().items()}
+    m.load_state_dict(bare, strict=True)
+
+
+def test_build_module_merges_nested_kwargs_like_update_dict():
+    """cflearn/modules/common.py:50-52: `update_dict(shallow_copy_dict(kwargs), kw)` merges nested dicts key by key."""
+    cfg = dict(in_channels=3, num_classes=8, img_size=32, latent_dim=64, encoder="vit", encoder_config=dict(patch_size=16, num_layers=3))
+    m = registry.build_module("cv_clf", config=cfg, encoder_config=dict(num_layers=1))
+    assert m.geo.L == 1 and m.geo.patch == 16 and cfg["encoder_config"]["num_layers"] == 3  # nested key overridden, sibling kept, config untouched
+    ln = torch.nn.LayerNorm(64, 1e-5)
+    e = registry.build_module("encoders.vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=64, num_layers=1, embedding_norm=ln))
+    assert e.geo.emb_eps == 1e-5  # leaves (modules) are shared, not deep-copied
+
+
+def test_install_into_the_real_reference_registry():
+    """drop the B200 classes into the reference's OWN module_dict and build through the reference's OWN
+    call sites (`build_module("cv_clf")`, `build_encoder("vit")`): class identity + identical state_dict layout."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import load_reference as lr
+
+    if not lr.reference_available():
+        pytest.skip("reference tree not present")
+    mods = lr.load_modules()
+    ref_dict = mods.module_dict
+    cfg = dict(in_channels=3, num_classes=10, img_size=32, latent_dim=128, encoder="vit", encoder_config=dict(patch_size=16, num_layers=2))
+    before = mods.build_module("cv_clf", config=cfg)
+    before_enc = mods.build_encoder("vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, num_layers=2))
+    replaced = registry.install_into(ref_dict)
+    try:
+        after = mods.build_module("cv_clf", config=cfg)                      # the reference's build_module -> our class
+        assert type(after) is vit.VanillaClassifierB200
+        assert [(k, tuple(v.shape)) for k, v in after.state_dict().items()] == [(k, tuple(v.shape)) for k, v in before.state_dict().items()]
+        after.load_state_dict(before.state_dict(), strict=True)             # reference checkpoint -> drop-in, strict
+        before.load_state_dict(after.state_dict(), strict=True)             # and back
+        enc = mods.build_encoder("vit", config=dict(img_size=32, patch_size=16, in_channels=3, latent_dim=128, num_layers=2))
+        assert type(enc) is vit.ViTEncoderB200
+        assert [(k, tuple(v.shape)) for k, v in enc.state_dict().items()] == [(k, tuple(v.shape)) for k, v in before_enc.state_dict().items()]
+        # the reference's OWN VanillaClassifier resolves its encoder through build_encoder: only `encoders.vit` replaced
+        ref_dict["cv_clf"] = replaced["cv_clf"]
+        hybrid = mods.build_module("cv_clf", config=cfg)
+        assert type(hybrid) is replaced["cv_clf"] and type(hybrid.encoder) is vit.ViTEncoderB200 and hasattr(hybrid.encoder, "encode")
+        assert list(hybrid.state_dict().keys()) == list(before.state_dict().keys())
+    finally:
+        for k in ("encoders.vit_b200", "cv_clf_b200", "fcnn_b200", "tet_b200", "clip_b200"):
+            ref_dict.pop(k, None)
+        ref_dict.update(replaced)

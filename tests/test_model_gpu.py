@@ -56,7 +56,7 @@ def run_ours(cfg, sd, x, y):
     loss = vit.cross_entropy(logits, y)
     loss.backward()
     torch.cuda.synchronize()
-    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    grads = {k: p.grad.detach().clone() for k, p in m.named_arena_parameters()}  # ViTEncoder keys + head.linear.*: the oracle's names
     return logits.detach(), loss.detach(), grads, m
 
 
@@ -195,12 +195,11 @@ def test_graphed_train_step_matches_eager_steps():
     graphed = build(cfg, sd)
     graphed.arena.ensure()
     opt_g = ArenaAdam(graphed, lr=1e-3, capturable=True)
-    # capture runs warm-up steps on the static (zero) batch: undo their effect so both models start identically
-    gs = GraphedTrainStep(graphed, opt_g, batch=4, warmup=1)
-    graphed.load_state_dict(sd)
-    opt_g.exp_avg.zero_()
-    opt_g.exp_avg_sq.zero_()
-    opt_g.step_dev.zero_()
+    # the capture's warm-up steps (real Adam updates on an all-zero batch) must leave no trace: no manual reset here
+    gs = GraphedTrainStep(graphed, opt_g, batch=4, warmup=2)
+    assert int(opt_g.step_dev.item()) == 0 and float(opt_g.exp_avg.abs().max()) == 0.0
+    for k, p in graphed.named_arena_parameters():
+        assert torch.equal(p.detach().cpu(), sd[k]), k
     losses_g = [gs.step(x.to(DEV), y.to(DEV)).item() for x, y in xs]
     torch.cuda.synchronize()
     assert gs.launches_per_replay > 50

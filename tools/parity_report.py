@@ -36,7 +36,7 @@ def report(name, batch):
     loss = vit.cross_entropy(logits, y)
     loss.backward()
     torch.cuda.synchronize()
-    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    grads = {k: p.grad.detach().clone() for k, p in m.named_arena_parameters()}
     sdg = {k: v.to(DEV) for k, v in sd.items()}
     e_loss, e_grads, e_taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=True, want_taps=True)
     f_loss, f_grads, f_taps = vo.train_step(sdg, x, y, cfg, autocast_bf16=False, want_taps=True)
