@@ -175,6 +175,126 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# N > 1: gradient parity of the data-parallel path that is about to be timed (small config, every run)
+# ------------------------------------------------------------------------------------------------------------------
+def dp_gradient_parity(comm, rank, world, dev, flat=False):
+    """Runs the SAME graphed DP step the bench times (in-graph bucketed all-reduce over the native communicator) on a small
+    ViT with each rank's shard of a global batch, and compares the averaged gradients with a single-process run over the
+    whole batch on rank 0 (all-reduced grads == global-batch mean-loss grads).  Returns the relative L2
+    difference (rank 0; other ranks None) -- bf16 rounding of shard-wise weight gradients sets a floor of ~2e-3."""
+    import torch
+    import torch.distributed as dist
+
+    from cflearn_b200 import dp, registry
+    from cflearn_b200.optim import ArenaAdam, GraphedTrainStep
+
+    cfgs = dict(in_channels=3, num_classes=24, img_size=64, latent_dim=256, encoder="vit", encoder_config=dict(patch_size=16, num_layers=3))
+    per_rank = 8
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(per_rank * world, 3, 64, 64, generator=gen)
+    y = torch.randint(0, 24, (per_rank * world, 1), generator=gen)
+    torch.manual_seed(5)
+    m = registry.build_module("cv_clf", config=cfgs).to(dev)
+    with torch.no_grad():  # biases / LayerNorm parameters off their 0 / 1 initial values
+        for k, p in m.named_arena_parameters():
+            if k.endswith("bias") or "norm" in k:
+                p.add_(0.05 * torch.randn_like(p))
+    dp.broadcast_parameters(m)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    opt = ArenaAdam(m, lr=0.0, capturable=True)  # lr 0: the step leaves the parameters alone, the gradient arena is what we read
+    gs = GraphedTrainStep(m, opt, per_rank, comm=comm, flat=flat)
+    idx = list(dp.shard_indices(per_rank * world, rank, world))
+    gs.step(x[idx].to(dev), y[idx].to(dev))
+    torch.cuda.synchronize()
+    g_dp = m.arena.grad.clone()
+    ref = g_dp.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.equal(ref, g_dp)
+    flags = torch.tensor([1.0 if same else 0.0], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if flags.item() != 1.0:
+        raise SystemExit("bench.py: ranks disagree on the all-reduced gradients")
+    rel = None
+    if rank == 0:
+        single = registry.build_module("cv_clf", config=cfgs).to(dev)
+        single.load_state_dict(sd, strict=True)
+        single.train_step(x.to(dev), y.to(dev))
+        torch.cuda.synchronize()
+        g_one = single.arena.grad
+        rel = ((g_dp - g_one).norm() / g_one.norm()).item()
+        if not rel < 5e-3:
+            raise SystemExit(f"bench.py: data-parallel gradient parity failed: rel L2 {rel:.3e} >= 5e-3")
+    m.engine.reducer = None
+    del gs, m
+    return rel
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the real bar (BASELINE.md section 3): the reference path in PyTorch eager on the SAME GPU(s), torch DDP at N > 1
+# ------------------------------------------------------------------------------------------------------------------
+def eager_gpu_leg(rank, world, dev, steps, warmup):
+    """The oracle port (pinned bit-for-bit to the reference's modules, oracle/vit_oracle.py) under torch.autocast(bf16) on
+    CUDA: forward + cross-entropy + backward + torch's fused Adam, batch 256 per GPU, CUDA events; at N > 1 wrapped in
+    torch DistributedDataParallel over NCCL (what accelerate.prepare gives the reference, cflearn/trainer.py:266-273).
+    A BASELINE leg: nothing of the product is on this path, and the product never imports the oracle."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vit_oracle as vo
+
+    cfg = vo.vit_config(CONFIG_NAME)
+    sd = vo.init_state_dict(cfg, seed=0, perturb=False)
+    keys = list(sd.keys())
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(sd[k].clone()) for k in keys])
+
+        def forward(self, x):
+            return vo.classifier_forward(dict(zip(keys, self.ps)), x, cfg)
+
+    net = Net().to(dev)
+    mod = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index]) if world > 1 else net
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
+    B = PER_GPU_BATCH
+    x = torch.randn(B, 3, 224, 224, device=dev)
+    y = torch.randint(0, 1000, (B, 1), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = vo.cross_entropy(mod(x), y)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    del mod, net, opt, x, y
+    torch.cuda.empty_cache()
+    return {"value": round(world * B * steps / (ms / 1e3), 1), "unit": "samples/s", "ms_per_step": round(ms / steps, 3), "steps": steps,
+            "impl": "oracle port of the reference modules (pinned bit-for-bit), PyTorch eager, bf16 autocast, fused torch Adam"
+                    + (", torch DDP over NCCL" if world > 1 else ""), "torch": torch.__version__}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -199,18 +319,19 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    cfg = dict(img_size=224, patch_size=16, in_channels=3, latent_dim=768, num_layers=12, num_classes=1000)
     torch.manual_seed(0)
     model = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=1000, img_size=224, latent_dim=768, encoder="vit",
                                                         encoder_config=dict(patch_size=16, num_layers=12))).to(dev)
     model.arena.ensure()
+    comm = None
+    dp_parity = None
     if world > 1:
+        # the library's own NCCL communicator (csrc/comm.cu): its all-reduces are plain stream operations, so the bucketed
+        # exchange is captured INSIDE the step's CUDA graph on a forked stream, overlapped with the remaining backward
+        comm = dp.NativeComm(rank, world, dev)
         dp.broadcast_parameters(model)
-        dp.attach_reducer(model)
-    use_graph = not (args.no_graph or args.overlap_dp)
-    if use_graph and world > 1:
-        model.engine.reducer = None  # graphed DP step: one all-reduce of the flat gradient arena after the replay
+        dp_parity = dp_gradient_parity(comm, rank, world, dev, flat=args.flat_allreduce)
+    use_graph = not args.no_graph
     opt = ArenaAdam(model, lr=1e-3, capturable=use_graph)
     B = PER_GPU_BATCH
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)  # rank r uses its own data seed
@@ -219,20 +340,20 @@ def run_b200(args):
     host_y = [torch.randint(0, 1000, (B, 1), generator=g).pin_memory() for _ in range(n_host)]
     dev_x = [h.to(dev) for h in host_x]
     dev_y = [h.to(dev) for h in host_y]
-    loss_host = torch.zeros(1).pin_memory()
 
     gstep = None
-    if use_graph:  # zero_grad + fwd + CE + bwd (+ Adam at N = 1) as ONE CUDA graph; N > 1: all-reduce + Adam follow it
+    if use_graph:  # zero_grad + fwd + CE + bwd + (N > 1: per-block bucket all-reduces on a forked stream) + Adam as ONE CUDA graph
         from cflearn_b200.optim import GraphedTrainStep
 
-        model.arena.ensure()
-        gstep = GraphedTrainStep(model, opt, B)
+        gstep = GraphedTrainStep(model, opt, B, comm=comm, flat=args.flat_allreduce)
+    elif world > 1:
+        dp.attach_native_reducer(model, comm)
 
     def do_step(x, y):
         if gstep is not None:
             return gstep.step(x, y)
         opt.zero_grad()  # schema.py:984 (backward then overwrites the gradient arena instead of accumulating)
-        loss = model.train_step(x, y)
+        loss = model.train_step(x, y)  # N > 1: the native bucket reducer all-reduces inside backward
         opt.step()
         return loss
 
@@ -333,38 +454,89 @@ def run_b200(args):
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     d2h = 4
 
-    # ---- roofline of the dominant kernel: the tcgen05 GEMM (FeedForward up-projection, fused bias+GELU) ----------
+    # ---- roofline: every heavy kernel of the step timed ALONE at its bench shape (CUDA events on the launching stream);
+    # `roofline` proper names the top-time kernel of the step's launch list (profiles/r0X_step_launches.md): the split-K
+    # weight-gradient GEMM gemm_bf16_kernel<EPI_PARTIAL_F32> at the FeedForward shape; the others are listed beside it ------
     peaks = _peaks()
-    M, N, K = B * 197, 3072, 768
-    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
-    w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
-    bias = torch.zeros(N, device=dev, dtype=torch.bfloat16)
-    o0 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    o1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    for _ in range(3):
-        ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_BF16, out0=o0, out1=o1)
-    torch.cuda.synchronize()
-    reps = 20
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_BF16, out0=o0, out1=o1)
-    k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / reps
-    achieved = 2.0 * M * N * K / (k_ms * 1e-3) / 1e12
+    M, D_, FF_, H_ = B * 197, 768, 3072, 12
+
+    def bf(*shape, scale=1.0):
+        return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+    x768, x3072, hpre = bf(M, D_), bf(M, FF_), bf(M, FF_)
+    w_qkv, w_1, w_2 = bf(3 * D_, D_, scale=0.02), bf(FF_, D_, scale=0.02), bf(D_, FF_, scale=0.02)
+    b_qkv, b_1, b_o = bf(3 * D_, scale=0.02), bf(FF_, scale=0.02), bf(D_, scale=0.02)
+    resid = torch.randn(M, D_, device=dev)
+    o_qkv = torch.empty(M, 3 * D_, device=dev, dtype=torch.bfloat16)
+    o_ff0, o_ff1 = torch.empty(M, FF_, device=dev, dtype=torch.bfloat16), torch.empty(M, FF_, device=dev, dtype=torch.bfloat16)
+    o_res = torch.empty(M, D_, device=dev, dtype=torch.float32)
+    splits = ops.pick_splits(FF_, D_, M)
+    part = torch.empty(splits, FF_, D_, device=dev, dtype=torch.float32)
+    qkv = bf(B, 197, 3 * D_)
+    att_o, att_lse = ops.attention_fwd(qkv, B, 197, H_)
+    att_do = bf(M, D_)
+    att_dqkv = torch.empty(M, 3 * D_, device=dev, dtype=torch.bfloat16)
+
+    def time_kernel(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
+    gf = 2.0 * M * FF_ * D_
+    kernels = [
+        ("gemm_bf16_kernel<EPI_PARTIAL_F32> wgrad dW1 = dh^T.ln2 3072x768x50432 split-K", gf,
+         lambda: ops.gemm(x3072, x768, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_PARTIAL_F32, out0=part, splits=splits)),
+        ("gemm_bf16_kernel<EPI_BIAS_BF16> qkv 50432x2304x768", 2.0 * M * 3 * D_ * D_, lambda: ops.gemm(x768, w_qkv, bias=b_qkv, out0=o_qkv)),
+        ("gemm_bf16_kernel<EPI_BIAS_GELU_BF16> ff1 50432x3072x768", gf,
+         lambda: ops.gemm(x768, w_1, bias=b_1, epilogue=ops.EPI_BIAS_GELU_BF16, out0=o_ff0, out1=o_ff1)),
+        ("gemm_bf16_kernel<EPI_BIAS_RESID_F32> ff2 50432x768x3072", gf,
+         lambda: ops.gemm(x3072, w_2, bias=b_o, epilogue=ops.EPI_BIAS_RESID_F32, aux=resid, out0=o_res)),
+        ("gemm_bf16_kernel<EPI_DGELU_BF16> ff2-dgrad 50432x3072x768", gf,
+         lambda: ops.gemm(x768, w_2, b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=hpre, out0=o_ff0)),
+        ("attn_fwd_kernel B256 T197 H12", 4.0 * B * H_ * 197 * 197 * 64, lambda: ops.attention_fwd(qkv, B, 197, H_)),
+        ("attn_bwd_kernel B256 T197 H12", 10.0 * B * H_ * 197 * 197 * 64,
+         lambda: ops.attention_bwd(qkv, att_o, att_do, att_lse, B, 197, H_, dqkv=att_dqkv)),
+    ]
+    timed = []
+    for name, flops, fn in kernels:
+        k_ms = time_kernel(fn)
+        tf = flops / (k_ms * 1e-3) / 1e12
+        timed.append({"kernel": name, "kernel_ms": round(k_ms, 4), "achieved": round(tf, 1), "frac": round(tf / peaks["burst"], 4)})
+    del x768, x3072, hpre, o_qkv, o_ff0, o_ff1, o_res, part, qkv, att_o, att_do, att_dqkv
     step_tflops = FLOP_PER_IMAGE_FWD_BWD * B / (ms_step * 1e-3) / 1e12
+    traffic, traffic_note = None, "no ncu --set full capture of this build's kernel committed yet"
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")  # written from the committed capture by tools/ncu_summary.py
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_note = tj.get("wgrad_ff1_bytes_per_launch"), tj.get("note", "")
+    top = timed[0]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_bf16_kernel<EPI_BIAS_GELU_BF16> 50432x3072x768", "achieved": round(achieved, 1),
-        "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(achieved / peaks["burst"], 4),
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed ncu --set full
-        # capture (profiles/r01_ncu_summary.md: 82.4 MB + 566.2 MB); algorithmic bytes are 702 MB, so nothing is re-read
-        "traffic": 648528640, "traffic_unit": "B/launch (ncu, profiles/r01_ncu_summary.md)",
+        "bound": "tensor", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peaks["burst"], "unit": "TFLOP/s",
+        "frac": top["frac"], "kernel_ms": top["kernel_ms"],
+        "why_this_kernel": "top-time kernel of the step's ncu launch list (profiles/): the split-K wgrad GEMM variant",
+        "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)",
-        "kernel_ms": round(k_ms, 4),
+        "others": timed[1:],
         "step": {"achieved": round(step_tflops, 1), "peak": peaks["sustained"], "frac": round(step_tflops / peaks["sustained"], 4),
                  "note": "whole step, GEMM-only FLOPs 105.38 GFLOP/image, vs sustained cuBLAS bf16 peak"},
     }
+
+    # ---- the real bar: the reference path in PyTorch eager on the same GPU(s) (DDP at N > 1), same run ---------------
+    eager = None
+    if not args.no_eager_baseline:
+        if gstep is not None:
+            gstep = None  # free the graph's private pool (~17 GB) before eager allocates its ~40 GB of activations
+        torch.cuda.empty_cache()
+        eager = eager_gpu_leg(rank, world, dev, steps=min(args.steps, 10), warmup=3)
+        eager["speedup_of_value"] = round(value / eager["value"], 3)
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle on the host cores, bounded sample -------------------------
     cpu = None
@@ -382,13 +554,18 @@ def run_b200(args):
                        "global_batch": world * B, "seq_len": 197, "parallelism": f"dp{world}",
                        "optimizer": "adam (fused arena kernel, inside the timed region)",
                        "cuda_graph": bool(use_graph),
+                       "gradient_exchange": (None if world == 1 else ("one flat NCCL all-reduce after the graph (A/B mode)" if args.flat_allreduce else
+                                             "per-block bucket all-reduces (library-owned NCCL communicator) captured inside the step graph on a forked stream")),
                        "l2": "per-step working set (> 15 GB of activations) exceeds the 126 MB L2; no explicit flush needed"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": round(e2e_ms / args.steps, 3)},
-            "roofline": roofline, "cpu_baseline": cpu, "loss": round(final_loss, 4),
+            "roofline": roofline, "cpu_baseline": cpu, "eager_gpu": eager, "dp_parity_rel": dp_parity, "loss": round(final_loss, 4),
         }
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -401,7 +578,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--overlap-dp", action="store_true", help="N > 1: eager launches with the bucketed, overlapped all-reduce (implies --no-graph)")
+    ap.add_argument("--flat-allreduce", action="store_true", help="N > 1 A/B mode: graph up to backward, then ONE all-reduce of the gradient arena + Adam")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -161,18 +161,24 @@ class GraphedTrainStep:
     reducer launches ``ncclAllReduce`` per transformer block on a forked stream as soon as that block's gradients are
     complete -- and the Adam update behind the join."""
 
-    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, comm: Any = None):
+    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, comm: Any = None, flat: bool = False):
         if not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs ArenaAdam(capturable=True)")
         from . import _cabi, dp
 
         self.world = 1 if comm is None else comm.world
         self.comm = comm
+        # flat=True (A/B switch): the graph stops after backward; ONE all-reduce of the whole gradient arena and Adam are
+        # enqueued behind every replay -- the un-overlapped schedule round 1 measured
+        self.flat = bool(flat) and self.world > 1
         g = model.geo
         model.arena.ensure()
         dev = model.arena.flat.device
         self.model, self.optimizer = model, optimizer
-        if self.world > 1:
+        if self.flat:
+            model.engine.reducer = None
+            self.reducer = None
+        elif self.world > 1:
             red = model.engine.reducer
             if not isinstance(red, dp.NativeBucketReducer) or red.comm is not comm:
                 red = dp.attach_native_reducer(model, comm)
@@ -211,7 +217,8 @@ class GraphedTrainStep:
     def _eager(self) -> None:
         self.optimizer.zero_grad()
         loss = self.model.train_step(self.x, self.labels)  # DP: the reducer all-reduces bucket by bucket inside backward
-        self.optimizer.step()
+        if not self.flat:
+            self.optimizer.step()
         self.loss.copy_(loss)
         flag = getattr(self.model, "last_bad_flag", None)
         if flag is not None:
@@ -222,6 +229,9 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.labels.copy_(labels.reshape(self.labels.shape), non_blocking=True)
         self.graph.replay()
+        if self.flat:
+            self.comm.allreduce_(self.model.arena.grad, average=True)
+            self.optimizer.step()
         return self.loss
 
     def check_labels(self) -> None:
