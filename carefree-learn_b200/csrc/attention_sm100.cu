@@ -284,6 +284,300 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, version 2: persistent + warp-specialised, probabilities kept in TENSOR MEMORY
+// ------------------------------------------------------------------------------------------------
+// Version 1 above is one short-lived CTA per (batch, head, query tile): every CTA pays launch + TMEM allocation + the
+// full TMA latency before its first MMA, and its load -> S -> softmax -> P -> O -> store chain is serial (ncu, round 1:
+// tensor pipe 14 %, MUFU 30 %, 2.2 TB/s -- nothing saturated; 132 us against torch SDPA's 102 us).  Version 2:
+//   * ONE persistent CTA per SM walks over (batch, head) items; a 2-stage TMA ring prefetches the next item's Q / K / V
+//     (K and V are fetched once per item, not once per query tile) while the current one is being processed;
+//   * work unit = one 128-query tile; two TMEM slots of 256 columns alternate between units, so the tensor pipe computes
+//     S(u+1) = Q K^T while the softmax warps are busy with unit u, and O(u) = P V while they are busy with unit u+1;
+//   * 8 softmax warps (two threads per score row, ONE pass over TMEM: each thread keeps its half row in registers --
+//     setmaxnreg moves the registers of the idle / light warpgroups to them) write the bf16 probabilities back into the
+//     columns of S with tcgen05.st, and O = P V takes its A operand straight from TMEM (tcgen05.mma [d], [a_tmem], b_desc):
+//     P never goes through shared memory, which is what frees the 64 KB the second ring stage needs;
+//   * 4 epilogue warps drain O (TMEM -> registers -> the unit's own, by then dead, Q tile as staging -> coalesced 16-byte
+//     global stores), so the softmax warps never wait for the PV product.
+// Warpgroups: 0 = {TMA producer, MMA issuer, 2 idle warps}, 1 and 2 = softmax, 3 = epilogue.
+constexpr int F2_THREADS = 512;
+constexpr int F2_Q = 0;                    // 2 x 16 KB  (query tiles 0 / 1 of the item)
+constexpr int F2_K = 32768;                // 32 KB      (up to 256 keys)
+constexpr int F2_V = 65536;                // 32 KB
+constexpr int F2_STAGE = 98304;
+constexpr int F2_STATS = 2 * F2_STAGE;     // per TMEM slot: xmax[2][128], psum[2][128], rmax[128]  (floats)
+constexpr int F2_STATS_SLOT = (256 + 256 + 128) * 4;
+constexpr int F2_BAR = F2_STATS + 2 * F2_STATS_SLOT;
+constexpr int F2_SMEM = F2_BAR + 256 + 1024;
+constexpr uint32_t F2_SLOT_COLS = 256;     // S / P at column 0 of the slot, O at column 192 (P never exceeds 128 columns)
+constexpr uint32_t F2_O_COL = 192;
+
+// this warp's 32 accumulator rows (TMEM lane == row) x 64 fp32 columns -> bf16 * sc -> warp-private 4 KB staging area
+// (row r at r * 128 B, its eight 16-byte chunks XOR-swizzled with r & 7: both passes are bank-conflict free)
+__device__ __forceinline__ void stage_rows64(uint8_t* stage, uint32_t taddr, float sc, int lane) {
+    uint8_t* mine = stage + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+        tmem_ld_wait();
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+        o0.y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+        o0.z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+        o0.w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+        o1.x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+        o1.y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+        o1.z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+        o1.w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c) ^ sw) << 4)) = o0;
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c + 1) ^ sw) << 4)) = o1;
+    }
+}
+// staged rows -> global: 8 lanes x 16 B write one whole 128-byte row, 4 rows per instruction
+__device__ __forceinline__ void flush_rows64(const uint8_t* stage, __nv_bfloat16* g0, long long row_stride, int rows_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3);
+        const uint32_t ch = static_cast<uint32_t>(lane) & 7u;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (static_cast<uint32_t>(row) & 7u)) << 4));
+        if (row < rows_valid) *reinterpret_cast<uint4*>(g0 + row * row_stride + ch * 8) = val;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, const AttnParams p, const int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + F2_BAR);  // [2] stage loaded
+    uint64_t* empty_bar = full_bar + 2;                               // [2] stage free (epilogue warps of every unit of the item)
+    uint64_t* bar_s = full_bar + 4;                                   // [2] S of the slot's unit is in TMEM
+    uint64_t* bar_p = full_bar + 6;                                   // [2] P written (8 softmax warps)
+    uint64_t* bar_o = full_bar + 8;                                   // [2] O complete
+    uint64_t* bar_stats = full_bar + 10;                              // [2] row max / partial sums in smem (8 softmax warps)
+    uint64_t* slot_free = full_bar + 12;                              // [2] O read out of TMEM (4 epilogue warps)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(full_bar + 14);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_mt = (p.T + 127) / 128;
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_units = n_my * n_mt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], static_cast<uint32_t>(4 * n_mt));
+            mbar_init(&bar_s[i], 1);
+            mbar_init(&bar_p[i], 8);
+            mbar_init(&bar_o[i], 1);
+            mbar_init(&bar_stats[i], 8);
+            mbar_init(&slot_free[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int wg = warp >> 2;
+
+    if (wg == 0) {
+        setmaxnreg_dec<40>();
+        if (warp == 0) {
+            // ===================================== TMA producer =====================================
+            if (elect_one()) {
+                const uint32_t bytes = static_cast<uint32_t>(n_mt) * 16384u + 2u * static_cast<uint32_t>(p.tp) * 128u;
+                for (int it = 0; it < n_my; ++it) {
+                    const int s = it & 1;
+                    mbar_wait(&empty_bar[s], static_cast<uint32_t>((it >> 1) & 1) ^ 1u);
+                    const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                    const int h = w % p.H, b = w / p.H;
+                    uint8_t* st = smem + s * F2_STAGE;
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(st + F2_Q + mt * 16384, &tmQ, &full_bar[s], h * 64, mt * 128, b);
+                    tma_load_3d(st + F2_K, &tmKV, &full_bar[s], p.D + h * 64, 0, b);
+                    tma_load_3d(st + F2_V, &tmKV, &full_bar[s], 2 * p.D + h * 64, 0, b);
+                }
+            }
+        } else if (warp == 1) {
+            // ===================================== MMA issuer =======================================
+            if (elect_one()) {
+                const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(p.tp), 0, 0);
+                const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+                const int nkk = p.tp / 16;
+                auto issue_s = [&](int j) {
+                    const int it = j / n_mt, mt = j - it * n_mt, s = it & 1, slot = j & 1, k = j >> 1;
+                    if (mt == 0) mbar_wait(&full_bar[s], static_cast<uint32_t>((it >> 1) & 1));
+                    mbar_wait(&slot_free[slot], static_cast<uint32_t>(k & 1) ^ 1u);  // O of unit j-2 has left the slot
+                    tc_fence_after_sync();
+                    const uint32_t q_base = smem_u32(smem + s * F2_STAGE + F2_Q + mt * 16384);
+                    const uint32_t k_base = smem_u32(smem + s * F2_STAGE + F2_K);
+                    const uint32_t d = tmem_base + static_cast<uint32_t>(slot) * F2_SLOT_COLS;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(d, make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128),
+                                  idesc_s, kk > 0 ? 1u : 0u);
+                    umma_commit(&bar_s[slot]);
+                };
+                if (n_units > 0) issue_s(0);
+                if (n_units > 1) issue_s(1);
+                for (int j = 0; j < n_units; ++j) {
+                    const int it = j / n_mt, s = it & 1, slot = j & 1, k = j >> 1;
+                    mbar_wait(&bar_p[slot], static_cast<uint32_t>(k & 1));
+                    tc_fence_after_sync();
+                    const uint32_t v_base = smem_u32(smem + s * F2_STAGE + F2_V);
+                    const uint32_t base = tmem_base + static_cast<uint32_t>(slot) * F2_SLOT_COLS;
+                    for (int kk = 0; kk < nkk; ++kk)  // A = P[128 x 16] from TMEM (8 packed columns per k-step), B = V MN-major
+                        umma_bf16_ts(base + F2_O_COL, base + static_cast<uint32_t>(kk * 8), make_smem_desc(v_base + kk * 2048, 0, 1024, kSwz128),
+                                     idesc_o, kk > 0 ? 1u : 0u);
+                    umma_commit(&bar_o[slot]);
+                    if (j + 2 < n_units) issue_s(j + 2);  // runs under the softmax of unit j+1
+                }
+            }
+        }
+    } else if (wg == 3) {
+        // ===================================== epilogue warps =====================================
+        setmaxnreg_dec<72>();
+        const uint32_t q = static_cast<uint32_t>(warp & 3);
+        const int r = static_cast<int>(q) * 32 + lane;
+        for (int j = 0; j < n_units; ++j) {
+            const int it = j / n_mt, mt = j - it * n_mt, s = it & 1, slot = j & 1, k = j >> 1;
+            const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int h = w % p.H, b = w / p.H;
+            const int row0 = mt * 128 + static_cast<int>(q) * 32;
+            const bool dead = row0 >= p.T;
+            const float* stats = reinterpret_cast<const float*>(smem + F2_STATS + slot * F2_STATS_SLOT);
+            mbar_wait(&bar_stats[slot], static_cast<uint32_t>(k & 1));
+            const float sum = stats[256 + r] + stats[384 + r];
+            const float m = stats[512 + r];
+            mbar_wait(&bar_o[slot], static_cast<uint32_t>(k & 1));
+            tc_fence_after_sync();
+            uint8_t* stage = smem + s * F2_STAGE + F2_Q + mt * 16384 + static_cast<int>(q) * 4096;  // the unit's own Q tile: dead since S
+            if (!dead)
+                stage_rows64(stage, tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(slot) * F2_SLOT_COLS + F2_O_COL, 1.0f / sum, lane);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_free[slot]);
+            if (!dead) {
+                __nv_bfloat16* g0 = out + (static_cast<long long>(b) * p.T + row0) * p.D + h * 64;
+                flush_rows64(stage, g0, p.D, p.T - row0, lane);
+                const int i = row0 + lane;
+                if (i < p.T) lse_out[(static_cast<long long>(b) * p.H + h) * p.T + i] = m * p.scale + logf(sum);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+    } else {
+        // ===================================== softmax warps ======================================
+        setmaxnreg_inc<200>();
+        const uint32_t q = static_cast<uint32_t>(warp & 3);
+        const int hf = (warp - 4) >> 2;                    // which half of the score columns this thread owns
+        const int r = static_cast<int>(q) * 32 + lane;     // row of the query tile == TMEM lane
+        const float sl2 = p.scale * kLog2e;
+        const int nchunk = p.tp / 16;
+        const int nc0 = (nchunk + 1) / 2;
+        const int cb = hf ? nc0 : 0;
+        const int nmine = hf ? nchunk - nc0 : nc0;          // <= 8 chunks of 16 columns
+        for (int j = 0; j < n_units; ++j) {
+            const int it = j / n_mt, mt = j - it * n_mt, slot = j & 1, k = j >> 1;
+            const int i = mt * 128 + r;
+            const bool dead = mt * 128 + static_cast<int>(q) * 32 >= p.T;  // all 32 rows of this warp are padding
+            float* stats = reinterpret_cast<float*>(smem + F2_STATS + slot * F2_STATS_SLOT);
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(slot) * F2_SLOT_COLS;
+            int nvalid = p.T;
+            if (p.causal && i + 1 < nvalid) nvalid = i + 1;
+            mbar_wait(&bar_s[slot], static_cast<uint32_t>(k & 1));
+            tc_fence_after_sync();
+            uint32_t v[8][16];
+            float m = -INFINITY;
+            if (!dead) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < nmine) tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < nmine) {
+                        const int col0 = (cb + c) * 16;
+                        if (!p.causal && col0 + 16 <= p.T) {  // warp-uniform: whole chunk valid
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) m = fmaxf(m, __uint_as_float(v[c][jj]));
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj)
+                                if (col0 + jj < nvalid) m = fmaxf(m, __uint_as_float(v[c][jj]));
+                        }
+                    }
+                }
+            }
+            stats[hf * 128 + r] = m;
+            // every S column of this slot has been read into registers once all 256 threads pass this barrier: only then may
+            // the (other half's) P columns overwrite them
+            tc_fence_before_sync();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tc_fence_after_sync();
+            m = fmaxf(stats[r], stats[128 + r]);
+            const float m2 = m * sl2;
+            float sum = 0.f;
+            if (!dead) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < nmine) {
+                        const int col0 = (cb + c) * 16;
+                        float pv[16];
+                        if (!p.causal && col0 + 16 <= p.T) {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                pv[jj] = fast_ex2(fmaf(__uint_as_float(v[c][jj]), sl2, -m2));
+                                sum += pv[jj];
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                const float e = fast_ex2(fmaf(__uint_as_float(v[c][jj]), sl2, -m2));
+                                pv[jj] = (col0 + jj < nvalid) ? e : 0.f;
+                                sum += pv[jj];
+                            }
+                        }
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
+                        tmem_st_32x32b_x8(taddr + static_cast<uint32_t>((cb + c) * 8), pk);  // P[row, col0 .. col0+16) -> 8 packed columns
+                    }
+                }
+                tmem_st_wait();
+            }
+            stats[256 + hf * 128 + r] = sum;
+            if (hf == 0) stats[512 + r] = m;
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bar_p[slot]);
+                mbar_arrive(&bar_stats[slot]);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 constexpr int AB_THREADS = 288;
@@ -569,6 +863,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 using namespace b200;
 
+static int g_attn_fwd_version = 2;
+
 static int attn_check(int B, int T, int H, int Dh) {
     if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");
     if (Dh != 64) return set_error(B200_ERR_ARG, "attention: head dim must be 64");
@@ -593,14 +889,29 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
     const int dev = current_device_slot();
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
         configured[dev] = true;
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = tp; p.scale = scale; p.causal = causal;
     const int n_mt = (T + 127) / 128;
-    attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
+    if (g_attn_fwd_version == 1) {
+        attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
+    } else {
+        const int n_items = B * H;
+        const int grid = n_items < num_sms() ? n_items : num_sms();
+        attn_fwd2_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p, n_items);
+    }
     return check_launch("attention_fwd");
+}
+
+// 2 (default): persistent pipelined forward with P in tensor memory; 1: the round-1 kernel (A/B timing, same results up to
+// the summation order of the row sums)
+extern "C" int b200_set_attention_fwd_version(int version) {
+    const int old = g_attn_fwd_version;
+    g_attn_fwd_version = version == 1 ? 1 : 2;
+    return old;
 }
 
 extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,

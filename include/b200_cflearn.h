@@ -124,6 +124,9 @@ int b200_colsum_finish2(const float* part, long long part_ld, int nparts, int co
  * --------------------------------------------------------------------------------------------------------- */
 int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int H, int Dh, float scale,
                        int causal, cudaStream_t stream);
+/* forward kernel version: 2 (default) = persistent, warp-specialised, probabilities kept in tensor memory; 1 = the
+ * round-1 kernel (one CTA per query tile).  Returns the previous setting.  For A/B timing; results agree to fp32 rounding. */
+int b200_set_attention_fwd_version(int version);
 /* dbias_part (optional, f32 [B, 3*H*Dh]): per-image column sums of the bf16 dqkv rows written; summed over the batch
  * (b200_colsum_finish, nparts = B) they are the gradient of the packed qkv bias (attentions.py:112-119). */
 int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,

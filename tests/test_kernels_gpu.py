@@ -329,7 +329,27 @@ def _attn_ref(qkv, B, T, H, causal):
 
 
 @pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False), (2, 128, 1, True)])
-def test_attention_fwd(B, T, H, causal):
+@pytest.mark.parametrize("version", [2, 1])
+def test_attention_fwd(B, T, H, causal, version):
+    """version 2: persistent pipelined kernel with P in tensor memory (default); version 1: the round-1 kernel."""
+    from cflearn_b200 import _cabi
+
+    prev = _cabi.lib().b200_set_attention_fwd_version(version)
+    try:
+        _attention_fwd_case(B, T, H, causal)
+    finally:
+        _cabi.lib().b200_set_attention_fwd_version(prev)
+
+
+def test_attention_fwd_many_items_per_cta():
+    """More (batch, head) items than SMs: every persistent CTA walks several items through both ring stages and both TMEM
+    slots (the small cases above give each CTA at most one item)."""
+    _attention_fwd_case(40, 197, 12, False)
+    _attention_fwd_case(64, 77, 8, True)
+    _attention_fwd_case(37, 50, 12, False)
+
+
+def _attention_fwd_case(B, T, H, causal):
     qkv = _rand_bf16(B * T, 3 * H * 64, seed=71)
     out, lse = ops.attention_fwd(qkv, B, T, H, causal=causal)
     torch.cuda.synchronize()

@@ -43,6 +43,20 @@ h = bf(M, FF)
 act = torch.empty(M, FF, device=dev, dtype=torch.bfloat16)
 gw = torch.empty(FF, D, device=dev)
 rows = []
+only_attn = len(sys.argv) > 1 and sys.argv[1] == "attn"
+if only_attn:
+    qkv = bf(B, T, 3 * D)
+    out, lse = ops.attention_fwd(qkv, B, T, H)
+    dout = bf(B, T, D)
+    rows.append(("attention fwd  B256 T197 H12", timeit(lambda: ops.attention_fwd(qkv, B, T, H)), 4 * B * H * T * T * 64))
+    rows.append(("attention bwd  B256 T197 H12", timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, T, H)), 10 * B * H * T * T * 64))
+    qk = bf(256, 77, 3 * 512)
+    rows.append(("attention fwd  B256 T77 H8 causal (CLIP text)", timeit(lambda: ops.attention_fwd(qk, 256, 77, 8, causal=True)), 4 * 256 * 8 * 77 * 77 * 64))
+    qv = bf(256, 50, 3 * 768)
+    rows.append(("attention fwd  B256 T50 H12 (CLIP vision)", timeit(lambda: ops.attention_fwd(qv, 256, 50, 12)), 4 * 256 * 12 * 50 * 50 * 64))
+    for name, us, fl in rows:
+        print(f"{name:48s} {us:8.1f} us  {fl / us / 1e6:7.0f} TFLOP/s", flush=True)
+    sys.exit(0)
 rows.append(("gemm qkv       bias      50432x2304x768", timeit(lambda: ops.gemm(x768, w_qkv, bias=b_qkv)), 2 * M * 3 * D * D))
 rows.append(("gemm out-proj  resid f32 50432x768x768", timeit(lambda: ops.gemm(x768, w_o, bias=b_o, epilogue=ops.EPI_BIAS_RESID_F32, aux=resid)), 2 * M * D * D))
 rows.append(("gemm ff1       gelu      50432x3072x768", timeit(lambda: ops.gemm(x768, w_1, bias=b_1, epilogue=ops.EPI_BIAS_GELU_BF16, out1=act)), 2 * M * FF * D))
