@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_IMAGE_FWD_BWD = 105_382_969_344  # BASELINE.md section 2 (GEMM-only, 3x forward)
+CLIP_FLOP_PER_PAIR_FWD_BWD = 3 * 14_780_000_000  # 14.78 GFLOP / pair forward (vision 8.82 + text 5.96)
 CONFIG_NAME = "vit_b16"
 PER_GPU_BATCH = 256
 
@@ -320,9 +321,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
-    model = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=1000, img_size=224, latent_dim=768, encoder="vit",
-                                                        encoder_config=dict(patch_size=16, num_layers=12))).to(dev)
-    model.arena.ensure()
+    is_clip = args.config == "clip"
+    if is_clip:  # BASELINE.json configs[3]: CLIP() defaults = ViT-B/32 vision tower + 12 x 512 text tower, context 77, vocab 49,408
+        model = registry.build_module("clip").to(dev)
+    else:
+        model = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=1000, img_size=224, latent_dim=768, encoder="vit",
+                                                            encoder_config=dict(patch_size=16, num_layers=12))).to(dev)
+    for a in (model.arenas() if is_clip else [model.arena]):
+        a.ensure()
     comm = None
     dp_parity = None
     if world > 1:
@@ -330,24 +336,32 @@ def run_b200(args):
         # exchange is captured INSIDE the step's CUDA graph on a forked stream, overlapped with the remaining backward
         comm = dp.NativeComm(rank, world, dev)
         dp.broadcast_parameters(model)
-        dp_parity = dp_gradient_parity(comm, rank, world, dev, flat=args.flat_allreduce)
+        dp_parity = dp_gradient_parity(comm, rank, world, dev, flat=args.flat_allreduce)  # (the ViT path's reducer; CLIP reuses it per tower)
     use_graph = not args.no_graph
     opt = ArenaAdam(model, lr=1e-3, capturable=use_graph)
     B = PER_GPU_BATCH
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)  # rank r uses its own data seed
     n_host = 2
     host_x = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_host)]
-    host_y = [torch.randint(0, 1000, (B, 1), generator=g).pin_memory() for _ in range(n_host)]
+    if is_clip:  # ids uniform in [1, V-2], EOS (= V-1, the arg-max id) forced at a random position >= 1
+        host_y = []
+        for _ in range(n_host):
+            ids = torch.randint(1, 49407, (B, 77), generator=g)
+            ids[torch.arange(B), torch.randint(1, 77, (B,), generator=g)] = 49407
+            host_y.append(ids.pin_memory())
+    else:
+        host_y = [torch.randint(0, 1000, (B, 1), generator=g).pin_memory() for _ in range(n_host)]
     dev_x = [h.to(dev) for h in host_x]
     dev_y = [h.to(dev) for h in host_y]
 
     gstep = None
-    if use_graph:  # zero_grad + fwd + CE + bwd + (N > 1: per-block bucket all-reduces on a forked stream) + Adam as ONE CUDA graph
+    if use_graph:  # zero_grad + fwd + loss + bwd + (N > 1: per-block bucket all-reduces on a forked stream) + Adam as ONE CUDA graph
         from cflearn_b200.optim import GraphedTrainStep
 
-        gstep = GraphedTrainStep(model, opt, B, comm=comm, flat=args.flat_allreduce)
+        static_inputs = [torch.zeros_like(dev_x[0]), torch.zeros_like(dev_y[0])] if is_clip else None
+        gstep = GraphedTrainStep(model, opt, B, comm=comm, flat=args.flat_allreduce, inputs=static_inputs)
     elif world > 1:
-        dp.attach_native_reducer(model, comm)
+        dp.attach_native_reducers(model, comm)
 
     def do_step(x, y):
         if gstep is not None:
@@ -454,6 +468,7 @@ def run_b200(args):
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     d2h = 4
 
+    flop_per_sample = CLIP_FLOP_PER_PAIR_FWD_BWD if is_clip else FLOP_PER_IMAGE_FWD_BWD
     # ---- roofline: every heavy kernel of the step timed ALONE at its bench shape (CUDA events on the launching stream);
     # `roofline` proper names the top-time kernel of the step's launch list (profiles/r0X_step_launches.md): the split-K
     # weight-gradient GEMM gemm_bf16_kernel<EPI_PARTIAL_F32> at the FeedForward shape; the others are listed beside it ------
@@ -510,7 +525,7 @@ def run_b200(args):
         tf = flops / (k_ms * 1e-3) / 1e12
         timed.append({"kernel": name, "kernel_ms": round(k_ms, 4), "achieved": round(tf, 1), "frac": round(tf / peaks["burst"], 4)})
     del x768, x3072, hpre, o_qkv, o_ff0, o_ff1, o_res, part, qkv, att_o, att_do, att_dqkv
-    step_tflops = FLOP_PER_IMAGE_FWD_BWD * B / (ms_step * 1e-3) / 1e12
+    step_tflops = flop_per_sample * B / (ms_step * 1e-3) / 1e12
     traffic, traffic_note = None, "no ncu --set full capture of this build's kernel committed yet"
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")  # written from the committed capture by tools/ncu_summary.py
     if os.path.isfile(tpath):
@@ -526,12 +541,12 @@ def run_b200(args):
         "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)",
         "others": timed[1:],
         "step": {"achieved": round(step_tflops, 1), "peak": peaks["sustained"], "frac": round(step_tflops / peaks["sustained"], 4),
-                 "note": "whole step, GEMM-only FLOPs 105.38 GFLOP/image, vs sustained cuBLAS bf16 peak"},
+                 "note": f"whole step, GEMM-only FLOPs {flop_per_sample / 1e9:.2f} GFLOP/sample (3x forward), vs sustained cuBLAS bf16 peak"},
     }
 
     # ---- the real bar: the reference path in PyTorch eager on the same GPU(s) (DDP at N > 1), same run ---------------
     eager = None
-    if not args.no_eager_baseline:
+    if not args.no_eager_baseline and not is_clip:
         if gstep is not None:
             gstep = None  # free the graph's private pool (~17 GB) before eager allocates its ~40 GB of activations
         torch.cuda.empty_cache()
@@ -547,11 +562,14 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "train samples/sec, ViT-B/16 224px, fwd+bwd+adam step", "value": round(value, 1), "unit": "samples/s",
+            "metric": ("train pairs/sec, CLIP ViT-B/32 + text transformer, contrastive fwd+bwd+adam step" if is_clip else
+                       "train samples/sec, ViT-B/16 224px, fwd+bwd+adam step"), "value": round(value, 1), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViT-B/16 classifier 224x224, 1000 classes, batch 256 per GPU (BASELINE.json configs[1]/[2])",
-                       "global_batch": world * B, "seq_len": 197, "parallelism": f"dp{world}",
+            "config": {"workload": ("CLIP ViT-B/32 + 12x512 text transformer (ctx 77, vocab 49408), symmetric cross-entropy over the local batch, "
+                                    "256 image-text pairs per GPU (BASELINE.json configs[3])" if is_clip else
+                                    "ViT-B/16 classifier 224x224, 1000 classes, batch 256 per GPU (BASELINE.json configs[1]/[2])"),
+                       "global_batch": world * B, "seq_len": "50 / 77" if is_clip else 197, "parallelism": f"dp{world}",
                        "optimizer": "adam (fused arena kernel, inside the timed region)",
                        "cuda_graph": bool(use_graph),
                        "gradient_exchange": (None if world == 1 else ("one flat NCCL all-reduce after the graph (A/B mode)" if args.flat_allreduce else
@@ -576,6 +594,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="vit", choices=["vit", "clip"], help="vit: BASELINE.json configs[1]/[2] (the metric); clip: configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--flat-allreduce", action="store_true", help="N > 1 A/B mode: graph up to backward, then ONE all-reduce of the gradient arena + Adam")

@@ -60,6 +60,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_add_pos": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_add_pos_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_softmax_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P, _P]),
+    "b200_symmetric_xent_fwd_bwd": (c_int, [_P, _LL, _P, _P, _P, c_int, c_float, _P, _P]),
     "b200_adam_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P, _P]),
     "b200_adam_step_dev": (c_int, [_P, _P, _P, _P, _LL, _P, _P, c_int, _P]),
     "b200_cast_f32_to_bf16": (c_int, [_P, _P, _LL, _P]),

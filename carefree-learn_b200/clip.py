@@ -12,7 +12,7 @@ The reference defines no CLIP loss or training step; gradients fl
 from __future__ import annotations
 
 import math
-from typing import Any, Optional, Tuple
+from typing import Any, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -20,7 +20,7 @@ from torch import Tensor
 
 from . import ops
 from ._cabi import B200Error, call
-from .vit import TeTEncoderB200, ViTEncoderB200
+from .vit import ParamArena, TeTEncoderB200, ViTEncoderB200
 
 
 def l2_normalize(t: Tensor) -> Tensor:
@@ -143,6 +143,39 @@ class _MatmulNTFn(torch.autograd.Function):
         return (da if ctx.dtypes[0] == torch.bfloat16 else da.float()), (db if ctx.dtypes[1] == torch.bfloat16 else db.float())
 
 
+class _SymmetricXentFn(torch.autograd.Function):
+    """``(CE(L, arange) + CE(L^T, arange)) / 2`` on the bf16 logits [B, B] (fp32 maths, like autocast's cross_entropy)."""
+
+    @staticmethod
+    def forward(ctx: Any, logits: Tensor) -> Tensor:
+        if not logits.is_cuda or logits.dtype != torch.bfloat16 or logits.dim() != 2 or logits.shape[0] != logits.shape[1] or logits.stride(1) != 1:
+            raise B200Error("symmetric_cross_entropy expects the square bf16 logits CLIPB200.forward returns (CUDA; no CPU fallback)")
+        Bn = logits.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        ws = torch.empty(2 * Bn, dtype=torch.float32, device=logits.device)
+        call("b200_symmetric_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), loss.data_ptr(), None, ws.data_ptr(), Bn, 1.0, None, ops._stream())
+        ctx.save_for_backward(logits, ws)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: Tensor) -> Tuple[Any, ...]:
+        logits, ws = ctx.saved_tensors
+        Bn = logits.shape[0]
+        go = grad_out.reshape(1).contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.bfloat16, device=logits.device)
+        call("b200_symmetric_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), loss.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), Bn, 1.0,
+             go.data_ptr(), ops._stream())
+        return (dlogits,)
+
+
+def symmetric_cross_entropy(logits_per_image: Tensor) -> Tensor:
+    """The contrastive objective of CLIP on ``logits_per_image`` [B, B] (targets ``arange(B)`` in both directions).  The
+    reference ships no loss for its CLIP module (none in ``models/`` or ``losses/``); this is the standard
+    definition, restated for the parity tests in ``oracle/clip_oracle.py::symmetric_cross_entropy``."""
+    return _SymmetricXentFn.apply(logits_per_image)
+
+
 class CLIPB200(nn.Module):
     def __init__(self, img_size: int = 224, latent_dim: int = 512, *, use_vision: bool = True, in_channels: int = 3,
                  vision_latent_dim: int = 768, vision_patch_size: int = 32, vision_num_heads: int = 12, vision_num_layers: int = 12,
@@ -177,6 +210,42 @@ class CLIPB200(nn.Module):
         self.text_projection = nn.Linear(text_latent_dim, latent_dim)
         self.text_latent_dim, self.text_num_layers = text_latent_dim, text_num_layers
         self.reset_parameters()
+        # the parameters outside the towers live in a third flat arena (same machinery: one Adam launch, one all-reduce)
+        self._glue_keys = ["logit_scale", "token_embedding.weight", "text_projection.weight", "text_projection.bias"]
+        glue = {"logit_scale": self.logit_scale, "token_embedding.weight": self.token_embedding.weight,
+                "text_projection.weight": self.text_projection.weight, "text_projection.bias": self.text_projection.bias}
+        self.glue = ParamArena([(k, tuple(p.shape)) for k, p in glue.items()])
+        self.glue.attach(glue)
+        self.comm: Any = None  # dp.NativeComm when data parallel (dp.attach_native_reducers)
+
+    # ---- what the optimizer / the data-parallel layer iterate over --------------------------------------------------
+    def towers(self) -> List[nn.Module]:
+        return [self.vit, self.text_transformer]
+
+    def arenas(self) -> List[ParamArena]:
+        return [self.vit.arena, self.text_transformer.arena, self.glue]
+
+    def _collect_glue_grads(self) -> None:
+        """autograd hands the loose parameters' gradients over as separate tensors: move them into the glue arena."""
+        with torch.no_grad():
+            for k in self._glue_keys:
+                p = self.glue.params[k]
+                v = self.glue.g(k)
+                if p.grad is None:
+                    v.zero_()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def train_step(self, image: Tensor, text: Tensor) -> Tensor:
+        """forward + symmetric cross-entropy + backward (+ data parallel: the towers' bucket reducers run inside their
+        backward, the loose parameters are all-reduced here); returns the loss (fp32 scalar on the device)."""
+        loss = symmetric_cross_entropy(self.forward(image, text))
+        loss.backward()
+        self._collect_glue_grads()
+        if self.comm is not None and self.comm.world > 1:
+            self.comm.allreduce_(self.glue.grad, average=True)
+        return loss.detach()
 
     def reset_parameters(self) -> None:
         """clip.py:188-207: the text tower is re-initialised with CLIP's own standard deviations (the vision tower keeps the
@@ -199,6 +268,7 @@ class CLIPB200(nn.Module):
             nn.init.zeros_(self.text_projection.bias)
 
     def encode_image(self, image: Tensor) -> Tensor:  # clip.py:209-216
+        self.glue.ensure()
         return l2_normalize(self.vit(image))
 
     def encode_text(self, indices: Tensor, *, apply_pooling: bool = True, deterministic: bool = True, clip_skip: int = 0) -> Tensor:

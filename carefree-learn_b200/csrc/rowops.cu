@@ -557,6 +557,54 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const __nv_bfloat16* 
         }
     }
 }
+// ------------------------------------------------------------------------------------------------
+// symmetric (contrastive) cross entropy over a square bf16 logits matrix L [B, B] with targets arange(B):
+//   loss = (CE(L, arange) + CE(L^T, arange)) / 2        -- the usual CLIP objective.  The reference defines none
+//   (SURVEY.md 8d); the product-side definition follows oracle/clip_oracle.py::symmetric_cross_entropy: fp32 maths on the
+//   bf16 logits (autocast runs cross_entropy in fp32), and ONE rounding of the summed gradient to bf16.
+// stats kernel: warp w < B -> log-sum-exp of row w; warp w >= B -> of column w - B.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sym_xent_stats_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int B,
+                                                             float* __restrict__ lse /* [2B] */) {
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= 2 * B) return;
+    const bool col = w >= B;
+    const int k = col ? w - B : w;
+    const long long base = col ? k : static_cast<long long>(k) * ld;
+    const long long stride = col ? ld : 1;
+    float m = -INFINITY;
+    for (int j = lane; j < B; j += 32) m = fmaxf(m, __bfloat162float(logits[base + j * stride]));
+    m = warp_max(m);
+    float sacc = 0.f;
+    for (int j = lane; j < B; j += 32) sacc += expf(__bfloat162float(logits[base + j * stride]) - m);
+    sacc = warp_sum(sacc);
+    if (lane == 0) lse[w] = m + logf(sacc);
+}
+// loss (deterministic single-block sum) = mean_i( (lse_row[i] - L_ii) + (lse_col[i] - L_ii) ) / 2
+__global__ void sym_xent_loss_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int B, const float* __restrict__ lse,
+                                     float* __restrict__ loss) {
+    __shared__ float sred[8];
+    float sacc = 0.f;
+    for (int i = threadIdx.x; i < B; i += 256) sacc += lse[i] + lse[B + i] - 2.0f * __bfloat162float(logits[static_cast<long long>(i) * ld + i]);
+    sacc = warp_sum(sacc);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = sacc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int k = 0; k < 8; ++k) t += sred[k]; loss[0] = 0.5f * t / static_cast<float>(B); }
+}
+// dL_ij = bf16( sc / (2B) * ( softmax_row(i)_j + softmax_col(j)_i - 2 [i == j] ) )
+__global__ void sym_xent_grad_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int B, const float* __restrict__ lse,
+                                     __nv_bfloat16* __restrict__ dlogits, float gscale, const float* __restrict__ gscale_dev) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(B) * B) return;
+    const int i = static_cast<int>(idx / B), j = static_cast<int>(idx % B);
+    const float l = __bfloat162float(logits[static_cast<long long>(i) * ld + j]);
+    const float sc = gscale * (gscale_dev != nullptr ? gscale_dev[0] : 1.0f) * 0.5f / static_cast<float>(B);
+    float g = expf(l - lse[i]) + expf(l - lse[B + j]);
+    if (i == j) g -= 2.0f;
+    dlogits[static_cast<long long>(i) * ld + j] = __float2bfloat16_rn(g * sc);
+}
+
 __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
     __shared__ float sred[8];
     float s = 0.f;
@@ -839,6 +887,24 @@ extern "C" int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl,
     if (loss_mean != nullptr) {
         mean_kernel<<<1, 256, 0, stream>>>(loss_rows, B, loss_mean);
         rc = check_launch("loss_mean");
+    }
+    return rc;
+}
+
+extern "C" int b200_symmetric_xent_fwd_bwd(const void* logits_bf16, long long ldl, float* loss, void* dlogits_bf16, float* lse_ws, int B,
+                                           float grad_scale, const float* grad_scale_dev, cudaStream_t stream) {
+    if (B <= 0 || logits_bf16 == nullptr || loss == nullptr || lse_ws == nullptr) return set_error(B200_ERR_ARG, "symmetric_xent: bad arguments");
+    const __nv_bfloat16* lg = reinterpret_cast<const __nv_bfloat16*>(logits_bf16);
+    sym_xent_stats_kernel<<<(2 * B + 7) / 8, 256, 0, stream>>>(lg, ldl, B, lse_ws);
+    int rc = check_launch("symmetric_xent_stats");
+    if (rc) return rc;
+    sym_xent_loss_kernel<<<1, 256, 0, stream>>>(lg, ldl, B, lse_ws, loss);
+    if ((rc = check_launch("symmetric_xent_loss")) != 0) return rc;
+    if (dlogits_bf16 != nullptr) {
+        const long long n = static_cast<long long>(B) * B;
+        sym_xent_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(lg, ldl, B, lse_ws, reinterpret_cast<__nv_bfloat16*>(dlogits_bf16),
+                                                                                        grad_scale, grad_scale_dev);
+        rc = check_launch("symmetric_xent_grad");
     }
     return rc;
 }

@@ -211,6 +211,32 @@ def attach_native_reducer(module, comm: NativeComm) -> NativeBucketReducer:
     return red
 
 
+def _towers(module) -> List[Any]:
+    """The sub-modules that own a fused engine: the module itself (ViT encoder / classifier / text encoder) or CLIP's towers."""
+    if hasattr(module, "towers"):
+        return list(module.towers())
+    return [module]
+
+
+def attach_native_reducers(module, comm: NativeComm) -> List[NativeBucketReducer]:
+    """Bucket reducers on every tower of ``module``; a module with loose parameters outside the towers (CLIP: logit_scale,
+    token embedding, text projection) all-reduces them itself through ``module.comm`` at the end of its ``train_step``."""
+    reds = []
+    for t in _towers(module):
+        red = t.engine.reducer
+        if not isinstance(red, NativeBucketReducer) or red.comm is not comm:
+            red = attach_native_reducer(t, comm)
+        reds.append(red)
+    if hasattr(module, "towers"):
+        module.comm = comm
+    return reds
+
+
+def detach_reducers(module) -> None:
+    for t in _towers(module):
+        t.engine.reducer = None
+
+
 def allreduce_flat_cpu(grad: torch.Tensor, buckets: List[Tuple[int, int]], group=None) -> None:
     """Host-side (gloo) version of the bucket protocol, used by the world_size=2 CPU tests."""
     world = dist.get_world_size(group)
@@ -229,6 +255,8 @@ def attach_reducer(module, process_group=None) -> GradBucketReducer:
 
 
 def broadcast_parameters(module, src: int = 0, process_group=None) -> None:
-    """Identical replicas at start (what DDP's constructor does): one broadcast of the flat fp32 arena."""
-    module.arena.ensure()
-    dist.broadcast(module.arena.flat, src=src, group=process_group)
+    """Identical replicas at start (what DDP's constructor does): one broadcast per flat fp32 arena."""
+    arenas = list(module.arenas()) if hasattr(module, "arenas") else [module.arena]
+    for a in arenas:
+        a.ensure()
+        dist.broadcast(a.flat, src=src, group=process_group)

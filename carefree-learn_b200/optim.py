@@ -38,8 +38,22 @@ class ArenaAdam:
         self.hyper_dev: Optional[Tensor] = None
         self._hyper_host: Optional[Tensor] = None
         self._hyper_sent: Optional[tuple] = None
-        self.exp_avg: Optional[Tensor] = None
-        self.exp_avg_sq: Optional[Tensor] = None
+        # one (exp_avg, exp_avg_sq) pair per parameter arena: a ViT / classifier has one arena, CLIP three (vision tower,
+        # text tower, and the loose parameters: logit_scale, token embedding, text projection)
+        self.exp_avgs: List[Tensor] = []
+        self.exp_avg_sqs: List[Tensor] = []
+
+    def arenas(self) -> List[Any]:
+        m = self.module
+        return list(m.arenas()) if hasattr(m, "arenas") else [m.arena]
+
+    @property
+    def exp_avg(self) -> Optional[Tensor]:
+        return self.exp_avgs[0] if self.exp_avgs else None
+
+    @property
+    def exp_avg_sq(self) -> Optional[Tensor]:
+        return self.exp_avg_sqs[0] if self.exp_avg_sqs else None
 
     # ---- hyper-parameters ---------------------------------------------------------------------------------------
     @property
@@ -86,12 +100,13 @@ class ArenaAdam:
 
     # ---- state --------------------------------------------------------------------------------------------------
     def _state(self) -> None:
-        arena = self.module.arena
-        arena.ensure()
-        if self.exp_avg is None or self.exp_avg.device != arena.flat.device:
-            dev = arena.flat.device
-            self.exp_avg = torch.zeros_like(arena.flat)
-            self.exp_avg_sq = torch.zeros_like(arena.flat)
+        arenas = self.arenas()
+        for a in arenas:
+            a.ensure()
+        dev = arenas[0].flat.device
+        if not self.exp_avgs or self.exp_avgs[0].device != dev or len(self.exp_avgs) != len(arenas):
+            self.exp_avgs = [torch.zeros_like(a.flat) for a in arenas]
+            self.exp_avg_sqs = [torch.zeros_like(a.flat) for a in arenas]
             if self.capturable:
                 self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=dev)
                 self.hyper_dev = torch.zeros(6, dtype=torch.float32, device=dev)
@@ -100,25 +115,29 @@ class ArenaAdam:
         if self.capturable and not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
 
-    def step(self, lo: int = 0, hi: Optional[int] = None, *, increment: bool = True) -> None:
-        """Update arena elements [lo, hi) (default: everything).  ``increment=False``: a further slice of the SAME
-        optimisation step (per-bucket updates); the step counter advances once per step."""
+    def state_tensors(self) -> List[Tensor]:
+        """Everything a step mutates besides the gradients: parameters, moments, the device step counter."""
         self._state()
-        arena = self.module.arena
-        hi = arena.total if hi is None else hi
-        n = hi - lo
-        off = 4 * lo
-        if self.capturable:
-            call("b200_adam_step_dev", arena.flat.data_ptr() + off, arena.grad.data_ptr() + off, self.exp_avg.data_ptr() + off,
-                 self.exp_avg_sq.data_ptr() + off, n, self.hyper_dev.data_ptr(), self.step_dev.data_ptr(), int(increment), ops._stream())
-            return
-        if increment:
+        out = [a.flat for a in self.arenas()] + self.exp_avgs + self.exp_avg_sqs
+        if self.step_dev is not None:
+            out.append(self.step_dev)
+        return out
+
+    def step(self) -> None:
+        """One Adam update of every arena (one launch per arena; the step counter advances once)."""
+        self._state()
+        if not self.capturable:
             self.step_count += 1
-        lr, b1, b2, eps, wd, gs = self._hyper_tuple()
-        if gs != 1.0:
-            raise ValueError("grad_scale needs ArenaAdam(capturable=True)")
-        call("b200_adam_step", arena.flat.data_ptr() + off, arena.grad.data_ptr() + off, self.exp_avg.data_ptr() + off,
-             self.exp_avg_sq.data_ptr() + off, n, lr, b1, b2, eps, wd, self.step_count, None, ops._stream())
+            lr, b1, b2, eps, wd, gs = self._hyper_tuple()
+            if gs != 1.0:
+                raise ValueError("grad_scale needs ArenaAdam(capturable=True)")
+        for idx, a in enumerate(self.arenas()):
+            if self.capturable:
+                call("b200_adam_step_dev", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avgs[idx].data_ptr(), self.exp_avg_sqs[idx].data_ptr(),
+                     a.total, self.hyper_dev.data_ptr(), self.step_dev.data_ptr(), int(idx == 0), ops._stream())
+            else:
+                call("b200_adam_step", a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avgs[idx].data_ptr(), self.exp_avg_sqs[idx].data_ptr(),
+                     a.total, lr, b1, b2, eps, wd, self.step_count, None, ops._stream())
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if set_to_none:
@@ -128,7 +147,7 @@ class ArenaAdam:
     def state_dict(self) -> Dict[str, Any]:
         step = int(self.step_dev.item()) if self.step_dev is not None else self.step_count
         g = self.param_groups[0]
-        return {"step": step, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": g["lr"],
+        return {"step": step, "exp_avg": list(self.exp_avgs), "exp_avg_sq": list(self.exp_avg_sqs), "lr": g["lr"],
                 "betas": g["betas"], "eps": g["eps"], "weight_decay": g["weight_decay"]}
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
@@ -138,11 +157,14 @@ class ArenaAdam:
             if k in sd:
                 g[k] = tuple(sd[k]) if k == "betas" else float(sd[k])
         with torch.no_grad():
-            for name in ("exp_avg", "exp_avg_sq"):
-                if sd.get(name) is not None:
-                    getattr(self, name).copy_(sd[name].to(getattr(self, name).device))
-                else:
-                    getattr(self, name).zero_()
+            for name, mine in (("exp_avg", self.exp_avgs), ("exp_avg_sq", self.exp_avg_sqs)):
+                src = sd.get(name)
+                src = [src] if isinstance(src, Tensor) else src
+                for i, t in enumerate(mine):
+                    if src is not None and i < len(src) and src[i] is not None:
+                        t.copy_(src[i].to(t.device))
+                    else:
+                        t.zero_()
             self.step_count = int(sd.get("step", 0))
             if self.step_dev is not None:
                 self.step_dev.fill_(self.step_count)
@@ -151,51 +173,52 @@ class ArenaAdam:
 
 
 class GraphedTrainStep:
-    """Whole training step of a ``VanillaClassifierB200`` as one CUDA graph with static input / loss buffers.
+    """Whole training step of a B200 module (``VanillaClassifierB200`` or ``CLIPB200``) as one CUDA graph with static
+    input / loss buffers.
 
-    ``step(x, labels)`` copies the batch into the static buffers (device->device or pinned-host->device, on the
-    current stream), replays the graph and returns the static loss tensor (fp32 scalar, on the device).  The warm-up
-    runs needed before the capture leave NO trace: parameters, Adam moments and the step counter are restored.
+    ``step(*inputs)`` copies the batch into the static buffers (device->device or pinned-host->device, on the current
+    stream), replays the graph and returns the static loss tensor (fp32 scalar, on the device).  The warm-up runs needed
+    before the capture leave NO trace: parameters, Adam moments and the step counter are restored.
 
     Data parallel (``comm``: a ``dp.NativeComm``): the graph also holds the gradient exchange -- the model's bucket
-    reducer launches ``ncclAllReduce`` per transformer block on a forked stream as soon as that block's gradients are
-    complete -- and the Adam update behind the join."""
+    reducers launch ``ncclAllReduce`` per transformer block on a forked stream as soon as that block's gradients are
+    complete -- and the Adam update behind the join.  ``inputs``: the static input tensors (default: an image batch
+    [batch, C, S, S] fp32 and int64 labels [batch, 1] for the classifier)."""
 
-    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, comm: Any = None, flat: bool = False):
+    def __init__(self, model: Any, optimizer: ArenaAdam, batch: int, warmup: int = 2, comm: Any = None, flat: bool = False,
+                 inputs: Optional[List[Tensor]] = None):
         if not optimizer.capturable:
             raise ValueError("GraphedTrainStep needs ArenaAdam(capturable=True)")
         from . import _cabi, dp
 
         self.world = 1 if comm is None else comm.world
         self.comm = comm
-        # flat=True (A/B switch): the graph stops after backward; ONE all-reduce of the whole gradient arena and Adam are
+        # flat=True (A/B switch): the graph stops after backward; ONE all-reduce per gradient arena and Adam are
         # enqueued behind every replay -- the un-overlapped schedule round 1 measured
         self.flat = bool(flat) and self.world > 1
-        g = model.geo
-        model.arena.ensure()
-        dev = model.arena.flat.device
         self.model, self.optimizer = model, optimizer
-        if self.flat:
-            model.engine.reducer = None
-            self.reducer = None
-        elif self.world > 1:
-            red = model.engine.reducer
-            if not isinstance(red, dp.NativeBucketReducer) or red.comm is not comm:
-                red = dp.attach_native_reducer(model, comm)
-            self.reducer = red
+        arenas = optimizer.arenas()
+        for a in arenas:
+            a.ensure()
+        dev = arenas[0].flat.device
+        if self.flat or self.world == 1:
+            dp.detach_reducers(model)
+            if hasattr(model, "comm"):
+                model.comm = None
         else:
-            if model.engine.reducer is not None:
-                raise ValueError("single-process graph: detach the bucket reducer first (model.engine.reducer = None)")
-            self.reducer = None
-        self.x = torch.zeros((batch, g.cin, g.img, g.img), dtype=torch.float32, device=dev)
-        self.labels = torch.zeros((batch, 1), dtype=torch.int64, device=dev)
+            dp.attach_native_reducers(model, comm)
+        if inputs is None:
+            g = model.geo
+            inputs = [torch.zeros((batch, g.cin, g.img, g.img), dtype=torch.float32, device=dev),
+                      torch.zeros((batch, 1), dtype=torch.int64, device=dev)]
+        self.inputs = inputs
+        self.x, self.labels = inputs[0], inputs[-1]
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.bad_label = torch.zeros(1, dtype=torch.int32, device=dev)
-        optimizer._state()
-        arena = model.arena
         # warm up on a side stream (allocator pools, workspaces, lazy function attributes, NCCL connections), then
         # capture.  Warm-up steps run real Adam updates on an all-zero batch, so everything they touch is put back.
-        snap = [t.clone() for t in (arena.flat, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.step_dev)]
+        state = optimizer.state_tensors()
+        snap = [t.clone() for t in state]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -209,14 +232,15 @@ class GraphedTrainStep:
             self._eager()
         self.launches_per_replay = _cabi.launch_count() - n0  # b200 kernels inside one replay of the graph
         with torch.no_grad():
-            for dst, src in zip((arena.flat, optimizer.exp_avg, optimizer.exp_avg_sq, optimizer.step_dev), snap):
+            for dst, src in zip(state, snap):
                 dst.copy_(src)
-        optimizer.step_count = int(snap[3].item())
+        if optimizer.step_dev is not None:
+            optimizer.step_count = int(optimizer.step_dev.item())
         torch.cuda.synchronize()
 
     def _eager(self) -> None:
         self.optimizer.zero_grad()
-        loss = self.model.train_step(self.x, self.labels)  # DP: the reducer all-reduces bucket by bucket inside backward
+        loss = self.model.train_step(*self.inputs)  # DP: the reducers all-reduce bucket by bucket inside backward
         if not self.flat:
             self.optimizer.step()
         self.loss.copy_(loss)
@@ -224,13 +248,14 @@ class GraphedTrainStep:
         if flag is not None:
             self.bad_label.copy_(flag)
 
-    def step(self, x: Tensor, labels: Tensor) -> Tensor:
+    def step(self, *inputs: Tensor) -> Tensor:
         self.optimizer.sync_hyper()  # lr schedule: 24 bytes host->device when (and only when) a value changed
-        self.x.copy_(x, non_blocking=True)
-        self.labels.copy_(labels.reshape(self.labels.shape), non_blocking=True)
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
         self.graph.replay()
         if self.flat:
-            self.comm.allreduce_(self.model.arena.grad, average=True)
+            for a in self.optimizer.arenas():
+                self.comm.allreduce_(a.grad, average=True)
             self.optimizer.step()
         return self.loss
 

@@ -186,6 +186,12 @@ int b200_scatter_rows(const float* dout, const int* pos, float* dx, int B, int T
 int b200_softmax_xent_fwd_bwd(const void* logits_bf16, long long ldl, const long long* labels, float* loss_rows,
                               float* loss_mean, void* dlogits_bf16, int* bad_label_flag, int B, int C,
                               float grad_scale, const float* grad_scale_dev, cudaStream_t stream);
+/* Symmetric (contrastive) cross entropy of a square bf16 logits matrix L [B, B] (leading dimension ldl) with targets
+ * arange(B): loss[0] = (CE(L) + CE(L^T)) / 2, dlogits = bf16 of the fp32 gradient scaled by grad_scale (* grad_scale_dev[0]).
+ * The training objective of CLIP (cflearn/modules/multimodal/clip.py:209-256 produce L; the reference ships no loss for
+ * it, SURVEY.md 8d -- the definition is oracle/clip_oracle.py::symmetric_cross_entropy).  lse_ws: 2*B floats of scratch. */
+int b200_symmetric_xent_fwd_bwd(const void* logits_bf16, long long ldl, float* loss, void* dlogits_bf16, float* lse_ws, int B,
+                                float grad_scale, const float* grad_scale_dev, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimizer step on the flat fp32 arenas (torch.optim.Adam semantics without amsgrad; the reference's default

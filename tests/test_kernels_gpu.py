@@ -437,3 +437,25 @@ def test_layernorm_bwd_fp32_upstream(rows, dim):
     ops.layernorm_bwd(dy, x.detach(), g.detach(), mean, rstd, rows=rows, dim=dim, ld_x=dim, dres=None, dx_out=dx, ld_dx=dim,
                       dx_bf16=None, dgamma=dg, dbeta=db)
     assert _relerr(dx, x.grad) < 1e-5 and _relerr(dg, g.grad) < 1e-5 and _relerr(db, b.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B", [5, 64, 256])
+def test_symmetric_xent_matches_fp32_reference(B):
+    """CLIP's contrastive loss kernel: (CE(L) + CE(L^T)) / 2 on bf16 logits, fp32 maths, ONE bf16 rounding of the gradient."""
+    from cflearn_b200._cabi import call
+
+    g = torch.Generator().manual_seed(123)
+    ld = (B + 7) // 8 * 8
+    logits = torch.zeros(B, ld, dtype=torch.bfloat16, device=DEV)[:, :B]
+    logits.copy_((torch.randn(B, B, generator=g) * 4).to(DEV))
+    loss = torch.empty(1, device=DEV)
+    ws = torch.empty(2 * B, device=DEV)
+    dl = torch.zeros(B, ld, dtype=torch.bfloat16, device=DEV)[:, :B]
+    call("b200_symmetric_xent_fwd_bwd", logits.data_ptr(), logits.stride(0), loss.data_ptr(), dl.data_ptr(), ws.data_ptr(), B, 1.0, None, ops._stream())
+    torch.cuda.synchronize()
+    lf = logits.float().clone().requires_grad_(True)
+    tgt = torch.arange(B, device=DEV)
+    ref = 0.5 * (F.cross_entropy(lf, tgt) + F.cross_entropy(lf.t(), tgt))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    _assert_bf16_close(dl.contiguous(), lf.grad, "symmetric xent gradient")

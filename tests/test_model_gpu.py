@@ -418,3 +418,79 @@ def test_clip_forward_backward_parity(name, batch):
     seq = torch.randn(batch, ids.shape[1], 64, device=DEV)
     assert torch.equal(_ArgmaxPoolFn.apply(seq, ids), seq[torch.arange(batch, device=DEV), ids.argmax(-1)])
     print(f"{name}: logits vs eager {rel(logits, e_logits):.2e} (bf16 floor {floor:.2e})")
+
+
+@pytest.mark.parametrize("name,batch", [("clip_tiny", 6), ("clip", 16)])
+def test_clip_train_step_symmetric_cross_entropy(name, batch):
+    """The product-side CLIP step: ``CLIPB200.train_step`` = forward + symmetric cross-entropy + backward.
+    Loss and all 303 parameter gradients against the oracle's definition of the same step (``clip_oracle.forward`` +
+    ``symmetric_cross_entropy``) run eagerly on this GPU under bf16 autocast and in fp32; gradients land in the three
+    flat arenas the optimizer / the data-parallel reducer work on."""
+    import clip_oracle as co
+    from cflearn_b200.optim import ArenaAdam
+
+    cfg = co.clip_config(name)
+    sd = co.init_state_dict(cfg, seed=0)
+    x, ids = co.synthetic_batch(cfg, batch, seed=4)
+    x, ids = x.to(DEV), ids.to(DEV)
+    m = _clip_module(cfg, sd)
+    loss = m.train_step(x, ids)
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+
+    def oracle(autocast):
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in sdg.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            lg = co.forward(params, x, ids, cfg)
+            ls = co.symmetric_cross_entropy(lg)
+        ls.backward()
+        return ls.detach(), {k: v.grad for k, v in params.items()}
+
+    e_loss, e_grads = oracle(True)
+    f_loss, f_grads = oracle(False)
+    assert abs(loss.item() - f_loss.item()) < 1.5 * abs(e_loss.item() - f_loss.item()) + 2e-3 * max(1.0, abs(f_loss.item())), (loss.item(), e_loss.item(), f_loss.item())
+    assert set(grads) == set(e_grads)
+    for k in sorted(grads):
+        ours_vs_eager, ours_vs_fp32, eager_vs_fp32 = rel(grads[k], e_grads[k]), rel(grads[k], f_grads[k]), rel(e_grads[k], f_grads[k])
+        assert ours_vs_eager < VS_EAGER_FACTOR * eager_vs_fp32 + SLACK, f"{k}: ours vs eager {ours_vs_eager}, floor {eager_vs_fp32}"
+        assert ours_vs_fp32 < VS_FP32_FACTOR * eager_vs_fp32 + SLACK, (k, ours_vs_fp32, eager_vs_fp32)
+    # the loose parameters' gradients were moved into the glue arena (what Adam and the all-reduce see)
+    for k in ("logit_scale", "token_embedding.weight", "text_projection.weight", "text_projection.bias"):
+        assert torch.equal(m.glue.g(k), grads[k]) and m.glue.params[k].grad.data_ptr() == m.glue.g(k).data_ptr()
+    # one fused Adam step over the three arenas == torch.optim.Adam on the same gradients
+    ref_params = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    for rp, p in zip(ref_params, m.parameters()):
+        rp.grad = p.grad.clone()
+    torch.optim.Adam(ref_params, lr=1e-3).step()
+    ArenaAdam(m, lr=1e-3).step()
+    torch.cuda.synchronize()
+    for rp, p in zip(ref_params, m.parameters()):
+        assert torch.allclose(rp, p, rtol=1e-5, atol=1e-7)
+    print(f"{name}: loss ours {loss.item():.5f} eager {e_loss.item():.5f} fp32 {f_loss.item():.5f}")
+
+
+def test_clip_graphed_train_step_matches_eager_steps():
+    """The CUDA-graphed CLIP step (what `bench.py --config clip` times) reproduces eagerly launched steps."""
+    import clip_oracle as co
+    from cflearn_b200.optim import ArenaAdam, GraphedTrainStep
+
+    cfg = co.clip_config("clip_tiny")
+    sd = co.init_state_dict(cfg, seed=0)
+    batches = [co.synthetic_batch(cfg, 6, seed=10 + i) for i in range(3)]
+    eager, graphed = _clip_module(cfg, sd), _clip_module(cfg, sd)
+    opt_e = ArenaAdam(eager, lr=1e-3)
+    losses_e = []
+    for x, ids in batches:
+        opt_e.zero_grad()
+        losses_e.append(eager.train_step(x.to(DEV), ids.to(DEV)).item())
+        opt_e.step()
+    opt_g = ArenaAdam(graphed, lr=1e-3, capturable=True)
+    x0, i0 = batches[0]
+    gs = GraphedTrainStep(graphed, opt_g, 6, warmup=2, inputs=[torch.zeros_like(x0, device=DEV), torch.zeros_like(i0, device=DEV)])
+    losses_g = [gs.step(x.to(DEV), ids.to(DEV)).item() for x, ids in batches]
+    torch.cuda.synchronize()
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) < 1e-4 * max(1.0, abs(a)), (losses_e, losses_g)
+    for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=1e-6), k
