@@ -44,6 +44,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_colsum_finish2": (c_int, [_P, _LL, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, _P]),
     "b200_attention_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "b200_set_attention_fwd_version": (c_int, [c_int]),
+    "b200_set_attention_bwd_version": (c_int, [c_int]),
     "b200_attention_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P]),
     "b200_fcnn_step": (
         c_int,
@@ -95,6 +96,8 @@ def _load() -> None:
             fn.argtypes = args
         if os.environ.get("B200_ATTN_FWD", "") in ("1", "2"):  # A/B switch for profiling
             lib.b200_set_attention_fwd_version(int(os.environ["B200_ATTN_FWD"]))
+        if os.environ.get("B200_ATTN_BWD", "") in ("1", "2"):
+            lib.b200_set_attention_bwd_version(int(os.environ["B200_ATTN_BWD"]))
         if os.environ.get("B200_GEMM_MULTICAST", "") in ("0", "1", "2"):  # A/B/C switch for profiling; results are identical
             lib.b200_set_gemm_multicast(int(os.environ["B200_GEMM_MULTICAST"]))
         _lib = lib

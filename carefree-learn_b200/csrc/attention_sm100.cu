@@ -859,11 +859,413 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, version 2: persistent, transposed scores, P^T / dS^T operands in TENSOR MEMORY
+// ------------------------------------------------------------------------------------------------
+// Version 1 above spends ~33 k cycles per (batch, head) where the tensor + MUFU work is ~7 k: one CTA per item pays
+// launch + TMEM allocation + 128 KB of un-overlapped TMA loads, and inside the item S / dP -> softmax -> dV / dK / dQ is
+// one serial chain (all 512 TMEM columns taken, P and dS staged through shared memory).  Version 2:
+//   * ONE persistent CTA per SM walks over the items; every operand buffer (K|V per key tile, Q|dO per query tile) has
+//     its own full / empty barrier pair, so the next item's tiles stream in as soon as the current item has issued its
+//     last MMA on that buffer (K_0 / V_0 are free after the first key tile, ...): no load is ever exposed;
+//   * scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T (TMEM lane = key), in sub-tiles of 64 queries:
+//     a sub-tile's S^T | dP^T take 128 columns, so TWO of them fit beside the four 64-column accumulators
+//     (dK, dV, dQ_0, dQ_1 = 256 columns) and the tensor pipe works on sub-tile u+1 / u+2 while the compute warps are on u;
+//   * the compute warps (lane = key row, two threads per row) write P^T and dS^T back into their OWN S^T / dP^T columns as
+//     packed bf16 (tcgen05.st); dV += P^T dO and dK += dS^T Q read their A operand from tensor memory
+//     (tcgen05.mma [d], [a_tmem], b_desc), so P never touches shared memory and dS^T goes there only for dQ += dS K,
+//     where it is consumed MN-major (M = query) straight from the [key][query] tile the threads wrote;
+//   * 4 epilogue warps drain dK / dV after each key tile and dQ after each item (coalesced stores, column sums for the
+//     qkv-bias gradient) and, in their idle time, compute delta_i = sum_d dO[i,d] O[i,d] for the NEXT item.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = compute, 10..13 = epilogue.
+constexpr int B2_THREADS = 448;
+constexpr int B2_SQ = 0;           // 2 x 16 KB   query tiles
+constexpr int B2_SDO = 32768;      // 2 x 16 KB
+constexpr int B2_SK = 65536;       // 2 x 16 KB   key tiles
+constexpr int B2_SV = 98304;       // 2 x 16 KB
+constexpr int B2_SDS = 131072;     // 2 pair buffers x 2 blocks x 16 KB: dS^T [128 keys][64 queries] bf16, 128 B rows, swizzled
+constexpr int B2_STG = 196608;     // 4 x 4 KB    epilogue staging
+constexpr int B2_LSE = B2_STG + 16384;          // [2 items][256] floats (lse * log2 e; +inf for padded queries)
+constexpr int B2_DELTA = B2_LSE + 2048;         // [2 items][256]
+constexpr int B2_CSUM = B2_DELTA + 2048;        // 24 x 64 floats: column sums of dQ / dK / dV per (tile, lane quadrant)
+constexpr int B2_BAR = B2_CSUM + 24 * 64 * 4;
+constexpr int B2_SMEM = B2_BAR + 256 + 1024;
+constexpr uint32_t T2_BUF = 128;   // per S^T|dP^T buffer: S^T at +0, dP^T at +64
+constexpr uint32_t T2_DK = 256, T2_DV = 320, T2_DQ = 384;
+
+// staged rows -> global as in flush_rows64, plus the fp32 column sums of the bf16 values written (qkv-bias gradient)
+__device__ __forceinline__ void flush_rows64_colsum(const uint8_t* stage, __nv_bfloat16* g0, long long row_stride, int rows_valid, int lane,
+                                                    float* csum) {
+    __syncwarp();
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3);
+        const uint32_t ch = static_cast<uint32_t>(lane) & 7u;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (static_cast<uint32_t>(row) & 7u)) << 4));
+        if (row < rows_valid) {
+            *reinterpret_cast<uint4*>(g0 + row * row_stride + ch * 8) = val;
+            acc[0] += bf16lo(val.x); acc[1] += bf16hi(val.x); acc[2] += bf16lo(val.y); acc[3] += bf16hi(val.y);
+            acc[4] += bf16lo(val.z); acc[5] += bf16hi(val.z); acc[6] += bf16lo(val.w); acc[7] += bf16hi(val.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // lanes l, l^8, l^16, l^24 hold the same 8 columns of different rows
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    }
+    if (lane < 8) {
+        reinterpret_cast<float4*>(csum + lane * 8)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(csum + lane * 8)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                 const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
+                 const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_part,
+                 const AttnParams p, const int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* csum = reinterpret_cast<float*>(smem + B2_CSUM);
+    uint64_t* full_q = reinterpret_cast<uint64_t*>(smem + B2_BAR);  // [2] Q_mt | dO_mt loaded
+    uint64_t* empty_q = full_q + 2;                                 // [2] ... no longer read by any MMA
+    uint64_t* full_kv = full_q + 4;                                 // [2] K_kt | V_kt loaded
+    uint64_t* empty_kv = full_q + 6;
+    uint64_t* bar_sdp = full_q + 8;                                 // [2] S^T | dP^T of the buffer's sub-tile are in TMEM
+    uint64_t* bar_pds = full_q + 10;                                // [2] P^T | dS^T written (8 compute warps)
+    uint64_t* bar_dsfree = full_q + 12;                             // [2] dS^T pair buffer consumed by its dQ MMAs
+    uint64_t* bar_kv = full_q + 14;                                 // dK | dV of the key tile complete
+    uint64_t* bar_kvfree = full_q + 15;                             // ... and read out (4 epilogue warps)
+    uint64_t* bar_dq = full_q + 16;                                 // dQ of the item complete
+    uint64_t* bar_dqfree = full_q + 17;
+    uint64_t* bar_delta = full_q + 18;                              // [2] lse / delta of the item (parity buffer) in smem (4 epilogue warps)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(full_q + 20);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_kt = (p.T + 127) / 128;          // key tiles == query tiles (pairs of 64-query sub-tiles)
+    const int n_qs = (p.tp + 63) / 64;           // 64-query sub-tiles
+    const int U = n_kt * n_qs;                   // sub-iterations per item
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const long long D3 = 3ll * p.D;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_q[i], 1);
+            mbar_init(&empty_q[i], 1);
+            mbar_init(&full_kv[i], 1);
+            mbar_init(&empty_kv[i], 1);
+            mbar_init(&bar_sdp[i], 1);
+            mbar_init(&bar_pds[i], 8);
+            mbar_init(&bar_dsfree[i], 1);
+            mbar_init(&bar_delta[i], 4);
+        }
+        mbar_init(bar_kv, 1);
+        mbar_init(bar_kvfree, 4);
+        mbar_init(bar_dq, 1);
+        mbar_init(bar_dqfree, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            for (int it = 0; it < n_my; ++it) {
+                const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+                const int h = w % p.H, b = w / p.H;
+                const uint32_t par = static_cast<uint32_t>(it & 1);
+                for (int t = 0; t < n_kt; ++t) {  // (buffers are released in the order kv0, q0, kv1, q1: wait in that order)
+                    mbar_wait(&empty_kv[t], par ^ 1u);
+                    mbar_expect_tx(&full_kv[t], 2u * 16384u);
+                    tma_load_3d(smem + B2_SK + t * 16384, &tmQKV, &full_kv[t], p.D + h * 64, t * 128, b);
+                    tma_load_3d(smem + B2_SV + t * 16384, &tmQKV, &full_kv[t], 2 * p.D + h * 64, t * 128, b);
+                    mbar_wait(&empty_q[t], par ^ 1u);
+                    mbar_expect_tx(&full_q[t], 2u * 16384u);
+                    tma_load_3d(smem + B2_SQ + t * 16384, &tmQKV, &full_q[t], h * 64, t * 128, b);
+                    tma_load_3d(smem + B2_SDO + t * 16384, &tmDO, &full_q[t], h * 64, t * 128, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (elect_one()) {
+            const uint32_t idesc_ts = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A from TMEM (K-major), B MN-major
+            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major (smem), B MN-major
+            const int G = n_my * U;
+            auto issue_sdp = [&](int g) {
+                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
+                const uint32_t par = static_cast<uint32_t>(it & 1);
+                if (qs == 0) mbar_wait(&full_kv[kt], par);
+                if (kt == 0 && (qs & 1) == 0) mbar_wait(&full_q[mt], par);
+                tc_fence_after_sync();
+                const int nq = min(64, p.tp - qs * 64);
+                const uint32_t idesc_nn = make_idesc_bf16(128, static_cast<uint32_t>(nq), 0, 0);
+                const uint32_t k_base = smem_u32(smem + B2_SK + kt * 16384), v_base = smem_u32(smem + B2_SV + kt * 16384);
+                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t d = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(d, make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
+                              idesc_nn, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(d + 64, make_smem_desc(v_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
+                              idesc_nn, kk > 0 ? 1u : 0u);
+                umma_commit(&bar_sdp[g & 1]);
+            };
+            // S^T / dP^T run up to two sub-iterations ahead of the compute warps.  Across an item boundary that is only possible
+            // when the next item's first tiles can already be resident, i.e. when the current item released K_0|V_0 and
+            // Q_0|dO_0 at least two sub-iterations before its end (two key tiles and >= 3 query sub-tiles, e.g. T = 197);
+            // otherwise the look-ahead stops at the boundary -- waiting there for loads that need a LATER commit of this
+            // thread would deadlock.
+            const bool cross = (n_kt == 2 && n_qs >= 3);
+            int nxt = 0;
+            auto pump = [&](int g_cur) {
+                const int cur_item = g_cur < 0 ? 0 : g_cur / U;
+                const bool item_finished = g_cur >= 0 && (g_cur % U) == U - 1;
+                while (nxt < G && nxt <= g_cur + 2) {
+                    const int it2 = nxt / U;
+                    if (!cross && it2 > cur_item && !item_finished) break;
+                    if (!cross && it2 > cur_item + 1) break;
+                    issue_sdp(nxt);
+                    ++nxt;
+                }
+            };
+            pump(-1);
+            int pc = 0;   // dS^T pairs completed so far (pair buffer = pc & 1)
+            int kc = 0;   // key tiles completed so far
+            for (int g = 0; g < G; ++g) {
+                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
+                const int nq = min(64, p.tp - qs * 64);
+                const int nk = min(128, p.tp - kt * 128);
+                const uint32_t buf = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
+                mbar_wait(&bar_pds[g & 1], static_cast<uint32_t>((g >> 1) & 1));
+                if (qs == 0 && kc > 0) mbar_wait(bar_kvfree, static_cast<uint32_t>((kc - 1) & 1));  // dK / dV of the previous key tile read out
+                tc_fence_after_sync();
+                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
+                for (int kk = 0; kk < (nq >> 4); ++kk) {  // reduction over the queries of the sub-tile, 16 per step
+                    // every 16-query chunk was written back, packed to 8 columns, at the START of its own 16 fp32 columns
+                    const uint32_t acol = static_cast<uint32_t>(kk * 16);
+                    const uint32_t acc = (qs > 0 || kk > 0) ? 1u : 0u;
+                    umma_bf16_ts(tmem_base + T2_DV, buf + acol, make_smem_desc(do_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
+                    umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, make_smem_desc(q_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
+                }
+                const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
+                if (pair_done) {
+                    if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
+                    tc_fence_after_sync();
+                    const uint32_t ds_base = smem_u32(smem + B2_SDS + (pc & 1) * 32768);
+                    const uint32_t k_base = smem_u32(smem + B2_SK + kt * 16384);
+                    for (int kk = 0; kk < (nk >> 4); ++kk)  // reduction over the keys of the tile
+                        umma_bf16(tmem_base + T2_DQ + static_cast<uint32_t>(mt * 64), make_smem_desc(ds_base + kk * 2048, 16384, 1024, kSwz128),
+                                  make_smem_desc(k_base + kk * 2048, 0, 1024, kSwz128), idesc_dq, (kt > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&bar_dsfree[pc & 1]);
+                    ++pc;
+                    if (kt == n_kt - 1) umma_commit(&empty_q[mt]);  // last MMAs on Q_mt / dO_mt of this item
+                }
+                if (qs == n_qs - 1) {
+                    umma_commit(bar_kv);
+                    umma_commit(&empty_kv[kt]);
+                    ++kc;
+                    if (kt == n_kt - 1) umma_commit(bar_dq);
+                }
+                pump(g);
+            }
+        }
+    } else if (warp >= 10) {
+        // ===================================== epilogue warps =====================================
+        const uint32_t q = static_cast<uint32_t>(warp & 3);
+        const int et = (warp - 10) * 32 + lane;  // 0..127
+        uint8_t* stage = smem + B2_STG + (warp - 10) * 4096;
+        auto prepare = [&](int it) {  // lse (scaled) and delta of item `it` -> its parity buffers
+            const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int h = w % p.H, b = w / p.H;
+            float* lse_s = reinterpret_cast<float*>(smem + B2_LSE) + (it & 1) * 256;
+            float* delta_s = reinterpret_cast<float*>(smem + B2_DELTA) + (it & 1) * 256;
+            for (int i = et; i < 256; i += 128) {
+                float dl = 0.f, ls = INFINITY;  // padded query columns: exp2(s - inf) = 0 -> P = dS = 0 for free
+                if (i < p.T) {
+                    const uint4* po = reinterpret_cast<const uint4*>(o_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
+                    const uint4* pd = reinterpret_cast<const uint4*>(do_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint4 a = __ldg(po + k), gg = __ldg(pd + k);
+                        dl += bf16lo(a.x) * bf16lo(gg.x) + bf16hi(a.x) * bf16hi(gg.x) + bf16lo(a.y) * bf16lo(gg.y) + bf16hi(a.y) * bf16hi(gg.y) +
+                              bf16lo(a.z) * bf16lo(gg.z) + bf16hi(a.z) * bf16hi(gg.z) + bf16lo(a.w) * bf16lo(gg.w) + bf16hi(a.w) * bf16hi(gg.w);
+                    }
+                    ls = __ldg(lse_in + (static_cast<long long>(b) * p.H + h) * p.T + i) * kLog2e;
+                }
+                lse_s[i] = ls;
+                delta_s[i] = dl;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_delta[it & 1]);
+        };
+        if (n_my > 0) prepare(0);
+        int kc = 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int h = w % p.H, b = w / p.H;
+            for (int k = et; k < 24 * 64; k += 128) csum[k] = 0.f;  // (slots of absent tiles stay zero)
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (it + 1 < n_my) prepare(it + 1);  // the other parity buffer: its previous user (item it-1) has been read out completely
+            for (int kt = 0; kt < n_kt; ++kt, ++kc) {
+                mbar_wait(bar_kv, static_cast<uint32_t>(kc & 1));
+                tc_fence_after_sync();
+                const int key0 = kt * 128 + static_cast<int>(q) * 32;
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16);
+                const bool live = key0 < p.T;
+                __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + key0) * D3 + h * 64;
+                if (live) {
+                    stage_rows64(stage, taddr + T2_DK, p.scale, lane);
+                    flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
+                    stage_rows64(stage, taddr + T2_DV, 1.0f, lane);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_kvfree);
+                if (live) flush_rows64_colsum(stage, g0 + 2 * p.D, D3, p.T - key0, lane, csum + (16 + kt * 4 + static_cast<int>(q)) * 64);
+            }
+            mbar_wait(bar_dq, static_cast<uint32_t>(it & 1));
+            tc_fence_after_sync();
+            for (int mt = 0; mt < n_kt; ++mt) {
+                const int row0 = mt * 128 + static_cast<int>(q) * 32;
+                if (row0 < p.T) {
+                    stage_rows64(stage, tmem_base + ((q * 32u) << 16) + T2_DQ + static_cast<uint32_t>(mt * 64), p.scale, lane);
+                    if (mt == n_kt - 1) {  // everything of this item has left tensor memory
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_dqfree);
+                    }
+                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + row0) * D3 + h * 64, D3, p.T - row0, lane,
+                                        csum + (mt * 4 + static_cast<int>(q)) * 64);
+                } else if (mt == n_kt - 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_dqfree);
+                }
+            }
+            if (dbias_part != nullptr) {
+                // per-(batch, head) column sums of dq | dk | dv in a fixed order: the qkv-bias gradient is their sum over the batch
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                for (int idx = et; idx < 192; idx += 128) {
+                    const int sec = idx >> 6, c = idx & 63;
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t += csum[(sec * 8 + k) * 64 + c];
+                    dbias_part[static_cast<long long>(b) * D3 + sec * p.D + h * 64 + c] = t;
+                }
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // csum is zeroed again at the top
+        }
+    } else {
+        // ===================================== compute warps ======================================
+        const uint32_t q = static_cast<uint32_t>(warp & 3);
+        const int hf = (warp - 2) >> 2;                  // which half of the sub-tile's query columns this thread owns
+        const int r = static_cast<int>(q) * 32 + lane;   // key row inside the key tile == TMEM lane
+        const uint32_t rsw = static_cast<uint32_t>(r) & 7u;
+        const float sl2 = p.scale * kLog2e;
+        const int G = n_my * U;
+        int pc = 0;
+        for (int g = 0; g < G; ++g) {
+            const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs;
+            const int nq = min(64, p.tp - qs * 64);
+            const int nk = min(128, p.tp - kt * 128);
+            const int nch = nq >> 4;                             // 16-column chunks in this sub-tile (1..4)
+            const int cb = hf ? (nch + 1) >> 1 : 0;              // this thread's chunks [cb, ce)
+            const int ce = hf ? nch : (nch + 1) >> 1;
+            const bool dead = static_cast<int>(q) * 32 >= nk;    // all 32 key rows of this warp lie outside the (padded) key tile
+            const int j = kt * 128 + r;                          // key index
+            const float* lse_s = reinterpret_cast<const float*>(smem + B2_LSE) + (it & 1) * 256;
+            const float* delta_s = reinterpret_cast<const float*>(smem + B2_DELTA) + (it & 1) * 256;
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(g & 1) * T2_BUF;
+            uint8_t* blk = smem + B2_SDS + (pc & 1) * 32768 + (qs & 1) * 16384 + r * 128;
+            if (u == 0) mbar_wait(&bar_delta[it & 1], static_cast<uint32_t>((it >> 1) & 1));
+            if ((qs & 1) == 0 && pc >= 2) mbar_wait(&bar_dsfree[pc & 1], static_cast<uint32_t>(((pc >> 1) - 1) & 1));  // pair buffer consumed by its dQ MMAs
+            mbar_wait(&bar_sdp[g & 1], static_cast<uint32_t>((g >> 1) & 1));
+            tc_fence_after_sync();
+            if (!dead) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = cb + cc;
+                    if (c < ce) {  // warp-uniform
+                        uint32_t sv[16], dv[16];
+                        // this thread's columns: chunk c of the sub-tile lives at S^T / dP^T column c * 16
+                        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), sv);
+                        tmem_ld_32x32b_x16(taddr + 64 + static_cast<uint32_t>(c * 16), dv);
+                        const int i0 = qs * 64 + c * 16;  // first query of the chunk
+                        float ls[16], dl[16];
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 a = *reinterpret_cast<const float4*>(lse_s + i0 + k4 * 4);
+                            const float4 d4 = *reinterpret_cast<const float4*>(delta_s + i0 + k4 * 4);
+                            ls[k4 * 4 + 0] = a.x; ls[k4 * 4 + 1] = a.y; ls[k4 * 4 + 2] = a.z; ls[k4 * 4 + 3] = a.w;
+                            dl[k4 * 4 + 0] = d4.x; dl[k4 * 4 + 1] = d4.y; dl[k4 * 4 + 2] = d4.z; dl[k4 * 4 + 3] = d4.w;
+                        }
+                        tmem_ld_wait();
+                        float pv[16], ds[16];
+                        const bool keyok = j < p.T;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
+                            const bool ok = keyok && (!p.causal || j <= i0 + jj);
+                            pv[jj] = ok ? e : 0.f;
+                            ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - dl[jj]) : 0.f;
+                        }
+                        uint32_t pk[8], dk[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
+                            dk[jj] = pack_bf16x2(ds[2 * jj], ds[2 * jj + 1]);
+                        }
+                        // packed values over the first 8 of the chunk's OWN 16 columns: no other thread's unread S^T / dP^T is touched
+                        const uint32_t ocol = static_cast<uint32_t>(c * 16);
+                        tmem_st_32x32b_x8(taddr + ocol, pk);
+                        tmem_st_32x32b_x8(taddr + 64 + ocol, dk);
+                        // dS^T[key r][queries i0 .. i0+16) -> 32 bytes of the [key][query] tile (swizzled 16-byte chunks)
+                        const uint32_t c16 = static_cast<uint32_t>(c * 2);
+                        *reinterpret_cast<uint4*>(blk + ((c16 ^ rsw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                        *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ rsw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+                    }
+                }
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_pds[g & 1]);
+            if ((qs & 1) == 1 || qs == n_qs - 1) ++pc;
+        }
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 static int g_attn_fwd_version = 2;
+static int g_attn_bwd_version = 2;
 
 static int attn_check(int B, int T, int H, int Dh) {
     if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");
@@ -937,13 +1339,29 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     const int dev = current_device_slot();
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
         configured[dev] = true;
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
-    attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
-                                                            reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
-                                                            reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
+    if (g_attn_bwd_version == 1) {
+        attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+                                                                reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
+                                                                reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
+    } else {
+        const int n_items = B * H;
+        const int grid = n_items < num_sms() ? n_items : num_sms();
+        attn_bwd2_kernel<<<grid, B2_THREADS, B2_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+                                                                reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
+                                                                reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p, n_items);
+    }
     return check_launch("attention_bwd");
+}
+
+// 2 (default): persistent backward with transposed scores and P^T / dS^T operands in tensor memory; 1: the round-1 kernel
+extern "C" int b200_set_attention_bwd_version(int version) {
+    const int old = g_attn_bwd_version;
+    g_attn_bwd_version = version == 1 ? 1 : 2;
+    return old;
 }

@@ -127,6 +127,8 @@ int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, 
 /* forward kernel version: 2 (default) = persistent, warp-specialised, probabilities kept in tensor memory; 1 = the
  * round-1 kernel (one CTA per query tile).  Returns the previous setting.  For A/B timing; results agree to fp32 rounding. */
 int b200_set_attention_fwd_version(int version);
+/* same for the backward kernel: 2 (default) = persistent, transposed scores, P^T / dS^T operands in tensor memory; 1 = round 1 */
+int b200_set_attention_bwd_version(int version);
 /* dbias_part (optional, f32 [B, 3*H*Dh]): per-image column sums of the bf16 dqkv rows written; summed over the batch
  * (b200_colsum_finish, nparts = B) they are the gradient of the packed qkv bias (attentions.py:112-119). */
 int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,

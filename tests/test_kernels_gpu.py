@@ -362,8 +362,29 @@ def _attention_fwd_case(B, T, H, causal):
     assert _relerr(out, sdpa) < 5e-3
 
 
-@pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False)])
-def test_attention_bwd(B, T, H, causal):
+@pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False), (2, 130, 2, False), (2, 16, 1, True)])
+@pytest.mark.parametrize("version", [2, 1])
+def test_attention_bwd(B, T, H, causal, version):
+    """version 2: persistent kernel, transposed scores, P^T / dS^T operands in tensor memory (default); version 1: round 1."""
+    from cflearn_b200 import _cabi
+
+    prev = _cabi.lib().b200_set_attention_bwd_version(version)
+    try:
+        _attention_bwd_case(B, T, H, causal)
+    finally:
+        _cabi.lib().b200_set_attention_bwd_version(prev)
+
+
+def test_attention_bwd_many_items_per_cta():
+    """More (batch, head) items than SMs: operand buffers, TMEM buffers, dS^T pair buffers and the lse / delta parity
+    buffers are all recycled several times per persistent CTA (with and without the cross-item look-ahead)."""
+    _attention_bwd_case(40, 197, 12, False)
+    _attention_bwd_case(64, 77, 8, True)
+    _attention_bwd_case(37, 50, 12, False)
+    _attention_bwd_case(30, 130, 6, False)
+
+
+def _attention_bwd_case(B, T, H, causal):
     D = H * 64
     qkv = _rand_bf16(B * T, 3 * D, seed=81)
     dout = _rand_bf16(B * T, D, seed=82)
