@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p, POINTER
 from typing import Any, Callable, Dict, List, Optional
 
 LIB_NAME = "libb200_cflearn.so"
@@ -52,6 +52,7 @@ SIGNATURES: Dict[str, Any] = {
          POINTER(c_int), _P],
     ),
     "b200_patch_im2col": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_patch_im2col_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_double, POINTER(c_double), POINTER(c_double), _P]),
     "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_embedding_fwd": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P]),

@@ -376,6 +376,58 @@ __global__ void patch_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* 
     reinterpret_cast<uint4*>(dst)[1] = o1;
 }
 
+// The same gather straight from the RAW batch: uint8 [B, S, S, C] (HWC, what the reference's loader holds before its runtime
+// blocks) -> normalise -> bf16 im2col matrix.  Replaces, per step, the numpy passes static_normalize (x.astype(float64) /
+// division, cflearn/data/blocks/cv/normalize.py:11-24), imagenet / affine normalisation ((x - mean) / std in float64,
+// :27-67), hwc_to_chw (hwc_to_chw.py:9-15), the float32 tensor conversion + host->device copy of TensorBatcher
+// (cflearn/data/utils.py:255-283) and autocast's bf16 cast of the conv input: the GPU receives 1 byte per value instead
+// of 4, and the 154 MB fp32 image tensor is never materialised.  Arithmetic follows the reference's rounding chain:
+// float64 -> float32 -> bf16.  thread = (b, y, x16): 16 consecutive pixels (16 * C bytes) -> 16 k of one patch row per channel.
+struct NormParams {
+    double division;
+    double mean[4];
+    double stdv[4];
+};
+template <int C>
+__global__ void patch_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ cols, int B, int img, int P,
+                                       const NormParams np_) {
+    const int segs = img / 16;
+    const long long total = static_cast<long long>(B) * img * segs;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x16 = static_cast<int>(i % segs);
+    const long long r = i / segs;
+    const int y = static_cast<int>(r % img);
+    const int b = static_cast<int>(r / img);
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * img + y) * img + x16 * 16) * C);
+    uint32_t w[4 * C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const uint4 t = __ldg(src + k);
+        w[4 * k + 0] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+    }
+    const int side = img / P;
+    const int py = y / P, ky = y % P;
+    const int px = (x16 * 16) / P, kx0 = (x16 * 16) % P;
+    const long long row = (static_cast<long long>(b) * side + py) * side + px;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int byte = k * C + c;  // pixel k, channel c inside the 16 * C bytes
+            const double raw = static_cast<double>((w[byte >> 2] >> ((byte & 3) * 8)) & 0xffu);
+            v[k] = static_cast<float>((raw / np_.division - np_.mean[c]) / np_.stdv[c]);
+        }
+        __nv_bfloat16* dst = cols + row * (static_cast<long long>(C) * P * P) + (static_cast<long long>(c) * P + ky) * P + kx0;
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+        reinterpret_cast<uint4*>(dst)[0] = o0;
+        reinterpret_cast<uint4*>(dst)[1] = o1;
+    }
+}
+
 // net[b, t, d..d+7] = (t == 0 ? cls : float(patch[b*np + t-1])) + pos[t]
 __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ net, int B, int np, int D) {
@@ -813,6 +865,32 @@ extern "C" int b200_patch_im2col(const float* x, void* cols_bf16, int B, int C, 
     const long long total = static_cast<long long>(B) * C * img * (img / 16);
     patch_im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(cols_bf16), B, C, img, patch);
     return check_launch("patch_im2col");
+}
+
+extern "C" int b200_patch_im2col_u8(const void* x_u8_hwc, void* cols_bf16, int B, int C, int img, int patch, double division,
+                                    const double* mean_host, const double* std_host, cudaStream_t stream) {
+    if (B <= 0 || img <= 0 || patch <= 0 || patch % 16 != 0 || img % patch != 0) return set_error(B200_ERR_ARG, "patch_im2col_u8: need patch % 16 == 0 and img % patch == 0");
+    if (C < 1 || C > 4) return set_error(B200_ERR_ARG, "patch_im2col_u8: 1 <= channels <= 4");
+    if (division == 0.0) return set_error(B200_ERR_ARG, "patch_im2col_u8: division == 0");
+    if ((reinterpret_cast<uintptr_t>(x_u8_hwc) & 15u) != 0) return set_error(B200_ERR_ALIGN, "patch_im2col_u8: input not 16-byte aligned");
+    NormParams np_;
+    np_.division = division;
+    for (int c = 0; c < 4; ++c) {
+        np_.mean[c] = (mean_host != nullptr && c < C) ? mean_host[c] : 0.0;
+        np_.stdv[c] = (std_host != nullptr && c < C) ? std_host[c] : 1.0;
+        if (np_.stdv[c] == 0.0) return set_error(B200_ERR_ARG, "patch_im2col_u8: std == 0");
+    }
+    const long long total = static_cast<long long>(B) * img * (img / 16);
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    const uint8_t* x = reinterpret_cast<const uint8_t*>(x_u8_hwc);
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(cols_bf16);
+    switch (C) {
+        case 1: patch_im2col_u8_kernel<1><<<blocks, 256, 0, stream>>>(x, cols, B, img, patch, np_); break;
+        case 2: patch_im2col_u8_kernel<2><<<blocks, 256, 0, stream>>>(x, cols, B, img, patch, np_); break;
+        case 3: patch_im2col_u8_kernel<3><<<blocks, 256, 0, stream>>>(x, cols, B, img, patch, np_); break;
+        default: patch_im2col_u8_kernel<4><<<blocks, 256, 0, stream>>>(x, cols, B, img, patch, np_); break;
+    }
+    return check_launch("patch_im2col_u8");
 }
 
 extern "C" int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,

@@ -235,6 +235,21 @@ def patch_im2col(x: Tensor, patch: int) -> Tensor:
     return cols
 
 
+def patch_im2col_u8(x: Tensor, patch: int, division: float = 255.0, mean=None, std=None) -> Tensor:
+    """uint8 [B, S, S, C] (HWC) -> normalised bf16 im2col matrix: the reference's host-side input pipeline fused into the stem."""
+    _need_cuda(x)
+    if x.dtype != torch.uint8 or x.dim() != 4 or not x.is_contiguous() or x.shape[1] != x.shape[2]:
+        raise B200Error("patch_im2col_u8: need contiguous uint8 [B, S, S, C]")
+    B, S, _, C = x.shape
+    side = S // patch
+    cols = torch.empty((B * side * side, C * patch * patch), dtype=torch.bfloat16, device=x.device)
+    dbl = ctypes.c_double * C
+    m = dbl(*[float(v) for v in mean]) if mean is not None else None
+    sd = dbl(*[float(v) for v in std]) if std is not None else None
+    call("b200_patch_im2col_u8", x.data_ptr(), cols.data_ptr(), B, C, S, patch, float(division), m, sd, _stream())
+    return cols
+
+
 def add_pos(x: Tensor, pos: Tensor, B: int, T: int, D: int) -> Tensor:
     """net[b, t, :] = x[b, t, :] + pos[t, :] (fp32): the text tower's input stage."""
     _need_cuda(x, pos)

@@ -236,6 +236,9 @@ class ViTEngine:
         self.geo = geo
         self.arena = arena
         self.reducer = None  # set by dp.attach_reducer / dp.attach_native_reducer
+        # uint8 [B, S, S, C] inputs: {"division": 255.0, "mean": [...], "std": [...]} = the reference's static_normalize +
+        # imagenet / affine normalisation blocks (data/blocks/cv/normalize.py); None: division by 255 only
+        self.input_pipeline: Optional[Dict[str, Any]] = None
         self.shrink_next = 0  # SMs to leave free for an in-flight bucket all-reduce when launching the next GEMM (dp.py)
         self.d_input: Optional[Tensor] = None  # token mode: gradient w.r.t. the embedded input of the last backward
         # B200_SIDE_COLSUM=1 puts the HBM-bound bias-gradient column sums on a side stream (a parallel branch of the
@@ -266,7 +269,11 @@ class ViTEngine:
         B, T, D = x.shape[0], g.T, g.D
         if g.tokens:  # TeTEncoder.forward -> pre_process (api.py:419-438 without head token): x + pos
             return None, ops.add_pos(x, A.p("encoder.pos_encoding.pos_encoding"), B, T, D).view(B * T, D)
-        cols = ops.patch_im2col(x, g.patch)
+        if x.dtype == torch.uint8:  # raw HWC batch: the host-side normalise / transpose / float32 / H2D chain fused into the gather
+            pipe = self.input_pipeline or {}
+            cols = ops.patch_im2col_u8(x, g.patch, pipe.get("division", 255.0), pipe.get("mean"), pipe.get("std"))
+        else:
+            cols = ops.patch_im2col(x, g.patch)
         patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
                          bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
         net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(B * T, D)
@@ -349,9 +356,12 @@ class ViTEngine:
         if g.tokens:
             if x.dim() != 3 or x.shape[1] != g.T or x.shape[2] != g.D:
                 raise ValueError(f"expected embedded tokens [B, {g.T}, {g.D}], got {tuple(x.shape)}")
+        elif x.dtype == torch.uint8:
+            if x.dim() != 4 or x.shape[3] != g.cin or x.shape[1] != g.img or x.shape[2] != g.img:
+                raise ValueError(f"expected raw uint8 input [B, {g.img}, {g.img}, {g.cin}] (HWC), got {tuple(x.shape)}")
         elif x.dim() != 4 or x.shape[1] != g.cin or x.shape[2] != g.img or x.shape[3] != g.img:
             raise ValueError(f"expected input [B, {g.cin}, {g.img}, {g.img}], got {tuple(x.shape)}")
-        x = x.contiguous().float()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
         A.refresh_bf16()
         B, T, D, M = x.shape[0], g.T, g.D, x.shape[0] * g.T
         sv = _Saved()
@@ -674,6 +684,13 @@ class ViTEncoderB200(nn.Module):
     def encode(self, net: Tensor) -> Tensor:  # IEncoder.encode, cv/common.py:42-50
         return self.forward(net)
 
+    def set_input_pipeline(self, *, division: float = 255.0, mean: Any = None, std: Any = None) -> None:
+        """Accept RAW uint8 [B, S, S, C] batches: ``((x / division) - mean) / std`` (float64 -> float32 -> bf16, the reference's
+        static_normalize + imagenet_normalize / affine_normalize + hwc_to_chw runtime blocks) is evaluated inside the
+        patch gather on the GPU.  Float [B, C, S, S] inputs keep working unchanged."""
+        self.engine.input_pipeline = dict(division=float(division), mean=None if mean is None else [float(v) for v in mean],
+                                          std=None if std is None else [float(v) for v in std])
+
 
 class _TokenEncoderFn(torch.autograd.Function):
     @staticmethod
@@ -814,6 +831,9 @@ class VanillaClassifierB200(nn.Module):
     def named_arena_parameters(self):
         """(arena key, parameter): ``ViTEncoder`` keys + ``head.linear.*`` -- the names ``oracle/vit_oracle.py`` uses."""
         return self.encoder.named_arena_parameters()
+
+    def set_input_pipeline(self, **kw: Any) -> None:
+        self.encoder.set_input_pipeline(**kw)
 
     def _accept_bare_encoder_keys(self, state_dict: Dict[str, Tensor], prefix: str, *args: Any) -> None:
         enc = set(self.encoder_keys)

@@ -156,6 +156,13 @@ int b200_fcnn_step(const float* x, const float* y, const float* dpred, const flo
  *   assemble_bwd: dpatch bf16 [B*np, D] = bf16(dnet[:,1:,:]); dpos f32 [1+np, D] = sum_b dnet; dcls f32 [D]
  * --------------------------------------------------------------------------------------------------------- */
 int b200_patch_im2col(const float* x, void* cols_bf16, int B, int C, int img, int patch, cudaStream_t stream);
+/* The same matrix straight from the RAW batch: x = uint8 [B, img, img, C] (HWC, C <= 4), value = ((x / division) - mean[c])
+ * / std[c] evaluated in float64, rounded to float32, then to bf16 -- the reference's rounding chain.  Replaces the host-side
+ * runtime blocks static_normalize / imagenet_normalize / hwc_to_chw (cflearn/data/blocks/cv/normalize.py:11-67,
+ * hwc_to_chw.py:9-15), TensorBatcher's float32 conversion + host->device copy of 4 bytes per value
+ * (cflearn/data/utils.py:255-283) and autocast's bf16 cast.  mean / std: HOST pointers to C doubles (NULL: 0 / 1). */
+int b200_patch_im2col_u8(const void* x_u8_hwc, void* cols_bf16, int B, int C, int img, int patch, double division,
+                         const double* mean_host, const double* std_host, cudaStream_t stream);
 int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,
                          int D, cudaStream_t stream);
 int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, float* dcls, int B, int np, int D,

@@ -1,12 +1,16 @@
 """GPU parity tests of every C-ABI kernel against plain PyTorch references of the same op (fp32 math,
 bf16 rounding at the same points the reference's autocast path rounds).  Run on the B200 box: pytest -m gpu."""
 import math
+import os
+import sys
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-import cflearn_b200  # noqa: F401  (registers the package)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import cflearn_b200  # noqa: F401,E402  (registers the package)
 from cflearn_b200 import ops
 
 pytestmark = pytest.mark.gpu
@@ -480,3 +484,22 @@ def test_symmetric_xent_matches_fp32_reference(B):
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
     _assert_bf16_close(dl.contiguous(), lf.grad, "symmetric xent gradient")
+
+
+@pytest.mark.parametrize("B,C,S,P,norm", [(3, 3, 224, 16, True), (2, 3, 224, 32, False), (2, 1, 64, 16, True), (2, 4, 32, 16, True)])
+def test_patch_im2col_u8_fuses_the_input_pipeline_bit_exactly(B, C, S, P, norm):
+    """raw uint8 HWC batch -> normalised bf16 im2col matrix in one kernel == the reference's host-side blocks
+    (oracle/input_oracle.py: float64 normalise, hwc_to_chw, float32) followed by the fp32 im2col kernel.  Bit-exact: every
+    rounding point (float64 -> float32 -> bf16) is reproduced and the rest is an integer-indexed copy."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import input_oracle as io
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, (B, S, S, C), dtype=torch.uint8, generator=g)
+    mean = [0.485, 0.456, 0.406, 0.5][:C] if norm else None
+    std = [0.229, 0.224, 0.225, 0.25][:C] if norm else None
+    ref = io.input_pipeline(x.numpy(), 255.0, mean, std).to(DEV)           # float32 [B, C, S, S], what the reference feeds the model
+    want = ops.patch_im2col(ref.contiguous(), P)                           # (itself exact vs F.unfold: test_patch_glue)
+    got = ops.patch_im2col_u8(x.to(DEV), P, 255.0, mean, std)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)

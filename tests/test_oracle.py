@@ -213,3 +213,23 @@ def test_unet_live_pin_against_reference():
 
     make_golden_unet.pin("unet_tiny", 2, 8, 3, False)
     make_golden_unet.pin("unet_tiny", 2, 8, 3, True)
+
+
+def test_input_pipeline_oracle_known_values():
+    """oracle/input_oracle.py: static_normalize + imagenet_normalize + hwc_to_chw on hand-computed pixels."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import input_oracle as io
+
+    x = np.zeros((1, 2, 2, 3), dtype=np.uint8)
+    x[0, 0, 0] = (255, 0, 128)
+    x[0, 1, 1] = (51, 102, 204)
+    out = io.input_pipeline(x, 255.0, io.IMAGENET_MEAN, io.IMAGENET_STD)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (1, 3, 2, 2)
+    want = torch.tensor([(1.0 - 0.485) / 0.229, (0.0 - 0.456) / 0.224, (128 / 255 - 0.406) / 0.225], dtype=torch.float64).float()
+    assert torch.equal(out[0, :, 0, 0], want)
+    want2 = torch.tensor([(0.2 - 0.485) / 0.229, (0.4 - 0.456) / 0.224, (0.8 - 0.406) / 0.225], dtype=torch.float64).float()
+    assert torch.equal(out[0, :, 1, 1], want2)
+    plain = io.input_pipeline(x)  # division only
+    assert torch.equal(plain[0, :, 0, 0], torch.tensor([1.0, 0.0, 128 / 255], dtype=torch.float64).float())
