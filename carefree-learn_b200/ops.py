@@ -308,3 +308,38 @@ def cast_bf16(src: Tensor, dst: Optional[Tensor] = None) -> Tensor:
 def fill_f32(dst: Tensor, value: float) -> Tensor:
     call("b200_fill_f32", dst.data_ptr(), float(value), dst.numel(), _stream())
     return dst
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GroupNorm(32) + SiLU on channels-last activations (SD-v1.5 UNet)
+# ----------------------------------------------------------------------------------------------------------------
+def groupnorm_silu_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, silu: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """x: bf16 [B, HW, C] (channels last).  Returns (y bf16 [B, HW, C], mean f32 [B, 32], rstd f32 [B, 32])."""
+    _need_cuda(x, gamma, beta)
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or not x.is_contiguous():
+        raise B200Error("groupnorm_silu_fwd: need contiguous bf16 [B, HW, C]")
+    B, HW, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((B, 32), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((B, 32), dtype=torch.float32, device=x.device)
+    ws = WORKSPACE.get(x.device, int(_cabi.lib().b200_groupnorm_workspace_floats(B, HW, C)), "groupnorm")
+    call("b200_groupnorm_silu_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+         ws.data_ptr(), B, HW, C, float(eps), int(silu), _stream())
+    return y, mean, rstd
+
+
+def groupnorm_silu_bwd(x: Tensor, dy: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, rstd: Tensor, *, silu: bool = True,
+                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, accumulate: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(x, dy, gamma, beta, mean, rstd)
+    B, HW, C = x.shape
+    if dy.dtype != torch.bfloat16 or dy.shape != x.shape or not dy.is_contiguous():
+        raise B200Error("groupnorm_silu_bwd: dy must be contiguous bf16 with x's shape")
+    dx = torch.empty_like(x)
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        accumulate = False
+    ws = WORKSPACE.get(x.device, int(_cabi.lib().b200_groupnorm_workspace_floats(B, HW, C)), "groupnorm")
+    call("b200_groupnorm_silu_bwd", x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+         dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), B, HW, C, int(silu), int(accumulate), _stream())
+    return dx, dgamma, dbeta

@@ -224,6 +224,24 @@ int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStr
 int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * GroupNorm(32) (+ SiLU) on channels-last bf16 activations x [B, HW, C] (C contiguous, C % 32 == 0, C <= 2560): the
+ * normalisation in front of every 3x3 convolution of the SD-v1.5 UNet (BASELINE.json configs[4]).
+ *   y = bf16( act( (x - mean_g) * rstd_g * gamma_c + beta_c ) ),  act = SiLU if silu != 0 else identity
+ * with fp32 statistics per (image, group of C / 32 channels) and ONE rounding at the end, i.e. what
+ * F.group_norm -> F.silu -> autocast's bf16 cast at the following conv amount to
+ * (cflearn/modules/core/convs/residual.py:176-178,197-198,221,241; multimodal/diffusion/unet.py:264-268;
+ * SpatialTransformer.norm without activation, mixed_stacks/api.py:866-870).  mean / rstd: f32 [B, 32], kept for backward.
+ * Backward: dx = bf16 of the fp32 GroupNorm (o SiLU) gradient, dgamma / dbeta f32 [C] (accumulate != 0: added).
+ * workspace: b200_groupnorm_workspace_floats(B, HW, C) floats.  Deterministic (no atomics).
+ * --------------------------------------------------------------------------------------------------------- */
+long long b200_groupnorm_workspace_floats(int B, int HW, int C);
+int b200_groupnorm_silu_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, float* mean, float* rstd,
+                            float* workspace, int B, int HW, int C, float eps, int silu, cudaStream_t stream);
+int b200_groupnorm_silu_bwd(const void* x_bf16, const void* dy_bf16, const float* gamma, const float* beta, const float* mean,
+                            const float* rstd, void* dx_bf16, float* dgamma, float* dbeta, float* workspace, int B, int HW, int C,
+                            int silu, int accumulate, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (replaces the DDP wrap of `accelerator.prepare`, cflearn/trainer.py:226-229,
  * 266-273; the all-reduce sits between backward and optimizer.step, cflearn/schema.py:980-984).  One communicator per
  * process / GPU over NCCL (libnccl.so.2 is dlopen'ed at first use).  b200_comm_unique_id: rank 0 creates the 128-byte

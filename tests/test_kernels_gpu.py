@@ -503,3 +503,40 @@ def test_patch_im2col_u8_fuses_the_input_pipeline_bit_exactly(B, C, S, P, norm):
     got = ops.patch_im2col_u8(x.to(DEV), P, 255.0, mean, std)
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SD-v1.5 UNet building blocks: GroupNorm(32) + SiLU on channels-last activations
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C,silu,eps", [(2, 64, 64, 320, True, 1e-5), (2, 8, 8, 1280, True, 1e-5), (2, 16, 16, 2560, True, 1e-5),
+                                              (3, 32, 32, 640, False, 1e-6), (1, 16, 16, 960, True, 1e-5)])
+def test_groupnorm_silu_fwd_bwd_matches_eager_autocast(B, H, W, C, silu, eps):
+    """Real SD-v1.5 shapes (320 ch @ 64x64, 1280 ch @ 8x8, the 2560-channel skip concatenation, the SpatialTransformer's plain
+    GroupNorm).  Reference = what eager does under bf16 autocast (oracle/unet_oracle.py::res_block): F.group_norm in fp32 on
+    the bf16 activation, F.silu in fp32, ONE bf16 cast at the conv input; backward through the same graph."""
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).to(DEV).to(torch.bfloat16)        # NCHW, as the reference holds it
+    gamma = (1.0 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.05 * torch.randn(C, generator=g)).to(DEV)
+    dy = torch.randn(B, C, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.group_norm(xr.float(), 32, gr, br, eps)
+    ref = (F.silu(z) if silu else z)
+    ref_bf16 = ref.to(torch.bfloat16)
+    ref_bf16.backward(dy)
+    # channels-last views for the kernel
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(B, H * W, C).contiguous()  # noqa: E731
+    y, mean, rstd = ops.groupnorm_silu_fwd(nhwc(x), gamma, beta, eps, silu=silu)
+    dx, dgamma, dbeta = ops.groupnorm_silu_bwd(nhwc(x), nhwc(dy), gamma, beta, mean, rstd, silu=silu)
+    torch.cuda.synchronize()
+    _assert_bf16_close(y, nhwc(ref.detach()), "groupnorm+silu forward")
+    xs = x.float().view(B, 32, -1)
+    assert torch.allclose(mean, xs.mean(-1), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rstd, (xs.var(-1, unbiased=False) + eps).rsqrt(), rtol=1e-4, atol=1e-5)
+    _assert_bf16_close(dx, nhwc(xr.grad.float()), "groupnorm+silu backward dx")
+    assert _relerr(dgamma, gr.grad) < 1e-4 and _relerr(dbeta, br.grad) < 1e-4
+    # deterministic: a second run is bit-identical
+    y2, _, _ = ops.groupnorm_silu_fwd(nhwc(x), gamma, beta, eps, silu=silu)
+    dx2, dg2, db2 = ops.groupnorm_silu_bwd(nhwc(x), nhwc(dy), gamma, beta, mean, rstd, silu=silu)
+    assert torch.equal(y, y2) and torch.equal(dx, dx2) and torch.equal(dgamma, dg2) and torch.equal(dbeta, db2)
