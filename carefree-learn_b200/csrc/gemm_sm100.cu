@@ -67,6 +67,10 @@ struct GemmParams {
     void* out1;
     const void* aux;
     long long ldo;
+    // 3x3 convolution as implicit GEMM (conv != 0): A is a channels-last activation [B, H, W, Cin] behind a 4-D tensor map;
+    // an M tile is 128 consecutive pixels (whole image rows), k-block kb = (tap, 64-channel block), and the A tile of a tap is
+    // the SAME box shifted by (kx - 1, ky - 1) -- TMA zero-fills what falls outside the image: the padding costs nothing
+    int conv, conv_h, conv_w, conv_cin;
     int act;  // GELU / dGELU epilogues: 0 = exact erf GELU (nn.GELU()), 1 = QuickGELU x * sigmoid(1.702 x) (activations.py:151-153)
 };
 
@@ -192,7 +196,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2));
                         const int h = static_cast<int>(cta_rank);
-                        if (!p.a_mn) {
+                        if (p.conv) {
+                            const int cpb = p.conv_cin / BK;
+                            const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const int hw = p.conv_h * p.conv_w;
+                            const int bimg = m0 / hw, y0 = (m0 - bimg * hw) / p.conv_w;
+                            tma_load_4d_2sm(a_dst, &tmA, lead_full, c0, kx - 1, y0 + ky - 1, bimg);
+                        } else if (!p.a_mn) {
                             tma_load_2d_2sm(a_dst, &tmA, lead_full, kb * BK, m0);
                         } else {
 #pragma unroll
@@ -210,7 +221,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         continue;
                     }
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                    if (!p.a_mn) {
+                    if (p.conv) {
+                        const int cpb = p.conv_cin / BK;
+                        const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const int hw = p.conv_h * p.conv_w;
+                        const int bimg = m0 / hw, y0 = (m0 - bimg * hw) / p.conv_w;
+                        tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, kx - 1, y0 + ky - 1, bimg);
+                    } else if (!p.a_mn) {
                         tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
                     } else {
 #pragma unroll
@@ -867,10 +885,12 @@ extern "C" int b200_gemm_pick_splits(int M, int N, int K) {
     return best;
 }
 
-extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                              int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
-                              void* out1, const void* aux, long long ldo, int splits, int max_ctas,
-                              cudaStream_t stream) {
+struct ConvGeom { int B, H, W, Cin; };
+
+static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                         int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
+                         void* out1, const void* aux, long long ldo, int splits, int max_ctas,
+                         cudaStream_t stream, const ConvGeom* cg) {
     int act = 0;  // the QuickGELU epilogues are the GELU / dGELU kernels with another activation
     if (epilogue == B200_EPI_BIAS_QGELU_BF16) { epilogue = EPI_BIAS_GELU_BF16; act = 1; }
     if (epilogue == B200_EPI_DQGELU_BF16) { epilogue = EPI_DGELU_BF16; act = 1; }
@@ -889,10 +909,21 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
         uint64_t d[2], s[1];
         uint32_t bx[2];
+        if (cg != nullptr) {
+            // channels-last activation [B, H, W, Cin]: dims {Cin, W, H, B}; box = 64 channels x 128 consecutive pixels
+            const int hb = cg->H < BM / cg->W ? cg->H : BM / cg->W;      // image rows per tile
+            const int nb = BM / (cg->W * hb);                             // images per tile (> 1 only when H * W < 128)
+            uint64_t d4[4] = {static_cast<uint64_t>(cg->Cin), static_cast<uint64_t>(cg->W), static_cast<uint64_t>(cg->H), static_cast<uint64_t>(cg->B)};
+            uint64_t s4[3] = {static_cast<uint64_t>(cg->Cin) * 2, static_cast<uint64_t>(cg->W) * cg->Cin * 2,
+                              static_cast<uint64_t>(cg->H) * cg->W * cg->Cin * 2};
+            uint32_t b4[4] = {BK, static_cast<uint32_t>(cg->W), static_cast<uint32_t>(hb), static_cast<uint32_t>(nb)};
+            if ((rc = make_tmap(&tmA, A, 2, 4, d4, s4, b4, 128)) != 0) return rc;
+        } else {
         if (!a_mn_major) { d[0] = K; d[1] = M; bx[0] = BK; bx[1] = BM; }
         else             { d[0] = M; d[1] = K; bx[0] = 64; bx[1] = BK; }
         s[0] = static_cast<uint64_t>(lda) * 2;
         if ((rc = make_tmap(&tmA, A, 2, 2, d, s, bx, 128)) != 0) return rc;
+        }
         if (!b_mn_major) { d[0] = K; d[1] = N; bx[0] = BK; bx[1] = BN; }
         else             { d[0] = N; d[1] = K; bx[0] = 64; bx[1] = BK; }
         s[0] = static_cast<uint64_t>(ldb) * 2;
@@ -917,6 +948,10 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
     }
     GemmParams p;
     p.act = act;
+    p.conv = cg != nullptr ? 1 : 0;
+    p.conv_h = cg != nullptr ? cg->H : 0;
+    p.conv_w = cg != nullptr ? cg->W : 0;
+    p.conv_cin = cg != nullptr ? cg->Cin : 0;
     p.M = M; p.N = N; p.K = K;
     p.num_m_tiles = (M + BM - 1) / BM;
     p.num_n_tiles = (N + BN - 1) / BN;
@@ -946,4 +981,34 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
         case EPI_PARTIAL_F32: return launch_gemm<EPI_PARTIAL_F32>(tmA, tmB, tmBh, p, grid, stream);
         default: return set_error(B200_ERR_ARG, "gemm: unknown epilogue");
     }
+}
+
+extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                              int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
+                              void* out1, const void* aux, long long ldo, int splits, int max_ctas,
+                              cudaStream_t stream) {
+    return gemm_dispatch(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, bias, out0, out1, aux, ldo, splits, max_ctas, stream, nullptr);
+}
+
+// 3x3 convolution, stride 1, zero padding 1, on channels-last bf16 activations, as an implicit GEMM on the tcgen05 main loop:
+//   out[b, y, x, co] = epilogue( sum_{ky,kx,ci} x[b, y+ky-1, x+kx-1, ci] * w[co, ky, kx, ci] )
+// x: [B, H, W, Cin]; w_packed: [Cout, 9 * Cin] (tap-major: k = (ky * 3 + kx) * Cin + ci); out / aux: [B*H*W, ldo].
+// M = B*H*W pixels, N = Cout, K = 9 * Cin; the im2col matrix is never materialised -- every (tap, 64-channel) k-block is one
+// TMA box of the activation shifted by the tap, with the halo zero-filled by the TMA unit.
+// Replaces Conv2d.forward -> F.conv2d (cflearn/modules/core/convs/basic.py:155-174) as the SD-v1.5 UNet uses it
+// (convs/residual.py:179-186,199-205 conv1 / conv2; multimodal/diffusion/unet.py:213-217,269-272).  Its input gradient is the
+// same call with the weights flipped and transposed ([Cin, 9 * Cout], tap (2-ky, 2-kx)).
+extern "C" int b200_conv3x3_nhwc_bf16(const void* x, const void* w_packed, const void* bias, void* out0, const void* aux, long long ldo,
+                                      int B, int H, int W, int Cin, int Cout, int epilogue, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return set_error(B200_ERR_ARG, "conv3x3: non-positive size");
+    if (Cin % BK != 0) return set_error(B200_ERR_ARG, "conv3x3: Cin must be a multiple of 64");
+    if (W > BM || BM % W != 0) return set_error(B200_ERR_ARG, "conv3x3: the image width must divide 128");
+    const int hb = H < BM / W ? H : BM / W;
+    if (H % hb != 0 || BM % (W * hb) != 0) return set_error(B200_ERR_ARG, "conv3x3: H must be a multiple of 128 / W (or H * W must divide 128)");
+    if (epilogue != EPI_BIAS_BF16 && epilogue != EPI_BIAS_RESID_F32) return set_error(B200_ERR_ARG, "conv3x3: epilogue must be BIAS_BF16 or BIAS_RESID_F32");
+    ConvGeom cg{B, H, W, Cin};
+    const long long M = static_cast<long long>(B) * H * W;
+    if (M > 0x7fffffffll) return set_error(B200_ERR_ARG, "conv3x3: too many pixels");
+    return gemm_dispatch(x, Cin, 0, w_packed, 9ll * Cin, 0, static_cast<int>(M), Cout, 9 * Cin, epilogue, bias, out0, nullptr, aux, ldo, 1, 0,
+                         stream, &cg);
 }

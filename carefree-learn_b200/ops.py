@@ -343,3 +343,31 @@ def groupnorm_silu_bwd(x: Tensor, dy: Tensor, gamma: Tensor, beta: Tensor, mean:
     call("b200_groupnorm_silu_bwd", x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
          dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), B, HW, C, int(silu), int(accumulate), _stream())
     return dx, dgamma, dbeta
+
+
+def pack_conv3x3_weight(w: Tensor) -> Tensor:
+    """[Cout, Cin, 3, 3] (the reference's Conv2d.weight) -> bf16 [Cout, 9 * Cin], tap-major (k = (ky * 3 + kx) * Cin + ci)."""
+    co, ci, kh, kw = w.shape
+    if kh != 3 or kw != 3:
+        raise B200Error("pack_conv3x3_weight: 3x3 kernels only")
+    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.bfloat16).contiguous()
+
+
+def pack_conv3x3_weight_dgrad(w: Tensor) -> Tensor:
+    """Weights of the INPUT-gradient convolution: [Cin, 9 * Cout] with the taps flipped (dx = conv3x3(dy, flip(w)^T))."""
+    return pack_conv3x3_weight(w.flip(2, 3).transpose(0, 1))
+
+
+def conv3x3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor] = None, *, epilogue: int = EPI_BIAS_BF16, aux: Optional[Tensor] = None) -> Tensor:
+    """x: bf16 [B, H, W, Cin] channels-last; w_packed: bf16 [Cout, 9 * Cin] -> bf16 (or fp32 with the residual epilogue) [B, H, W, Cout]."""
+    _need_cuda(x, w_packed, bias, aux)
+    if x.dtype != torch.bfloat16 or x.dim() != 4 or not x.is_contiguous() or w_packed.dtype != torch.bfloat16 or not w_packed.is_contiguous():
+        raise B200Error("conv3x3: need contiguous bf16 x [B, H, W, Cin] and w_packed [Cout, 9 * Cin]")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    if w_packed.shape[1] != 9 * Cin or Cout % 8 != 0:
+        raise B200Error("conv3x3: weight shape does not match (need [Cout, 9 * Cin], Cout % 8 == 0)")
+    f32 = epilogue == EPI_BIAS_RESID_F32
+    out = torch.empty((B, H, W, Cout), dtype=torch.float32 if f32 else torch.bfloat16, device=x.device)
+    call("b200_conv3x3_nhwc_bf16", x.data_ptr(), w_packed.data_ptr(), _ptr(bias), out.data_ptr(), _ptr(aux), Cout, B, H, W, Cin, Cout, epilogue, _stream())
+    return out

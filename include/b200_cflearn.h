@@ -224,6 +224,19 @@ int b200_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, cudaStr
 int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * 3x3 convolution (stride 1, zero padding 1) on channels-last bf16 activations as an IMPLICIT GEMM on the tcgen05 main
+ * loop: x [B, H, W, Cin], w_packed [Cout, 9 * Cin] (k = (ky * 3 + kx) * Cin + ci), bias bf16 [Cout] or NULL,
+ * out0 / aux [B*H*W, ldo].  Cin % 64 == 0; W divides 128 and H is a multiple of 128 / W (or H * W divides 128).
+ * epilogue: B200_EPI_BIAS_BF16 or B200_EPI_BIAS_RESID_F32.  No im2col matrix exists: each (tap, 64-channel) k-block is ONE
+ * TMA box of the activation shifted by the tap, its halo zero-filled by the TMA unit.
+ * Replaces F.conv2d at cflearn/modules/core/convs/basic.py:155-174 for the UNet's 3x3 convolutions
+ * (convs/residual.py:179-186,199-205; multimodal/diffusion/unet.py:213-217,269-272); the input gradient is the same
+ * call with flipped, transposed weights.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_conv3x3_nhwc_bf16(const void* x, const void* w_packed, const void* bias, void* out0, const void* aux, long long ldo,
+                           int B, int H, int W, int Cin, int Cout, int epilogue, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * GroupNorm(32) (+ SiLU) on channels-last bf16 activations x [B, HW, C] (C contiguous, C % 32 == 0, C <= 2560): the
  * normalisation in front of every 3x3 convolution of the SD-v1.5 UNet (BASELINE.json configs[4]).
  *   y = bf16( act( (x - mean_g) * rstd_g * gamma_c + beta_c ) ),  act = SiLU if silu != 0 else identity

@@ -540,3 +540,33 @@ def test_groupnorm_silu_fwd_bwd_matches_eager_autocast(B, H, W, C, silu, eps):
     y2, _, _ = ops.groupnorm_silu_fwd(nhwc(x), gamma, beta, eps, silu=silu)
     dx2, dg2, db2 = ops.groupnorm_silu_bwd(nhwc(x), nhwc(dy), gamma, beta, mean, rstd, silu=silu)
     assert torch.equal(y, y2) and torch.equal(dx, dx2) and torch.equal(dgamma, dg2) and torch.equal(dbeta, db2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 8, 8, 1280, 1280), (3, 8, 8, 1280, 640), (2, 32, 32, 640, 320),
+                                            (1, 16, 16, 2560, 1280), (2, 16, 16, 64, 8)])
+def test_conv3x3_implicit_gemm_matches_conv2d(B, H, W, Cin, Cout):
+    """3x3 / stride 1 / zero padding 1 convolution on channels-last bf16 activations as an implicit GEMM (no im2col matrix; the
+    halo is the TMA unit's out-of-bound zero fill) at real SD-v1.5 shapes, forward and input gradient, against F.conv2d in fp32
+    on the same bf16 operands, rounded to bf16 at the same point (the conv output under autocast)."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (0.7 / math.sqrt(9 * Cin))).to(DEV).to(torch.bfloat16)
+    bias = (0.1 * torch.randn(Cout, generator=g)).to(DEV).to(torch.bfloat16)
+    ref = F.conv2d(x.float(), w.float(), bias.float(), padding=1)                                 # fp32 reference, NCHW
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = ops.conv3x3(x_nhwc, ops.pack_conv3x3_weight(w), bias)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (B, H, W, Cout)
+    _assert_bf16_close(out.reshape(-1, Cout), ref.permute(0, 2, 3, 1).reshape(-1, Cout), "conv3x3 forward")
+    # residual epilogue: fp32 stream + bf16(conv)
+    res = torch.randn(B, H, W, Cout, generator=g).to(DEV)
+    out_r = ops.conv3x3(x_nhwc, ops.pack_conv3x3_weight(w), bias, epilogue=ops.EPI_BIAS_RESID_F32, aux=res)
+    assert torch.allclose(out_r, res + out.float(), rtol=0, atol=0)
+    # input gradient = the same kernel with flipped / transposed weights
+    if Cout % 64 == 0:
+        dy = torch.randn(B, Cout, H, W, generator=g).to(DEV).to(torch.bfloat16)
+        xr = x.float().clone().requires_grad_(True)
+        F.conv2d(xr, w.float(), None, padding=1).backward(dy.float())
+        dx = ops.conv3x3(dy.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3_weight_dgrad(w))
+        torch.cuda.synchronize()
+        _assert_bf16_close(dx.reshape(-1, Cin), xr.grad.permute(0, 2, 3, 1).reshape(-1, Cin), "conv3x3 input gradient")
