@@ -24,20 +24,22 @@ from . import ops
 from ._cabi import call
 
 
-class ArenaAdam:
+class ArenaAdam(torch.optim.Optimizer):
+    """A real ``torch.optim.Optimizer`` (so ``torch.optim.lr_scheduler`` classes -- and the reference's own ``WarmupScheduler``,
+    cflearn/schedulers.py:126-171 -- accept it), with ONE parameter group holding every parameter of the module's arenas."""
+
     def __init__(self, module: Any, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  capturable: bool = False):
         self.module = module
         self.capturable = capturable
-        # the torch.optim surface schedulers and checkpoints use: ONE group holding every parameter of the arena
-        self.param_groups: List[Dict[str, Any]] = [dict(params=list(module.parameters()), lr=float(lr), betas=tuple(betas),
-                                                        eps=float(eps), weight_decay=float(weight_decay), grad_scale=1.0)]
-        self.defaults = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        super().__init__(list(module.parameters()), dict(lr=float(lr), betas=tuple(betas), eps=float(eps), weight_decay=float(weight_decay),
+                                                         grad_scale=1.0))
         self.step_count = 0
         self.step_dev: Optional[Tensor] = None
         self.hyper_dev: Optional[Tensor] = None
         self._hyper_host: Optional[Tensor] = None
         self._hyper_sent: Optional[tuple] = None
+        self._clip_dev: Optional[Tensor] = None  # when set: grad_scale lives on the device only (clip_grad_norm_)
         # one (exp_avg, exp_avg_sq) pair per parameter arena: a ViT / classifier has one arena, CLIP three (vision tower,
         # text tower, and the loose parameters: logit_scale, token embedding, text projection)
         self.exp_avgs: List[Tensor] = []
@@ -95,7 +97,8 @@ class ArenaAdam:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("ArenaAdam.sync_hyper() must run outside the capture (it is a host-to-device copy of new values)")
         self._hyper_host.copy_(torch.tensor(cur, dtype=torch.float32))
-        self.hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        n = 5 if self._clip_dev is not None else 6  # with clipping on, slot 5 (grad_scale) is written on the device every step
+        self.hyper_dev[:n].copy_(self._hyper_host[:n], non_blocking=True)
         self._hyper_sent = cur
 
     # ---- state --------------------------------------------------------------------------------------------------
@@ -123,7 +126,8 @@ class ArenaAdam:
             out.append(self.step_dev)
         return out
 
-    def step(self) -> None:
+    @torch.no_grad()
+    def step(self, closure: Any = None) -> None:  # type: ignore[override]
         """One Adam update of every arena (one launch per arena; the step counter advances once)."""
         self._state()
         if not self.capturable:
@@ -143,6 +147,23 @@ class ArenaAdam:
         if set_to_none:
             for p in self.module.parameters():
                 p.grad = None
+
+    def clip_grad_norm_(self, max_norm: float) -> Tensor:
+        """``trainer.clip_norm_step()`` (cflearn/schema.py:981; torch.nn.utils.clip_grad_norm_ over all parameters) without a
+        host round trip: the global L2 norm of the flat gradient arenas is taken on the device and the coefficient
+        ``min(1, max_norm / (norm + 1e-6))`` goes straight into the ``grad_scale`` slot the fused Adam kernel multiplies the
+        gradient by -- capturable in the step's CUDA graph.  Returns the norm (device scalar)."""
+        if not self.capturable:
+            raise ValueError("clip_grad_norm_ needs ArenaAdam(capturable=True) (the coefficient stays on the device)")
+        self._state()
+        sq = None
+        for a in self.arenas():
+            t = torch.linalg.vector_norm(a.grad) ** 2
+            sq = t if sq is None else sq + t
+        norm = sq.sqrt()
+        self._clip_dev = (float(max_norm) / (norm + 1e-6)).clamp(max=1.0)
+        self.hyper_dev[5:6].copy_(self._clip_dev.reshape(1))
+        return norm
 
     def state_dict(self) -> Dict[str, Any]:
         step = int(self.step_dev.item()) if self.step_dev is not None else self.step_count
@@ -241,6 +262,9 @@ class GraphedTrainStep:
     def _eager(self) -> None:
         self.optimizer.zero_grad()
         loss = self.model.train_step(*self.inputs)  # DP: the reducers all-reduce bucket by bucket inside backward
+        hook = getattr(self.model, "clip_norm_hook", None)
+        if hook is not None and not self.flat:
+            hook()  # device-side clip coefficient (trainer.B200TrainStep): captured with the step
         if not self.flat:
             self.optimizer.step()
         self.loss.copy_(loss)

@@ -100,6 +100,15 @@ class WithRegister:
         return issubclass(cls.d[name], cls)
 
 
+def check_requires(fn: Callable, name: str, strict: bool = True) -> bool:
+    """cftool.misc.check_requires as its call sites use it (cflearn/toolkit.py:1616-1618 ``scheduler_requires_metric``):
+    does ``fn`` take a parameter called ``name``?  (strict: as a named parameter, not through **kwargs)"""
+    params = inspect.signature(fn).parameters
+    if name in params:
+        return True
+    return (not strict) and any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+
+
 def squeeze(t: Any) -> Any:
     return t.squeeze()
 
@@ -138,6 +147,7 @@ def _install_stubs() -> None:
     real = {
         "shallow_copy_dict": shallow_copy_dict, "update_dict": update_dict, "safe_execute": safe_execute,
         "register_core": register_core, "WithRegister": WithRegister, "squeeze": squeeze, "l2_normalize": l2_normalize,
+        "check_requires": check_requires,
         "print_info": _noop, "print_warning": _noop, "print_error": _noop,
     }
     names = ["cftool", "cftool.misc", "cftool.array", "cftool.types", "cftool.cv", "cftool.pipeline", "cftool.dist",

@@ -364,3 +364,37 @@ def test_install_into_the_real_reference_registry():
         for k in ("encoders.vit_b200", "cv_clf_b200", "fcnn_b200", "tet_b200", "clip_b200"):
             ref_dict.pop(k, None)
         ref_dict.update(replaced)
+
+
+def test_reference_warmup_scheduler_drives_arena_adam():
+    """N2 / ADVICE r1: the reference's default scheduler (cflearn/schedulers.py:126-171 ``WarmupScheduler``, multiplier 3 then a
+    follow-up scheduler; pipeline/blocks/basic.py:334-352) accepts ``ArenaAdam`` (a real torch Optimizer) and writes the same
+    learning-rate sequence into its param group as it does for ``torch.optim.Adam``."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import load_reference as lr
+    from cflearn_b200.optim import ArenaAdam
+
+    if not lr.reference_available():
+        pytest.skip("reference tree not present")
+    lr.load_reference_modules()
+    import importlib
+
+    sch = importlib.import_module("cflearn.schedulers")
+    m = registry.build_module("cv_clf", config=dict(in_channels=3, num_classes=8, img_size=32, latent_dim=64, encoder="vit",
+                                                    encoder_config=dict(patch_size=16, num_layers=1)))
+    ours = ArenaAdam(m, lr=1e-3, capturable=False)
+    assert isinstance(ours, torch.optim.Optimizer)
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3))], lr=1e-3)
+    kw = dict(multiplier=3.0, warmup_step=4, scheduler_afterwards_base=torch.optim.lr_scheduler.StepLR,
+              scheduler_afterwards_config=dict(step_size=2, gamma=0.5))
+    s_ours, s_ref = sch.WarmupScheduler(ours, **kw), sch.WarmupScheduler(ref, **kw)
+    seq_o, seq_r = [], []
+    for _ in range(10):
+        ours._step_count += 1  # (no GPU here: count the step the scheduler expects without launching the kernel)
+        ref.step()
+        s_ours.step()
+        s_ref.step()
+        seq_o.append(ours.lr)
+        seq_r.append(ref.param_groups[0]["lr"])
+    assert seq_o == seq_r and max(seq_o) == pytest.approx(3e-3) and seq_o[-1] < 1e-3
+    assert ours._hyper_tuple()[0] == seq_o[-1]  # what the next step pushes to the device

@@ -494,3 +494,49 @@ def test_clip_graphed_train_step_matches_eager_steps():
         assert abs(a - b) < 1e-4 * max(1.0, abs(a)), (losses_e, losses_g)
     for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
         assert torch.allclose(p, q, rtol=1e-4, atol=1e-6), k
+
+
+def test_trainer_seam_matches_reference_update_sequence():
+    """N2 (trainer seam): ``B200TrainStep`` = forward/loss/backward -> clip_norm_step -> optimizer.step -> zero_grad ->
+    scheduler.step (cflearn/schema.py:977-986).  Three runs over the same batches must agree: (a) eager launches,
+    (b) the whole step as ONE CUDA graph (clip coefficient and learning rate read from device memory), (c) our gradients fed
+    to torch.nn.utils.clip_grad_norm_ + torch.optim.Adam + the same scheduler class."""
+    from cflearn_b200.optim import ArenaAdam
+    from cflearn_b200.trainer import B200TrainStep
+
+    cfg = vo.vit_config("vit_tiny")
+    sd = vo.init_state_dict(cfg, seed=0)
+    batches = [vo.synthetic_batch(cfg, 4, seed=20 + i) for i in range(6)]
+    sched = lambda opt: torch.optim.lr_scheduler.LambdaLR(opt, lambda k: 1.0 + 0.5 * min(k, 3) - 0.2 * max(k - 3, 0))  # noqa: E731 warm-up then decay
+    clip = 0.05  # small enough to be active on these gradients
+
+    def run(graph):
+        m = build(cfg, sd)
+        opt = ArenaAdam(m, lr=1e-3, capturable=True)
+        step = B200TrainStep(m, opt, scheduler=sched(opt), clip_norm=clip, graph=graph, batch=4)
+        losses = [step.step(x.to(DEV), y.to(DEV)).item() for x, y in batches]
+        torch.cuda.synchronize()
+        return m, losses
+
+    m_e, l_e = run(False)
+    m_g, l_g = run(True)
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) < 1e-5 * max(1.0, abs(a)), (l_e, l_g)
+    for (k, p), (_, q) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), k
+    # (c) torch's clip + Adam on OUR gradients
+    m_t = build(cfg, sd)
+    params = list(m_t.parameters())
+    topt = torch.optim.Adam(params, lr=1e-3)
+    tsched = sched(topt)
+    norms = []
+    for x, y in batches:
+        for p in params:
+            p.grad = None
+        m_t.train_step(x.to(DEV), y.to(DEV))
+        norms.append(torch.nn.utils.clip_grad_norm_(params, clip).item())
+        topt.step()
+        tsched.step()
+    assert max(norms) > clip  # clipping really happened
+    for (k, p), (_, q) in zip(m_e.named_parameters(), m_t.named_parameters()):
+        assert torch.allclose(p, q, rtol=2e-4, atol=1e-6), k
