@@ -390,7 +390,8 @@ def test_reference_warmup_scheduler_drives_arena_adam():
     s_ours, s_ref = sch.WarmupScheduler(ours, **kw), sch.WarmupScheduler(ref, **kw)
     seq_o, seq_r = [], []
     for _ in range(10):
-        ours._step_count += 1  # (no GPU here: count the step the scheduler expects without launching the kernel)
+        if hasattr(ours, "_opt_called"):
+            ours._opt_called = True  # (no GPU here: tell the scheduler a step happened without launching the kernel)
         ref.step()
         s_ours.step()
         s_ref.step()
