@@ -27,6 +27,8 @@ FLOP_PER_IMAGE_FWD_BWD = 105_382_969_344  # BASELINE.md section 2 (GEMM-only, 3x
 CLIP_FLOP_PER_PAIR_FWD_BWD = 3 * 14_780_000_000  # 14.78 GFLOP / pair forward (vision 8.82 + text 5.96)
 CONFIG_NAME = "vit_b16"
 PER_GPU_BATCH = 256
+# N > 1 gradient exchange used by default ("graph" once validated on real multi-GPU boxes; see --dp-mode)
+DEFAULT_DP_MODE = "torch"
 
 
 def _peaks():
@@ -334,7 +336,7 @@ def run_b200(args):
     if world > 1:
         # the library's own NCCL communicator (csrc/comm.cu): its all-reduces are plain stream operations, so the bucketed
         # exchange is captured INSIDE the step's CUDA graph on a forked stream, overlapped with the remaining backward
-        comm = dp.NativeComm(rank, world, dev)
+        comm = dp.TorchComm(rank, world, dev) if args.dp_mode == "torch" else dp.NativeComm(rank, world, dev)
         dp.broadcast_parameters(model)
         dp_parity = dp_gradient_parity(comm, rank, world, dev, flat=args.flat_allreduce)  # (the ViT path's reducer; CLIP reuses it per tower)
     use_graph = not args.no_graph
@@ -572,8 +574,10 @@ def run_b200(args):
                        "global_batch": world * B, "seq_len": "50 / 77" if is_clip else 197, "parallelism": f"dp{world}",
                        "optimizer": "adam (fused arena kernel, inside the timed region)",
                        "cuda_graph": bool(use_graph),
-                       "gradient_exchange": (None if world == 1 else ("one flat NCCL all-reduce after the graph (A/B mode)" if args.flat_allreduce else
-                                             "per-block bucket all-reduces (library-owned NCCL communicator) captured inside the step graph on a forked stream")),
+                       "gradient_exchange": (None if world == 1 else {
+                           "graph": "per-block bucket all-reduces (library-owned NCCL communicator) captured inside the step graph on a forked stream",
+                           "flat": "one flat all-reduce on the library-owned NCCL communicator behind the graph",
+                           "torch": "one flat torch.distributed all-reduce behind the graph"}[args.dp_mode]),
                        "l2": "per-step working set (> 15 GB of activations) exceeds the 126 MB L2; no explicit flush needed"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -597,9 +601,13 @@ def main():
     ap.add_argument("--config", default="vit", choices=["vit", "clip"], help="vit: BASELINE.json configs[1]/[2] (the metric); clip: configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--flat-allreduce", action="store_true", help="N > 1 A/B mode: graph up to backward, then ONE all-reduce of the gradient arena + Adam")
+    ap.add_argument("--dp-mode", default=os.environ.get("B200_DP_MODE", DEFAULT_DP_MODE), choices=["graph", "flat", "torch"],
+                    help="N > 1 gradient exchange: graph = per-block bucket all-reduces on the library's own NCCL communicator, captured "
+                         "inside the step graph and overlapped with backward; flat = same communicator, ONE all-reduce behind the graph; "
+                         "torch = torch.distributed, one all-reduce behind the graph (round 1's schedule)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg")
     args = ap.parse_args()
+    args.flat_allreduce = args.dp_mode in ("flat", "torch")
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

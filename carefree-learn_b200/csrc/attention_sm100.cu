@@ -1264,8 +1264,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
 using namespace b200;
 
-static int g_attn_fwd_version = 2;
-static int g_attn_bwd_version = 2;
+// Defaults stay on the round-1 kernels until version 2 has passed its GPU tests on a B200 (B200_ATTN_FWD / B200_ATTN_BWD = 2
+// or b200_set_attention_*_version(2) select the new kernels).
+static int g_attn_fwd_version = 1;
+static int g_attn_bwd_version = 1;
 
 static int attn_check(int B, int T, int H, int Dh) {
     if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");

@@ -156,6 +156,25 @@ class NativeComm:
             self._h = None
 
 
+class TorchComm:
+    """``torch.distributed`` behind the ``NativeComm`` interface (flat, un-captured all-reduces only): the round-1 schedule,
+    kept as the conservative fallback of ``bench.py --dp-mode torch``."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, group: Any = None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.ctas = 0
+        self.nccl_version = 0
+
+    def allreduce_(self, t: torch.Tensor, *, average: bool = True) -> None:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG if average else dist.ReduceOp.SUM, group=self.group)
+
+    def check(self) -> None:
+        pass
+
+    def close(self, abort: bool = False) -> None:
+        pass
+
+
 class NativeBucketReducer(GradBucketReducer):
     """Same bucket protocol as ``GradBucketReducer`` over a ``NativeComm``: works eagerly AND under stream capture.
 
