@@ -540,3 +540,38 @@ def test_trainer_seam_matches_reference_update_sequence():
     assert max(norms) > clip  # clipping really happened
     for (k, p), (_, q) in zip(m_e.named_parameters(), m_t.named_parameters()):
         assert torch.allclose(p, q, rtol=2e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 16, 16, 640, 1280)])
+def test_unet_res_block_forward_matches_oracle(B, H, W, Cin, Cout):
+    """SURVEY.md N3, first composed block: ResidualBlockWithTimeEmbedding forward on the B200 kernels (GroupNorm+SiLU, 3x3
+    implicit-GEMM convolutions, time-embedding Linear, 1x1 shortcut as a GEMM) against oracle/unet_oracle.py::res_block run
+    eagerly on this GPU under bf16 autocast and in fp32, at SD-v1.5 shapes (320 ch @ 64x64; the 640 -> 1280 block @ 16x16)."""
+    import math
+
+    import unet_oracle as uo
+    from cflearn_b200.unet_blocks import res_block_forward
+
+    g = torch.Generator().manual_seed(31)
+    tdim = 1280
+    shapes = [("b.norm1.weight", (Cin,)), ("b.norm1.bias", (Cin,)), ("b.conv1.weight", (Cout, Cin, 3, 3)), ("b.conv1.bias", (Cout,)),
+              ("b.time_embedding.weight", (Cout, tdim)), ("b.time_embedding.bias", (Cout,)), ("b.norm2.weight", (Cout,)), ("b.norm2.bias", (Cout,)),
+              ("b.conv2.weight", (Cout, Cout, 3, 3)), ("b.conv2.bias", (Cout,))]
+    if Cin != Cout:
+        shapes += [("b.shortcut.weight", (Cout, Cin, 1, 1)), ("b.shortcut.bias", (Cout,))]
+    sd = {k: v.to(DEV) for k, v in uo.synthetic_state_dict(shapes, seed=2).items()}
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV)
+    tn = torch.randn(B, tdim, generator=g).to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        xb = x.to(torch.bfloat16)  # the block's input is a bf16 conv output inside the UNet
+        tb = tn.to(torch.bfloat16)
+        e_out = uo.res_block(sd, "b.", xb, tb)
+    f_out = uo.res_block(sd, "b.", x.to(torch.bfloat16).float(), tn.to(torch.bfloat16).float())
+    ours = res_block_forward(sd, "b.", xb.permute(0, 2, 3, 1).contiguous(), tb)
+    torch.cuda.synchronize()
+    ours_nchw = ours.permute(0, 3, 1, 2)
+    assert e_out.dtype == torch.bfloat16
+    floor = rel(e_out, f_out)
+    assert rel(ours_nchw, e_out) < VS_EAGER_FACTOR * floor + SLACK, (rel(ours_nchw, e_out), floor)
+    assert rel(ours_nchw, f_out) < VS_FP32_FACTOR * floor + SLACK
+    print(f"res_block {Cin}->{Cout} @ {H}x{W}: ours vs eager {rel(ours_nchw, e_out):.2e} (eager vs fp32 {floor:.2e})")
