@@ -53,7 +53,7 @@ SIGNATURES: Dict[str, Any] = {
     ),
     "b200_patch_im2col": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_patch_im2col_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_double, POINTER(c_double), POINTER(c_double), _P]),
-    "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "b200_assemble_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "b200_assemble_tokens_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_embedding_fwd": (c_int, [_P, _P, _P, _LL, c_int, c_int, _P, _P]),
     "b200_embedding_bwd": (c_int, [_P, _P, _P, _LL, c_int, c_int, c_int, _P]),

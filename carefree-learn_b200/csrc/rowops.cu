@@ -429,8 +429,11 @@ __global__ void patch_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloa
 }
 
 // net[b, t, d..d+7] = (t == 0 ? cls : float(patch[b*np + t-1])) + pos[t]
+// conv_bias != nullptr: the patch rows first take eager's separate bias add, bf16(patch + bias), i.e. the SECOND rounding of
+// `F.conv2d(x, w, bias)` on CUDA (the convolution output is rounded to bf16, then `output.add_(bias)` rounds again)
 __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
-                                       const float* __restrict__ pos, float* __restrict__ net, int B, int np, int D) {
+                                       const float* __restrict__ pos, float* __restrict__ net, int B, int np, int D,
+                                       const __nv_bfloat16* __restrict__ conv_bias) {
     const int d8 = D / 8;
     const long long total = static_cast<long long>(B) * (np + 1) * d8;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -448,6 +451,13 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ patch, 
         const uint4 p = *reinterpret_cast<const uint4*>(patch + (static_cast<long long>(b) * np + (t - 1)) * D + dc);
         v[0] = bf16lo(p.x); v[1] = bf16hi(p.x); v[2] = bf16lo(p.y); v[3] = bf16hi(p.y);
         v[4] = bf16lo(p.z); v[5] = bf16hi(p.z); v[6] = bf16lo(p.w); v[7] = bf16hi(p.w);
+        if (conv_bias != nullptr) {
+            const uint4 cb = *reinterpret_cast<const uint4*>(conv_bias + dc);
+            v[0] = bf16_round(v[0] + bf16lo(cb.x)); v[1] = bf16_round(v[1] + bf16hi(cb.x));
+            v[2] = bf16_round(v[2] + bf16lo(cb.y)); v[3] = bf16_round(v[3] + bf16hi(cb.y));
+            v[4] = bf16_round(v[4] + bf16lo(cb.z)); v[5] = bf16_round(v[5] + bf16hi(cb.z));
+            v[6] = bf16_round(v[6] + bf16lo(cb.w)); v[7] = bf16_round(v[7] + bf16hi(cb.w));
+        }
     }
     const float4 p0 = *reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D + dc);
     const float4 p1 = *reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D + dc + 4);
@@ -894,10 +904,11 @@ extern "C" int b200_patch_im2col_u8(const void* x_u8_hwc, void* cols_bf16, int B
 }
 
 extern "C" int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,
-                                    int D, cudaStream_t stream) {
+                                    int D, const void* conv_bias_bf16, cudaStream_t stream) {
     if (B <= 0 || np <= 0 || D <= 0 || D % 8 != 0) return set_error(B200_ERR_ARG, "assemble_tokens: D % 8 != 0");
     const long long total = static_cast<long long>(B) * (np + 1) * (D / 8);
-    assemble_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(patch_bf16), cls, pos, net, B, np, D);
+    assemble_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(patch_bf16), cls, pos, net, B, np, D,
+                                                                                       reinterpret_cast<const __nv_bfloat16*>(conv_bias_bf16));
     return check_launch("assemble_tokens");
 }
 

@@ -32,6 +32,7 @@ LATENT_KEY = "latent"
 
 _ALIGN = 64  # elements; keeps every view 16-byte aligned in both the fp32 and the bf16 arena
 _NVTX = os.environ.get("B200_NVTX", "0") == "1"
+_STEM_BIAS_SPLIT = os.environ.get("B200_STEM_BIAS", "split") != "fused"
 
 
 class _nvtx:
@@ -274,9 +275,14 @@ class ViTEngine:
             cols = ops.patch_im2col_u8(x, g.patch, pipe.get("division", 255.0), pipe.get("mean"), pipe.get("std"))
         else:
             cols = ops.patch_im2col(x, g.patch)
+        # F.conv2d with a bias on CUDA is TWO roundings in eager: ATen's cuDNN path produces the bf16 convolution output and
+        # then runs `output.add_(bias)` on the bf16 tensor (aten/native/Convolution.cpp) -- unlike F.linear, whose bias is
+        # fused before the single rounding.  B200_STEM_BIAS=fused restores the single rounding (A/B; tools/probe_conv_bias.py).
+        split = g.conv_bias and _STEM_BIAS_SPLIT
         patch = ops.gemm(cols, A.w("to_patches.projection.weight").view(D, -1),
-                         bias=A.w("to_patches.projection.bias") if g.conv_bias else None)
-        net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D).view(B * T, D)
+                         bias=A.w("to_patches.projection.bias") if (g.conv_bias and not split) else None)
+        net = ops.assemble_tokens(patch, A.p("encoder.head_token"), A.p("encoder.pos_encoding.pos_encoding"), B, g.np, D,
+                                  conv_bias=A.w("to_patches.projection.bias") if split else None).view(B * T, D)
         return cols, net
 
     def block_forward(self, i: int, net: Tensor, B: int) -> Tuple[Tensor, Tuple[Tensor, ...]]:
@@ -880,7 +886,7 @@ class VanillaClassifierB200(nn.Module):
         loss records a flag on the device instead.  This raises ``ValueError`` for it once the flag has reached the host
         (``sync=True`` waits for it); ``forward`` calls it without waiting."""
         ev = self._bad_event
-        if ev is None:
+        if ev is None or torch.cuda.is_current_stream_capturing():  # (querying an event is not allowed while capturing)
             return
         if sync:
             ev.synchronize()

@@ -163,8 +163,10 @@ int b200_patch_im2col(const float* x, void* cols_bf16, int B, int C, int img, in
  * (cflearn/data/utils.py:255-283) and autocast's bf16 cast.  mean / std: HOST pointers to C doubles (NULL: 0 / 1). */
 int b200_patch_im2col_u8(const void* x_u8_hwc, void* cols_bf16, int B, int C, int img, int patch, double division,
                          const double* mean_host, const double* std_host, cudaStream_t stream);
+/* conv_bias_bf16 (bf16 [D] or NULL): the patch rows first become bf16(patch + bias) -- eager's F.conv2d with a bias on CUDA
+ * rounds the convolution output to bf16 and then adds the bias in a second bf16 op (ATen cuDNN path: `output.add_(bias)`). */
 int b200_assemble_tokens(const void* patch_bf16, const float* cls, const float* pos, float* net, int B, int np,
-                         int D, cudaStream_t stream);
+                         int D, const void* conv_bias_bf16, cudaStream_t stream);
 int b200_assemble_tokens_bwd(const float* dnet, void* dpatch_bf16, float* dpos, float* dcls, int B, int np, int D,
                              int accumulate, cudaStream_t stream);
 /* Text-tower input stage (TeTEncoder, cflearn/modules/nlp/encoder/transformer.py:92 -> mixed_stacks/api.py:419-438 without

@@ -165,6 +165,32 @@ def mixing_block(sd: StateDict, i: int, net: Tensor, num_heads: int, eps: float,
     return net + feed_forward(sd, b + "channel_mixing.net.", c, activation)
 
 
+def mixing_block_ops(sd: StateDict, i: int, net: Tensor, num_heads: int, eps: float) -> Dict[str, Tensor]:
+    """The SAME op sequence as ``mixing_block`` (GELU FeedForward, no mask) with every op boundary returned, for the per-op
+    teacher-forced parity tests (tests/_taps.py).  ``out`` is bit-identical to ``mixing_block(...)`` (checked in
+    tests/test_oracle.py).  Lines cited there: mixed_stacks/api.py:130-158, attentions.py:213-277, channel_mixers.py:29-36."""
+    b = f"encoder.mixing_blocks.{i}."
+    d = net.shape[-1]
+    bsz, t, _ = net.shape
+    o: Dict[str, Tensor] = {"x": net}
+    o["ln1"] = F.layer_norm(net, (d,), sd[b + "token_norm.weight"], sd[b + "token_norm.bias"], eps)
+    p = b + "token_mixing.net."
+    o["qkv"] = F.linear(o["ln1"], sd[p + "in_w"], sd[p + "qkv_bias"])
+    q, k, v = o["qkv"].chunk(3, dim=-1)
+    q, k, v = (z.view(bsz, t, num_heads, d // num_heads).permute(0, 2, 1, 3).contiguous() for z in (q, k, v))
+    att = F.scaled_dot_product_attention(q, k, v, None, 0.0)
+    o["attn"] = att.transpose(1, 2).contiguous().view(-1, t, d)
+    o["proj"] = F.linear(o["attn"], sd[p + "out_linear.linear.weight"], sd[p + "out_linear.linear.bias"])
+    o["mid"] = net + o["proj"]
+    o["ln2"] = F.layer_norm(o["mid"], (d,), sd[b + "channel_norm.weight"], sd[b + "channel_norm.bias"], eps)
+    c = b + "channel_mixing.net."
+    o["h"] = F.linear(o["ln2"], sd[c + "0.linear.weight"], sd[c + "0.linear.bias"])
+    o["act"] = F.gelu(o["h"])
+    o["ff"] = F.linear(o["act"], sd[c + "3.linear.weight"], sd[c + "3.linear.bias"])
+    o["out"] = o["mid"] + o["ff"]
+    return o
+
+
 def encoder_forward(sd: StateDict, x: Tensor, cfg: Dict[str, int], taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """ViTEncoder.forward (modules/cv/encoder/transformer.py:88-100) -> [B, latent_dim]."""
     d = cfg["latent_dim"]

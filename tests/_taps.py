@@ -153,3 +153,124 @@ def eager_self_noise(name: str, batch: int, seed: int = 1) -> Dict[str, float]:
     res["worst grad"] = max(rel(g1[k], g0[k]) for k in g0)
     res["median grad"] = sorted(rel(g1[k], g0[k]) for k in g0)[len(g0) // 2]
     return res
+
+
+def teacher_forced_op_errors(name: str, batch: int, blocks=None, seed: int = 1) -> Dict[str, float]:
+    """ONE rounding stage at a time: every kernel of a transformer block, forward and backward, is fed the EAGER run's own
+    input of that op (activation, upstream gradient, saved tensors) and compared with eager's output of the same op.  This is
+    the granularity at which BASELINE.json's 1e-3 is a property of the implementation: one bf16 rounding turns the ~1e-6
+    fp32 summation-order noise into ~5e-5; every further chained rounding takes eps to ~sqrt(eps * ulp), so a whole block
+    (4-5 chained roundings) already sits at 2-3e-3 between ANY two correct implementations (see ``teacher_forced_errors``)."""
+    cfg = vo.vit_config(name)
+    sd = vo.init_state_dict(cfg, seed=0)
+    x, y = vo.synthetic_batch(cfg, batch, seed=seed)
+    x, y = x.to(DEV), y.to(DEV)
+    _, _, taps = eager_with_taps(cfg, sd, x, y)
+    m = build(cfg, sd)
+    eng, A, g = m.engine, m.arena, m.geo
+    A.ensure()
+    A.refresh_bf16()
+    B, T, D, L, H = batch, g.T, g.D, g.L, g.H
+    M = B * T
+    G = A.grad
+    blocks = list(blocks) if blocks is not None else sorted({0, L // 2, L - 1})
+    params = {k: v.to(DEV) for k, v in sd.items()}
+    res: Dict[str, float] = {}
+    bf = lambda t: t.detach().to(torch.bfloat16).contiguous()  # noqa: E731
+    for i in blocks:
+        b = f"encoder.mixing_blocks.{i}."
+        pr = {k: v.detach().clone().requires_grad_(True) for k, v in params.items() if k.startswith(b)}
+        xin = (taps["tokens"] if i == 0 else taps[f"block{i - 1}"]).detach().clone().requires_grad_(True)
+        up = taps[f"block{i}"].grad.detach()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o = vo.mixing_block_ops(pr, i, xin, H, g.eps)
+        for t in o.values():
+            if t.requires_grad and not t.is_leaf:
+                t.retain_grad()
+        (o["out"].float() * up).sum().backward()
+        e = {k: v.detach() for k, v in o.items()}
+        ge = {k: v.grad.detach() for k, v in o.items() if v.grad is not None}
+        tag = f"block{i} "
+        with torch.no_grad():
+            x2 = e["x"].float().reshape(M, D).contiguous()
+            # ---------------- forward, op by op ----------------
+            ln1, mean1, rstd1 = ops.layernorm_fwd(x2, A.p(b + "token_norm.weight"), A.p(b + "token_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+            res[tag + "fwd LayerNorm1"] = rel(ln1, bf(e["ln1"]).view(M, D))
+            e_ln1 = bf(e["ln1"]).view(M, D)
+            qkv = ops.gemm(e_ln1, A.w(b + "token_mixing.net.in_w"), bias=A.w(b + "token_mixing.net.qkv_bias"))
+            res[tag + "fwd qkv GEMM"] = rel(qkv, e["qkv"].view(M, 3 * D))
+            e_qkv = bf(e["qkv"]).view(M, 3 * D)
+            attn, lse = ops.attention_fwd(e_qkv, B, T, H)
+            res[tag + "fwd attention"] = rel(attn, e["attn"].view(M, D))
+            e_attn = bf(e["attn"]).view(M, D)
+            mid = ops.gemm(e_attn, A.w(b + "token_mixing.net.out_linear.linear.weight"), bias=A.w(b + "token_mixing.net.out_linear.linear.bias"),
+                           epilogue=ops.EPI_BIAS_RESID_F32, aux=x2)
+            res[tag + "fwd out-proj (+residual)"] = rel(mid, e["mid"].view(M, D))
+            res[tag + "fwd out-proj (branch only)"] = rel(mid - x2, e["proj"].float().view(M, D))
+            e_mid = e["mid"].float().reshape(M, D).contiguous()
+            ln2, mean2, rstd2 = ops.layernorm_fwd(e_mid, A.p(b + "channel_norm.weight"), A.p(b + "channel_norm.bias"), g.eps, rows=M, dim=D, ld_x=D)
+            res[tag + "fwd LayerNorm2"] = rel(ln2, bf(e["ln2"]).view(M, D))
+            e_ln2 = bf(e["ln2"]).view(M, D)
+            act = torch.empty((M, g.FF), dtype=torch.bfloat16, device=DEV)
+            h = ops.gemm(e_ln2, A.w(b + "channel_mixing.net.0.linear.weight"), bias=A.w(b + "channel_mixing.net.0.linear.bias"),
+                         epilogue=ops.EPI_BIAS_GELU_BF16, out1=act)
+            res[tag + "fwd FF1 GEMM (h)"] = rel(h, e["h"].view(M, g.FF))
+            res[tag + "fwd FF1 GELU (act)"] = rel(act, e["act"].view(M, g.FF))
+            e_h, e_act = bf(e["h"]).view(M, g.FF), bf(e["act"]).view(M, g.FF)
+            out = ops.gemm(e_act, A.w(b + "channel_mixing.net.3.linear.weight"), bias=A.w(b + "channel_mixing.net.3.linear.bias"),
+                           epilogue=ops.EPI_BIAS_RESID_F32, aux=e_mid)
+            res[tag + "fwd FF2 (+residual)"] = rel(out, e["out"].view(M, D))
+            res[tag + "fwd FF2 (branch only)"] = rel(out - e_mid, e["ff"].float().view(M, D))
+            # ---------------- backward, op by op ----------------
+            pg = {k: v.grad for k, v in pr.items()}
+            d_ff = bf(ge["ff"]).view(M, D)                                     # dY of FF2 (bf16 under autocast)
+            dh = ops.gemm(d_ff, A.w(b + "channel_mixing.net.3.linear.weight"), b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=e_h)
+            res[tag + "bwd FF2 dgrad x GELU'"] = rel(dh, ge["h"].view(M, g.FF))
+            ops.wgrad(d_ff, e_act, A.g(b + "channel_mixing.net.3.linear.weight", G))
+            res[tag + "bwd FF2 wgrad"] = rel(A.g(b + "channel_mixing.net.3.linear.weight", G), pg[b + "channel_mixing.net.3.linear.weight"])
+            ops.colsum(d_ff, A.g(b + "channel_mixing.net.3.linear.bias", G))
+            res[tag + "bwd FF2 bias grad"] = rel(A.g(b + "channel_mixing.net.3.linear.bias", G), pg[b + "channel_mixing.net.3.linear.bias"])
+            e_dh = bf(ge["h"]).view(M, g.FF)
+            dln2 = ops.gemm(e_dh, A.w(b + "channel_mixing.net.0.linear.weight"), b_mn_major=True)
+            res[tag + "bwd FF1 dgrad"] = rel(dln2, ge["ln2"].view(M, D))
+            ops.wgrad(e_dh, e_ln2, A.g(b + "channel_mixing.net.0.linear.weight", G))
+            res[tag + "bwd FF1 wgrad"] = rel(A.g(b + "channel_mixing.net.0.linear.weight", G), pg[b + "channel_mixing.net.0.linear.weight"])
+            ops.colsum(e_dh, A.g(b + "channel_mixing.net.0.linear.bias", G))
+            res[tag + "bwd FF1 bias grad"] = rel(A.g(b + "channel_mixing.net.0.linear.bias", G), pg[b + "channel_mixing.net.0.linear.bias"])
+            e_dln2 = bf(ge["ln2"]).view(M, D)
+            dmid = torch.empty((M, D), dtype=torch.float32, device=DEV)
+            dmid_bf = torch.empty((M, D), dtype=torch.bfloat16, device=DEV)
+            ops.layernorm_bwd(e_dln2, e_mid, A.p(b + "channel_norm.weight"), mean2, rstd2, rows=M, dim=D, ld_x=D,
+                              dres=up.float().reshape(M, D).contiguous(), dx_out=dmid, ld_dx=D, dx_bf16=dmid_bf,
+                              dgamma=A.g(b + "channel_norm.weight", G), dbeta=A.g(b + "channel_norm.bias", G))
+            res[tag + "bwd LayerNorm2 dx (+residual grad)"] = rel(dmid, ge["mid"].view(M, D))
+            res[tag + "bwd LayerNorm2 dgamma"] = rel(A.g(b + "channel_norm.weight", G), pg[b + "channel_norm.weight"])
+            res[tag + "bwd LayerNorm2 dbeta"] = rel(A.g(b + "channel_norm.bias", G), pg[b + "channel_norm.bias"])
+            e_dproj = bf(ge["proj"]).view(M, D)
+            dattn = ops.gemm(e_dproj, A.w(b + "token_mixing.net.out_linear.linear.weight"), b_mn_major=True)
+            res[tag + "bwd out-proj dgrad"] = rel(dattn, ge["attn"].view(M, D))
+            ops.wgrad(e_dproj, e_attn, A.g(b + "token_mixing.net.out_linear.linear.weight", G))
+            res[tag + "bwd out-proj wgrad"] = rel(A.g(b + "token_mixing.net.out_linear.linear.weight", G), pg[b + "token_mixing.net.out_linear.linear.weight"])
+            e_dattn = bf(ge["attn"]).view(M, D)
+            dbias = A.g(b + "token_mixing.net.qkv_bias", G)
+            dqkv = ops.attention_bwd(e_qkv, e_attn, e_dattn, lse, B, T, H, dbias=dbias)
+            res[tag + "bwd attention (dqkv)"] = rel(dqkv, ge["qkv"].view(M, 3 * D))
+            e_dqkv = bf(ge["qkv"]).view(M, 3 * D)
+            ops.colsum(e_dqkv, dbias)
+            res[tag + "bwd qkv bias grad"] = rel(dbias, pg[b + "token_mixing.net.qkv_bias"])
+            dln1 = ops.gemm(e_dqkv, A.w(b + "token_mixing.net.in_w"), b_mn_major=True)
+            res[tag + "bwd qkv dgrad"] = rel(dln1, ge["ln1"].view(M, D))
+            ops.wgrad(e_dqkv, e_ln1, A.g(b + "token_mixing.net.in_w", G))
+            res[tag + "bwd qkv wgrad"] = rel(A.g(b + "token_mixing.net.in_w", G), pg[b + "token_mixing.net.in_w"])
+            e_dln1 = bf(ge["ln1"]).view(M, D)
+            dx = torch.empty((M, D), dtype=torch.float32, device=DEV)
+            dx_bf = torch.empty((M, D), dtype=torch.bfloat16, device=DEV)
+            ops.layernorm_bwd(e_dln1, x2, A.p(b + "token_norm.weight"), mean1, rstd1, rows=M, dim=D, ld_x=D,
+                              dres=ge["mid"].float().reshape(M, D).contiguous(), dx_out=dx, ld_dx=D, dx_bf16=dx_bf,
+                              dgamma=A.g(b + "token_norm.weight", G), dbeta=A.g(b + "token_norm.bias", G))
+            res[tag + "bwd LayerNorm1 dx (+residual grad)"] = rel(dx, xin.grad.view(M, D))
+            res[tag + "bwd LayerNorm1 dgamma"] = rel(A.g(b + "token_norm.weight", G), pg[b + "token_norm.weight"])
+            res[tag + "bwd LayerNorm1 dbeta"] = rel(A.g(b + "token_norm.bias", G), pg[b + "token_norm.bias"])
+        del o, e, ge
+    torch.cuda.synchronize()
+    return res

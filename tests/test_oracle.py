@@ -233,3 +233,19 @@ def test_input_pipeline_oracle_known_values():
     assert torch.equal(out[0, :, 1, 1], want2)
     plain = io.input_pipeline(x)  # division only
     assert torch.equal(plain[0, :, 0, 0], torch.tensor([1.0, 0.0, 128 / 255], dtype=torch.float64).float())
+
+
+def test_mixing_block_ops_is_the_same_computation_as_mixing_block():
+    """oracle/vit_oracle.py::mixing_block_ops (op boundaries exposed for the per-op parity tests) == mixing_block, bit for bit,
+    in fp32 and under bf16 autocast."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vit_oracle as vo
+
+    cfg = vo.vit_config("vit_tiny")
+    sd = vo.init_state_dict(cfg, seed=0)
+    x = torch.randn(3, 5, cfg["latent_dim"], generator=torch.Generator().manual_seed(1))
+    for autocast in (False, True):
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            a = vo.mixing_block(sd, 1, x, cfg["latent_dim"] // 64, 1e-6)
+            b = vo.mixing_block_ops(sd, 1, x, cfg["latent_dim"] // 64, 1e-6)["out"]
+        assert torch.equal(a, b)

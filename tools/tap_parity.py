@@ -5,10 +5,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _taps import eager_self_noise, teacher_forced_errors  # noqa: E402
+from _taps import eager_self_noise, teacher_forced_errors, teacher_forced_op_errors  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "vit_b16"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+ops_res = teacher_forced_op_errors(name, batch, blocks=None if name != "vit_b16" else (0, 6, 11))
+print(f"# teacher-forced PER-OP parity vs eager bf16 autocast, {name}, batch {batch} (relative L2; every op fed eager's own input)")
+for k, v in ops_res.items():
+    print(f"{k:52s} {v:.3e}")
+print(f"# worst op: {max(ops_res.values()):.3e}")
 out, gerr = teacher_forced_errors(name, batch)
 print(f"# teacher-forced stage parity vs eager bf16 autocast, {name}, batch {batch} (relative L2)")
 for k, v in out.items():
