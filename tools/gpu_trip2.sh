@@ -4,6 +4,7 @@
 mkdir -p gpurun_out
 export B200_ATTN_FWD=2 B200_ATTN_BWD=2
 timeout 120 python tools/probe_conv_bias.py > gpurun_out/r02_probe_conv_bias.txt 2>&1; cat gpurun_out/r02_probe_conv_bias.txt
+timeout 300 python tools/probe_layout.py > gpurun_out/r02_probe_layout.txt 2>&1; cat gpurun_out/r02_probe_layout.txt
 timeout 900 python tools/tap_parity.py vit_b16 256 > gpurun_out/tap_parity_b256.txt 2>&1; echo "tap_parity rc=$?"; grep -n "worst op\|stem" gpurun_out/tap_parity_b256.txt
 timeout 900 python -m pytest tests/test_taps_gpu.py -q -s > gpurun_out/pytest_taps.log 2>&1; echo "taps rc=$?"; tail -8 gpurun_out/pytest_taps.log
 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_taps_gpu.py > gpurun_out/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -12 gpurun_out/pytest_gpu.log
