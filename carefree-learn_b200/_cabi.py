@@ -45,6 +45,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_attention_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "b200_set_attention_fwd_version": (c_int, [c_int]),
     "b200_set_attention_bwd_version": (c_int, [c_int]),
+    "b200_set_attention_prefetch": (c_int, [c_int]),
     "b200_attention_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P]),
     "b200_fcnn_step": (
         c_int,
@@ -101,6 +102,8 @@ def _load() -> None:
             fn.argtypes = args
         if os.environ.get("B200_ATTN_FWD", "") in ("1", "2"):  # A/B switch for profiling
             lib.b200_set_attention_fwd_version(int(os.environ["B200_ATTN_FWD"]))
+        if os.environ.get("B200_ATTN_PREFETCH", "") in ("0", "1"):
+            lib.b200_set_attention_prefetch(int(os.environ["B200_ATTN_PREFETCH"]))
         if os.environ.get("B200_ATTN_BWD", "") in ("1", "2"):
             lib.b200_set_attention_bwd_version(int(os.environ["B200_ATTN_BWD"]))
         if os.environ.get("B200_GEMM_MULTICAST", "") in ("0", "1", "2"):  # A/B/C switch for profiling; results are identical

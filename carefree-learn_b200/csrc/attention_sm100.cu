@@ -116,7 +116,32 @@ struct AttnParams {
     int tp;           // T rounded up to a multiple of 16
     float scale;
     int causal;
+    // version-2 kernels: cooperative L2 prefetch.  A head's Q / K / V tile is T pieces of 128 bytes at a stride of 3 * D * 2
+    // bytes, and at any moment the 12 heads of an image are being fetched by 12 different SMs: DRAM sees 128-byte requests
+    // scattered over many pages.  Each persistent CTA therefore prefetches, one item ahead, ITS 1/H share of the image's
+    // CONTIGUOUS qkv rows (and of O / dO in the backward) into L2 -- whole DRAM pages -- and the strided TMA boxes that
+    // follow hit in L2.  0 switches it off (A/B timing).
+    int prefetch;
+    const void* qkv_base;   // packed qkv [B, T, 3 * D] bf16
+    const void* o_base;     // backward: O  [B, T, D] bf16
+    const void* do_base;    // backward: dO [B, T, D] bf16
 };
+
+// 1 / H share `h` of the contiguous block [base + b * bytes_per_image, + bytes_per_image): 16-byte granular
+__device__ __forceinline__ void prefetch_share(const void* base, long long bytes_per_image, int b, int h, int H) {
+    long long chunk = (bytes_per_image / H + 15) / 16 * 16;
+    const long long off = chunk * h;
+    if (off >= bytes_per_image) return;
+    if (off + chunk > bytes_per_image) chunk = (bytes_per_image - off) / 16 * 16;
+    if (chunk <= 0) return;
+    const char* p0 = reinterpret_cast<const char*>(base) + static_cast<long long>(b) * bytes_per_image + off;
+    while (chunk > 0) {  // (the size operand is 32 bits; keep single requests modest)
+        const uint32_t n = chunk > 65536 ? 65536u : static_cast<uint32_t>(chunk);
+        bulk_prefetch_l2(p0, n);
+        p0 += n;
+        chunk -= n;
+    }
+}
 
 __global__ void __launch_bounds__(AF_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
@@ -403,6 +428,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     mbar_wait(&empty_bar[s], static_cast<uint32_t>((it >> 1) & 1) ^ 1u);
                     const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
                     const int h = w % p.H, b = w / p.H;
+                    if (p.prefetch && it + 1 < n_my) {  // this CTA's share of the NEXT item's image, as whole contiguous rows
+                        const int w1 = w + static_cast<int>(gridDim.x);
+                        prefetch_share(p.qkv_base, static_cast<long long>(p.T) * 3 * p.D * 2, w1 / p.H, w1 % p.H, p.H);
+                    }
                     uint8_t* st = smem + s * F2_STAGE;
                     mbar_expect_tx(&full_bar[s], bytes);
                     for (int mt = 0; mt < n_mt; ++mt) tma_load_3d(st + F2_Q + mt * 16384, &tmQ, &full_bar[s], h * 64, mt * 128, b);
@@ -986,6 +1015,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const int w = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
                 const int h = w % p.H, b = w / p.H;
                 const uint32_t par = static_cast<uint32_t>(it & 1);
+                if (p.prefetch && it + 1 < n_my) {  // this CTA's share of the NEXT item's image: qkv, O and dO as whole contiguous rows
+                    const int w1 = w + static_cast<int>(gridDim.x);
+                    const int b1 = w1 / p.H, h1 = w1 % p.H;
+                    prefetch_share(p.qkv_base, static_cast<long long>(p.T) * 3 * p.D * 2, b1, h1, p.H);
+                    prefetch_share(p.o_base, static_cast<long long>(p.T) * p.D * 2, b1, h1, p.H);
+                    prefetch_share(p.do_base, static_cast<long long>(p.T) * p.D * 2, b1, h1, p.H);
+                }
                 for (int t = 0; t < n_kt; ++t) {  // (buffers are released in the order kv0, q0, kv1, q1: wait in that order)
                     mbar_wait(&empty_kv[t], par ^ 1u);
                     mbar_expect_tx(&full_kv[t], 2u * 16384u);
@@ -1268,6 +1304,7 @@ using namespace b200;
 // or b200_set_attention_*_version(2) select the new kernels).
 static int g_attn_fwd_version = 1;
 static int g_attn_bwd_version = 1;
+static int g_attn_prefetch = 1;
 
 static int attn_check(int B, int T, int H, int Dh) {
     if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");
@@ -1299,6 +1336,7 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = tp; p.scale = scale; p.causal = causal;
+    p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = nullptr; p.do_base = nullptr;
     const int n_mt = (T + 127) / 128;
     if (g_attn_fwd_version == 1) {
         attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
@@ -1347,6 +1385,7 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
+    p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = out_bf16; p.do_base = dout_bf16;
     if (g_attn_bwd_version == 1) {
         attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                                 reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
@@ -1359,6 +1398,12 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p, n_items);
     }
     return check_launch("attention_bwd");
+}
+
+extern "C" int b200_set_attention_prefetch(int enable) {
+    const int old = g_attn_prefetch;
+    g_attn_prefetch = enable ? 1 : 0;
+    return old;
 }
 
 // 2 (default): persistent backward with transposed scores and P^T / dS^T operands in tensor memory; 1: the round-1 kernel

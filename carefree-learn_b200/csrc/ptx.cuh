@@ -205,6 +205,10 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// L2 prefetch of a CONTIGUOUS byte range (16-byte aligned address and size): no smem destination, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
 // wait until at most 1 committed bulk store still has to read its smem source (two staging buffers in rotation)
 __device__ __forceinline__ void tma_store_wait_read1() {
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");

@@ -31,9 +31,10 @@ def timeit(fn, reps=20):
 B, T, H = 256, 197, 12
 qa = (torch.randn(B, T, 3 * H * 64, device=dev)).to(torch.bfloat16)
 qb = (torch.randn(B * H, T, 3 * 64, device=dev)).to(torch.bfloat16)
-for ver in (2, 1):
+for ver, pf in ((2, 1), (2, 0), (1, 0)):
     _cabi.lib().b200_set_attention_fwd_version(ver)
     _cabi.lib().b200_set_attention_bwd_version(ver)
+    _cabi.lib().b200_set_attention_prefetch(pf)
     ta = timeit(lambda: ops.attention_fwd(qa, B, T, H))
     tb = timeit(lambda: ops.attention_fwd(qb, B * H, T, 1))
     oa, la = ops.attention_fwd(qa, B, T, H)
@@ -41,7 +42,7 @@ for ver in (2, 1):
     da, db = torch.randn_like(oa), torch.randn_like(ob)
     tba = timeit(lambda: ops.attention_bwd(qa, oa, da, la, B, T, H))
     tbb = timeit(lambda: ops.attention_bwd(qb, ob, db, lb, B * H, T, 1))
-    print(f"attention v{ver}: fwd model layout {ta:.1f} us | one head per image {tb:.1f} us || bwd {tba:.1f} us | {tbb:.1f} us")
+    print(f"attention v{ver} prefetch={pf}: fwd model layout {ta:.1f} us | one head per image {tb:.1f} us || bwd {tba:.1f} us | {tbb:.1f} us")
 x = qa.view(B, T, 36, 64)
 t_strided = timeit(lambda: x.permute(0, 2, 1, 3).contiguous())
 t_contig = timeit(lambda: qa.clone())
