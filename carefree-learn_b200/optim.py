@@ -249,7 +249,9 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _cabi.launch_count()
-        with torch.cuda.graph(self.graph):
+        # thread_local: only THIS thread is held to the capture rules -- a torch.distributed watchdog thread polling its own
+        # events (the process group that bootstrapped the communicator) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._eager()
         self.launches_per_replay = _cabi.launch_count() - n0  # b200 kernels inside one replay of the graph
         with torch.no_grad():
