@@ -1304,7 +1304,7 @@ using namespace b200;
 // or b200_set_attention_*_version(2) select the new kernels).
 static int g_attn_fwd_version = 1;
 static int g_attn_bwd_version = 1;
-static int g_attn_prefetch = 1;
+static int g_attn_prefetch = 0;  // measured neutral (tools/probe_layout.py: the kernels are not DRAM-pattern bound), kept as a switch
 
 static int attn_check(int B, int T, int H, int Dh) {
     if (B <= 0 || T <= 0 || H <= 0) return set_error(B200_ERR_ARG, "attention: non-positive size");

@@ -129,7 +129,7 @@ int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, 
 int b200_set_attention_fwd_version(int version);
 /* same for the backward kernel: 2 (default) = persistent, transposed scores, P^T / dS^T operands in tensor memory; 1 = round 1 */
 int b200_set_attention_bwd_version(int version);
-/* version-2 kernels: cooperative L2 prefetch of the next item's image as whole contiguous rows (1 = on, default); A/B switch */
+/* version-2 kernels: cooperative L2 prefetch of the next item's image as whole contiguous rows (default 0: measured neutral) */
 int b200_set_attention_prefetch(int enable);
 /* dbias_part (optional, f32 [B, 3*H*Dh]): per-image column sums of the bf16 dqkv rows written; summed over the batch
  * (b200_colsum_finish, nparts = B) they are the gradient of the packed qkv bias (attentions.py:112-119). */

