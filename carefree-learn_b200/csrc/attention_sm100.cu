@@ -923,12 +923,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 //   * ONE persistent CTA per SM walks over the items; every operand buffer (K|V per key tile, Q|dO per query tile) has
 //     its own full / empty barrier pair, so the next item's tiles stream in as soon as the current item has issued its
 //     last MMA on that buffer (K_0 / V_0 are free after the first key tile, ...): no load is ever exposed;
-//   * scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T (TMEM lane = key), in sub-tiles of 32 queries:
-//     a sub-tile's S^T | dP^T take 64 columns, so FOUR of them fit beside the four 64-column accumulators
-//     (dK, dV, dQ_0, dQ_1 = 256 columns) and S^T / dP^T run up to four sub-tiles ahead of the compute warps.  (The first
-//     cut used two 64-query buffers: ncu showed the compute warps waiting 40 % of their time for S^T | dP^T -- the hand-off
-//     compute -> MMA thread -> dV / dK / dQ -> S^T / dP^T -> compute costs ~1500 cycles against ~1000 cycles of compute
-//     per sub-tile, and a look-ahead of two cannot hide it; profiles/r02_ncu_attention_v2.md.)
+//   * scores are computed TRANSPOSED, S^T = K Q^T and dP^T = V dO^T (TMEM lane = key), in sub-tiles of 64 queries:
+//     a sub-tile's S^T | dP^T take 128 columns, so TWO of them fit beside the four 64-column accumulators
+//     (dK, dV, dQ_0, dQ_1 = 256 columns) and the tensor pipe works on sub-tile u+1 / u+2 while the compute warps are on u;
 //   * the compute warps (lane = key row, two threads per row) write P^T and dS^T back into their OWN S^T / dP^T columns as
 //     packed bf16 (tcgen05.st); dV += P^T dO and dK += dS^T Q read their A operand from tensor memory
 //     (tcgen05.mma [d], [a_tmem], b_desc), so P never touches shared memory and dS^T goes there only for dQ += dS K,
@@ -941,16 +938,14 @@ constexpr int B2_SQ = 0;           // 2 x 16 KB   query tiles
 constexpr int B2_SDO = 32768;      // 2 x 16 KB
 constexpr int B2_SK = 65536;       // 2 x 16 KB   key tiles
 constexpr int B2_SV = 98304;       // 2 x 16 KB
-constexpr int B2_SDS = 131072;     // 2 group buffers x 2 blocks x 16 KB: dS^T [128 keys][64 queries] bf16, 128 B rows, swizzled
+constexpr int B2_SDS = 131072;     // 2 pair buffers x 2 blocks x 16 KB: dS^T [128 keys][64 queries] bf16, 128 B rows, swizzled
 constexpr int B2_STG = 196608;     // 4 x 4 KB    epilogue staging
 constexpr int B2_LSE = B2_STG + 16384;          // [2 items][256] floats (lse * log2 e; +inf for padded queries)
 constexpr int B2_DELTA = B2_LSE + 2048;         // [2 items][256]
 constexpr int B2_CSUM = B2_DELTA + 2048;        // 24 x 64 floats: column sums of dQ / dK / dV per (tile, lane quadrant)
 constexpr int B2_BAR = B2_CSUM + 24 * 64 * 4;
 constexpr int B2_SMEM = B2_BAR + 256 + 1024;
-constexpr int B2_QS = 32;          // queries per sub-tile
-constexpr int B2_NBUF = 4;         // S^T | dP^T buffers in tensor memory
-constexpr uint32_t T2_BUF = 64;    // per S^T|dP^T buffer: S^T at +0, dP^T at +32
+constexpr uint32_t T2_BUF = 128;   // per S^T|dP^T buffer: S^T at +0, dP^T at +64
 constexpr uint32_t T2_DK = 256, T2_DV = 320, T2_DQ = 384;
 
 // staged rows -> global as in flush_rows64, plus the fp32 column sums of the bf16 values written (qkv-bias gradient)
@@ -993,20 +988,20 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     uint64_t* empty_q = full_q + 2;                                 // [2] ... no longer read by any MMA
     uint64_t* full_kv = full_q + 4;                                 // [2] K_kt | V_kt loaded
     uint64_t* empty_kv = full_q + 6;
-    uint64_t* bar_sdp = full_q + 8;                                 // [4] S^T | dP^T of the buffer's sub-tile are in TMEM
-    uint64_t* bar_pds = full_q + 12;                                // [4] P^T | dS^T written (8 compute warps)
-    uint64_t* bar_dsfree = full_q + 16;                             // [2] dS^T group buffer consumed by its dQ MMAs
-    uint64_t* bar_kv = full_q + 18;                                 // dK | dV of the key tile complete
-    uint64_t* bar_kvfree = full_q + 19;                             // ... and read out (4 epilogue warps)
-    uint64_t* bar_dq = full_q + 20;                                 // dQ of the item complete
-    uint64_t* bar_dqfree = full_q + 21;
-    uint64_t* bar_delta = full_q + 22;                              // [2] lse / delta of the item (parity buffer) in smem (4 epilogue warps)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(full_q + 24);
+    uint64_t* bar_sdp = full_q + 8;                                 // [2] S^T | dP^T of the buffer's sub-tile are in TMEM
+    uint64_t* bar_pds = full_q + 10;                                // [2] P^T | dS^T written (8 compute warps)
+    uint64_t* bar_dsfree = full_q + 12;                             // [2] dS^T pair buffer consumed by its dQ MMAs
+    uint64_t* bar_kv = full_q + 14;                                 // dK | dV of the key tile complete
+    uint64_t* bar_kvfree = full_q + 15;                             // ... and read out (4 epilogue warps)
+    uint64_t* bar_dq = full_q + 16;                                 // dQ of the item complete
+    uint64_t* bar_dqfree = full_q + 17;
+    uint64_t* bar_delta = full_q + 18;                              // [2] lse / delta of the item (parity buffer) in smem (4 epilogue warps)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(full_q + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_kt = (p.T + 127) / 128;          // key tiles == query tiles (pairs of 64-query sub-tiles)
-    const int n_qs = (p.tp + B2_QS - 1) / B2_QS; // 32-query sub-tiles
+    const int n_qs = (p.tp + 63) / 64;           // 64-query sub-tiles
     const int U = n_kt * n_qs;                   // sub-iterations per item
     const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const long long D3 = 3ll * p.D;
@@ -1019,12 +1014,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             mbar_init(&empty_q[i], 1);
             mbar_init(&full_kv[i], 1);
             mbar_init(&empty_kv[i], 1);
-            mbar_init(&bar_dsfree[i], 1);
-            mbar_init(&bar_delta[i], 4);
-        }
-        for (int i = 0; i < B2_NBUF; ++i) {
             mbar_init(&bar_sdp[i], 1);
             mbar_init(&bar_pds[i], 8);
+            mbar_init(&bar_dsfree[i], 1);
+            mbar_init(&bar_delta[i], 4);
         }
         mbar_init(bar_kv, 1);
         mbar_init(bar_kvfree, 4);
@@ -1074,64 +1067,67 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major (smem), B MN-major
             const int G = n_my * U;
             auto issue_sdp = [&](int g) {
-                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 2;
+                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
                 const uint32_t par = static_cast<uint32_t>(it & 1);
                 if (qs == 0) mbar_wait(&full_kv[kt], par);
-                if (kt == 0 && (qs & 3) == 0) mbar_wait(&full_q[mt], par);
+                if (kt == 0 && (qs & 1) == 0) mbar_wait(&full_q[mt], par);
                 tc_fence_after_sync();
-                const int nq = min(B2_QS, p.tp - qs * B2_QS);
+                const int nq = min(64, p.tp - qs * 64);
                 const uint32_t idesc_nn = make_idesc_bf16(128, static_cast<uint32_t>(nq), 0, 0);
                 const uint32_t k_base = smem_u32(smem + B2_SK + kt * 16384), v_base = smem_u32(smem + B2_SV + kt * 16384);
-                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 3) * 4096);     // 32 query rows x 128 B
-                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 3) * 4096);
-                const uint32_t d = tmem_base + static_cast<uint32_t>(g % B2_NBUF) * T2_BUF;
+                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t d = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16(d, make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
                               idesc_nn, kk > 0 ? 1u : 0u);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(d + 32, make_smem_desc(v_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
+                    umma_bf16(d + 64, make_smem_desc(v_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
                               idesc_nn, kk > 0 ? 1u : 0u);
-                umma_commit(&bar_sdp[g % B2_NBUF]);
+                umma_commit(&bar_sdp[g & 1]);
             };
-            // S^T / dP^T run up to FOUR sub-tiles ahead of the compute warps (buffer g % 4 is free again as soon as the dV / dK
-            // MMAs of sub-tile g have been issued: the tensor pipe executes in issue order).  Across an item boundary a
-            // sub-tile may only be issued once THIS thread has already committed the release of the operand buffers it needs
-            // (rel_kv / rel_q count the items whose buffer was released): waiting for loads that depend on a LATER commit
-            // of this same thread would deadlock.
-            int rel_kv[2] = {0, 0}, rel_q[2] = {0, 0};
+            // S^T / dP^T run up to two sub-iterations ahead of the compute warps.  Across an item boundary that is only possible
+            // when the next item's first tiles can already be resident, i.e. when the current item released K_0|V_0 and
+            // Q_0|dO_0 at least two sub-iterations before its end (two key tiles and >= 3 query sub-tiles, e.g. T = 197);
+            // otherwise the look-ahead stops at the boundary -- waiting there for loads that need a LATER commit of this
+            // thread would deadlock.
+            const bool cross = (n_kt == 2 && n_qs >= 3);
             int nxt = 0;
             auto pump = [&](int g_cur) {
-                while (nxt < G && nxt <= g_cur + B2_NBUF) {
-                    const int it2 = nxt / U, u2 = nxt - it2 * U, kt2 = u2 / n_qs, mt2 = (u2 - kt2 * n_qs) >> 2;
-                    if (rel_kv[kt2] < it2 || rel_q[mt2] < it2) break;
+                const int cur_item = g_cur < 0 ? 0 : g_cur / U;
+                const bool item_finished = g_cur >= 0 && (g_cur % U) == U - 1;
+                while (nxt < G && nxt <= g_cur + 2) {
+                    const int it2 = nxt / U;
+                    if (!cross && it2 > cur_item && !item_finished) break;
+                    if (!cross && it2 > cur_item + 1) break;
                     issue_sdp(nxt);
                     ++nxt;
                 }
             };
             pump(-1);
-            int pc = 0;   // dS^T groups (128 queries) completed so far (group buffer = pc & 1)
+            int pc = 0;   // dS^T pairs completed so far (pair buffer = pc & 1)
             int kc = 0;   // key tiles completed so far
             for (int g = 0; g < G; ++g) {
-                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 2;
-                const int nq = min(B2_QS, p.tp - qs * B2_QS);
+                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
+                const int nq = min(64, p.tp - qs * 64);
                 const int nk = min(128, p.tp - kt * 128);
-                const uint32_t buf = tmem_base + static_cast<uint32_t>(g % B2_NBUF) * T2_BUF;
-                mbar_wait(&bar_pds[g % B2_NBUF], static_cast<uint32_t>((g / B2_NBUF) & 1));
+                const uint32_t buf = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
+                mbar_wait(&bar_pds[g & 1], static_cast<uint32_t>((g >> 1) & 1));
                 if (qs == 0 && kc > 0) mbar_wait(bar_kvfree, static_cast<uint32_t>((kc - 1) & 1));  // dK / dV of the previous key tile read out
                 tc_fence_after_sync();
-                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 3) * 4096);
-                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 3) * 4096);
+                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
+                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
                 for (int kk = 0; kk < (nq >> 4); ++kk) {  // reduction over the queries of the sub-tile, 16 per step
                     // every 16-query chunk was written back, packed to 8 columns, at the START of its own 16 fp32 columns
                     const uint32_t acol = static_cast<uint32_t>(kk * 16);
                     const uint32_t acc = (qs > 0 || kk > 0) ? 1u : 0u;
                     umma_bf16_ts(tmem_base + T2_DV, buf + acol, make_smem_desc(do_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
-                    umma_bf16_ts(tmem_base + T2_DK, buf + 32 + acol, make_smem_desc(q_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
+                    umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, make_smem_desc(q_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
                 }
-                const bool group_done = (qs & 3) == 3 || qs == n_qs - 1;
-                if (group_done) {
+                const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
+                if (pair_done) {
                     if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
                     tc_fence_after_sync();
                     const uint32_t ds_base = smem_u32(smem + B2_SDS + (pc & 1) * 32768);
@@ -1141,15 +1137,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                                   make_smem_desc(k_base + kk * 2048, 0, 1024, kSwz128), idesc_dq, (kt > 0 || kk > 0) ? 1u : 0u);
                     umma_commit(&bar_dsfree[pc & 1]);
                     ++pc;
-                    if (kt == n_kt - 1) {  // last MMAs on Q_mt / dO_mt of this item
-                        umma_commit(&empty_q[mt]);
-                        ++rel_q[mt];
-                    }
+                    if (kt == n_kt - 1) umma_commit(&empty_q[mt]);  // last MMAs on Q_mt / dO_mt of this item
                 }
                 if (qs == n_qs - 1) {
                     umma_commit(bar_kv);
                     umma_commit(&empty_kv[kt]);
-                    ++rel_kv[kt];
                     ++kc;
                     if (kt == n_kt - 1) umma_commit(bar_dq);
                 }
@@ -1245,7 +1237,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     } else {
         // ===================================== compute warps ======================================
         const uint32_t q = static_cast<uint32_t>(warp & 3);
-        const int hf = (warp - 2) >> 2;                  // which 16-query chunk of the 32-query sub-tile this thread owns
+        const int hf = (warp - 2) >> 2;                  // which half of the sub-tile's query columns this thread owns
         const int r = static_cast<int>(q) * 32 + lane;   // key row inside the key tile == TMEM lane
         const uint32_t rsw = static_cast<uint32_t>(r) & 7u;
         const float sl2 = p.scale * kLog2e;
@@ -1253,70 +1245,72 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         int pc = 0;
         for (int g = 0; g < G; ++g) {
             const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs;
-            const int nq = min(B2_QS, p.tp - qs * B2_QS);
+            const int nq = min(64, p.tp - qs * 64);
             const int nk = min(128, p.tp - kt * 128);
-            const bool mine = hf * 16 < nq;                      // a 16-query sub-tile has no second chunk
+            const int nch = nq >> 4;                             // 16-column chunks in this sub-tile (1..4)
+            const int cb = hf ? (nch + 1) >> 1 : 0;              // this thread's chunks [cb, ce)
+            const int ce = hf ? nch : (nch + 1) >> 1;
             const bool dead = static_cast<int>(q) * 32 >= nk;    // all 32 key rows of this warp lie outside the (padded) key tile
             const int j = kt * 128 + r;                          // key index
             const float* lse_s = reinterpret_cast<const float*>(smem + B2_LSE) + (it & 1) * 256;
             const float* delta_s = reinterpret_cast<const float*>(smem + B2_DELTA) + (it & 1) * 256;
-            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(g % B2_NBUF) * T2_BUF + static_cast<uint32_t>(hf * 16);
-            // dS^T tile: group buffer, 64-query block, key row; this chunk = 32 bytes at query offset (qs & 1) * 32 + hf * 16
-            uint8_t* blk = smem + B2_SDS + (pc & 1) * 32768 + ((qs >> 1) & 1) * 16384 + r * 128;
-            const uint32_t c16 = static_cast<uint32_t>((qs & 1) * 4 + hf * 2);
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(g & 1) * T2_BUF;
+            uint8_t* blk = smem + B2_SDS + (pc & 1) * 32768 + (qs & 1) * 16384 + r * 128;
             if (u == 0) mbar_wait(&bar_delta[it & 1], static_cast<uint32_t>((it >> 1) & 1));
-            if ((qs & 3) == 0 && pc >= 2) mbar_wait(&bar_dsfree[pc & 1], static_cast<uint32_t>(((pc >> 1) - 1) & 1));  // group buffer consumed by its dQ MMAs
-            mbar_wait(&bar_sdp[g % B2_NBUF], static_cast<uint32_t>((g / B2_NBUF) & 1));
+            if ((qs & 1) == 0 && pc >= 2) mbar_wait(&bar_dsfree[pc & 1], static_cast<uint32_t>(((pc >> 1) - 1) & 1));  // pair buffer consumed by its dQ MMAs
+            mbar_wait(&bar_sdp[g & 1], static_cast<uint32_t>((g >> 1) & 1));
             tc_fence_after_sync();
-            if (!dead && mine) {
-                uint32_t sv[16], dv[16];
-                tmem_ld_32x32b_x16(taddr, sv);
-                tmem_ld_32x32b_x16(taddr + 32, dv);
-                const int i0 = qs * B2_QS + hf * 16;  // first query of the chunk
-                float ls[16], dl[16];
+            if (!dead) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(lse_s + i0 + k4 * 4);
-                    const float4 d4 = *reinterpret_cast<const float4*>(delta_s + i0 + k4 * 4);
-                    ls[k4 * 4 + 0] = a4.x; ls[k4 * 4 + 1] = a4.y; ls[k4 * 4 + 2] = a4.z; ls[k4 * 4 + 3] = a4.w;
-                    dl[k4 * 4 + 0] = d4.x; dl[k4 * 4 + 1] = d4.y; dl[k4 * 4 + 2] = d4.z; dl[k4 * 4 + 3] = d4.w;
-                }
-                tmem_ld_wait();
-                float pv[16], ds[16];
-                if (!p.causal && kt * 128 + static_cast<int>(q) * 32 + 32 <= p.T) {  // warp-uniform: every key of this warp is valid
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = cb + cc;
+                    if (c < ce) {  // warp-uniform
+                        uint32_t sv[16], dv[16];
+                        // this thread's columns: chunk c of the sub-tile lives at S^T / dP^T column c * 16
+                        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), sv);
+                        tmem_ld_32x32b_x16(taddr + 64 + static_cast<uint32_t>(c * 16), dv);
+                        const int i0 = qs * 64 + c * 16;  // first query of the chunk
+                        float ls[16], dl[16];
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        pv[jj] = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
-                        ds[jj] = pv[jj] * (__uint_as_float(dv[jj]) - dl[jj]);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 a = *reinterpret_cast<const float4*>(lse_s + i0 + k4 * 4);
+                            const float4 d4 = *reinterpret_cast<const float4*>(delta_s + i0 + k4 * 4);
+                            ls[k4 * 4 + 0] = a.x; ls[k4 * 4 + 1] = a.y; ls[k4 * 4 + 2] = a.z; ls[k4 * 4 + 3] = a.w;
+                            dl[k4 * 4 + 0] = d4.x; dl[k4 * 4 + 1] = d4.y; dl[k4 * 4 + 2] = d4.z; dl[k4 * 4 + 3] = d4.w;
+                        }
+                        tmem_ld_wait();
+                        float pv[16], ds[16];
+                        const bool keyok = j < p.T;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
+                            const bool ok = keyok && (!p.causal || j <= i0 + jj);
+                            pv[jj] = ok ? e : 0.f;
+                            ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - dl[jj]) : 0.f;
+                        }
+                        uint32_t pk[8], dk[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
+                            dk[jj] = pack_bf16x2(ds[2 * jj], ds[2 * jj + 1]);
+                        }
+                        // packed values over the first 8 of the chunk's OWN 16 columns: no other thread's unread S^T / dP^T is touched
+                        const uint32_t ocol = static_cast<uint32_t>(c * 16);
+                        tmem_st_32x32b_x8(taddr + ocol, pk);
+                        tmem_st_32x32b_x8(taddr + 64 + ocol, dk);
+                        // dS^T[key r][queries i0 .. i0+16) -> 32 bytes of the [key][query] tile (swizzled 16-byte chunks)
+                        const uint32_t c16 = static_cast<uint32_t>(c * 2);
+                        *reinterpret_cast<uint4*>(blk + ((c16 ^ rsw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                        *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ rsw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
                     }
-                } else {
-                    const bool keyok = j < p.T;
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
-                        const bool ok = keyok && (!p.causal || j <= i0 + jj);
-                        pv[jj] = ok ? e : 0.f;
-                        ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - dl[jj]) : 0.f;
-                    }
                 }
-                uint32_t pk[8], dk[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
-                    dk[jj] = pack_bf16x2(ds[2 * jj], ds[2 * jj + 1]);
-                }
-                // packed values over the first 8 of the chunk's OWN 16 columns: no other thread's unread S^T / dP^T is touched
-                tmem_st_32x32b_x8(taddr, pk);
-                tmem_st_32x32b_x8(taddr + 32, dk);
-                *reinterpret_cast<uint4*>(blk + ((c16 ^ rsw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-                *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ rsw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
                 tmem_st_wait();
             }
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_pds[g % B2_NBUF]);
-            if ((qs & 3) == 3 || qs == n_qs - 1) ++pc;
+            if (lane == 0) mbar_arrive(&bar_pds[g & 1]);
+            if ((qs & 1) == 1 || qs == n_qs - 1) ++pc;
         }
     }
     __syncwarp();
@@ -1332,10 +1326,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
 using namespace b200;
 
-// Defaults stay on the round-1 kernels until version 2 has passed its GPU tests on a B200 (B200_ATTN_FWD / B200_ATTN_BWD = 2
-// or b200_set_attention_*_version(2) select the new kernels).
-static int g_attn_fwd_version = 1;
-static int g_attn_bwd_version = 1;
+// 0 = choose per shape (measured on a B200, profiles/r02_op_bench_attention.txt): the persistent version-2 kernels win when
+// an item has two query tiles (T > 128: forward 113 us vs 133 us, backward 338 us vs 357 us at B256 T197 H12); with a single,
+// mostly padded tile (CLIP: T = 77 / 50) the per-item pipeline hand-offs cost more than version 1's 3-CTAs-per-SM occupancy
+// hides (41.6 us vs 34.5 us, 52.2 us vs 42.0 us).  B200_ATTN_FWD / B200_ATTN_BWD = 1 | 2 or b200_set_attention_*_version
+// force one kernel (A/B timing, tests of both).
+static int g_attn_fwd_version = 0;
+static int g_attn_bwd_version = 0;
+static inline int attn_pick(int forced, int T) { return forced != 0 ? forced : (T > 128 ? 2 : 1); }
 static int g_attn_prefetch = 0;  // measured neutral (tools/probe_layout.py: the kernels are not DRAM-pattern bound), kept as a switch
 
 static int attn_check(int B, int T, int H, int Dh) {
@@ -1370,7 +1368,7 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = tp; p.scale = scale; p.causal = causal;
     p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = nullptr; p.do_base = nullptr;
     const int n_mt = (T + 127) / 128;
-    if (g_attn_fwd_version == 1) {
+    if (attn_pick(g_attn_fwd_version, T) == 1) {
         attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
     } else {
         const int n_items = B * H;
@@ -1380,11 +1378,11 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
     return check_launch("attention_fwd");
 }
 
-// 2 (default): persistent pipelined forward with P in tensor memory; 1: the round-1 kernel (A/B timing, same results up to
-// the summation order of the row sums)
+// 0 (default): per shape; 2: persistent pipelined forward with P in tensor memory; 1: the round-1 kernel (same results up to
+// the summation order of the row sums).  Returns the previous setting.
 extern "C" int b200_set_attention_fwd_version(int version) {
     const int old = g_attn_fwd_version;
-    g_attn_fwd_version = version == 1 ? 1 : 2;
+    g_attn_fwd_version = (version == 1 || version == 2) ? version : 0;
     return old;
 }
 
@@ -1418,7 +1416,7 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
     p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = out_bf16; p.do_base = dout_bf16;
-    if (g_attn_bwd_version == 1) {
+    if (attn_pick(g_attn_bwd_version, T) == 1) {
         attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                                 reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
@@ -1438,9 +1436,10 @@ extern "C" int b200_set_attention_prefetch(int enable) {
     return old;
 }
 
-// 2 (default): persistent backward with transposed scores and P^T / dS^T operands in tensor memory; 1: the round-1 kernel
+// 0 (default): per shape; 2: persistent backward with transposed scores and P^T / dS^T operands in tensor memory; 1: the
+// round-1 kernel.  Returns the previous setting.
 extern "C" int b200_set_attention_bwd_version(int version) {
     const int old = g_attn_bwd_version;
-    g_attn_bwd_version = version == 1 ? 1 : 2;
+    g_attn_bwd_version = (version == 1 || version == 2) ? version : 0;
     return old;
 }

@@ -38,6 +38,8 @@ class ArenaAdam(torch.optim.Optimizer):
         self.step_dev: Optional[Tensor] = None
         self.hyper_dev: Optional[Tensor] = None
         self._hyper_host: Optional[Tensor] = None
+        self._hyper_events: List[Any] = []
+        self._hyper_slot = -1
         self._hyper_sent: Optional[tuple] = None
         self._clip_dev: Optional[Tensor] = None  # when set: grad_scale lives on the device only (clip_grad_norm_)
         # one (exp_avg, exp_avg_sq) pair per parameter arena: a ViT / classifier has one arena, CLIP three (vision tower,
@@ -96,9 +98,18 @@ class ArenaAdam(torch.optim.Optimizer):
             return
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("ArenaAdam.sync_hyper() must run outside the capture (it is a host-to-device copy of new values)")
-        self._hyper_host.copy_(torch.tensor(cur, dtype=torch.float32))
+        # the copy is asynchronous: a pinned row may only be rewritten once the copy that read it has run (the host can be
+        # many replays ahead of the device), so the rows form a ring and each carries the event of its last copy
+        slot = self._hyper_slot = (self._hyper_slot + 1) % self._hyper_host.shape[0]
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        row = self._hyper_host[slot]
+        row.copy_(torch.tensor(cur, dtype=torch.float32))
         n = 5 if self._clip_dev is not None else 6  # with clipping on, slot 5 (grad_scale) is written on the device every step
-        self.hyper_dev[:n].copy_(self._hyper_host[:n], non_blocking=True)
+        self.hyper_dev[:n].copy_(row[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_events[slot] = ev
         self._hyper_sent = cur
 
     # ---- state --------------------------------------------------------------------------------------------------
@@ -113,7 +124,9 @@ class ArenaAdam(torch.optim.Optimizer):
             if self.capturable:
                 self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=dev)
                 self.hyper_dev = torch.zeros(6, dtype=torch.float32, device=dev)
-                self._hyper_host = torch.zeros(6, dtype=torch.float32).pin_memory()
+                self._hyper_host = torch.zeros(8, 6, dtype=torch.float32).pin_memory()
+                self._hyper_events = [None] * 8
+                self._hyper_slot = -1
                 self._hyper_sent = None
         if self.capturable and not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()

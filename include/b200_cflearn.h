@@ -124,10 +124,12 @@ int b200_colsum_finish2(const float* part, long long part_ld, int nparts, int co
  * --------------------------------------------------------------------------------------------------------- */
 int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, int T, int H, int Dh, float scale,
                        int causal, cudaStream_t stream);
-/* forward kernel version: 2 (default) = persistent, warp-specialised, probabilities kept in tensor memory; 1 = the
- * round-1 kernel (one CTA per query tile).  Returns the previous setting.  For A/B timing; results agree to fp32 rounding. */
+/* forward kernel version: 0 (default) = chosen per shape (2 when T > 128, else 1); 2 = persistent, warp-specialised,
+ * probabilities kept in tensor memory; 1 = the round-1 kernel (one CTA per query tile).  Returns the previous setting.
+ * For A/B timing and tests of both kernels; results agree to fp32 rounding. */
 int b200_set_attention_fwd_version(int version);
-/* same for the backward kernel: 2 (default) = persistent, transposed scores, P^T / dS^T operands in tensor memory; 1 = round 1 */
+/* same for the backward kernel: 0 (default) = per shape; 2 = persistent, transposed scores, P^T / dS^T operands in tensor
+ * memory; 1 = round 1 */
 int b200_set_attention_bwd_version(int version);
 /* version-2 kernels: cooperative L2 prefetch of the next item's image as whole contiguous rows (default 0: measured neutral) */
 int b200_set_attention_prefetch(int enable);

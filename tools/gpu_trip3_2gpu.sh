@@ -2,7 +2,9 @@
 # round-2 trip 3 (2 GPUs): data-parallel parity through the library-owned NCCL communicator (eager / graphed / flat) and the
 # three gradient-exchange schedules of bench.py
 mkdir -p gpurun_out
-export B200_ATTN_FWD=${B200_ATTN_FWD:-2} B200_ATTN_BWD=${B200_ATTN_BWD:-2}
+timeout 300 python tools/probe_trainer_seam.py > gpurun_out/r02_probe_trainer_seam.txt 2>&1; echo "probe seam rc=$?"; cut -c1-420 gpurun_out/r02_probe_trainer_seam.txt | tail -7
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -k "attention" > gpurun_out/pytest_attn.log 2>&1; echo "attention tests rc=$?"; tail -2 gpurun_out/pytest_attn.log
+timeout 300 python tools/op_bench.py attn > gpurun_out/r02_op_bench_attn_auto.txt 2>&1; cat gpurun_out/r02_op_bench_attn_auto.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541"
 timeout 600 $TR tools/dp_check.py > gpurun_out/r02_dp_check.log 2>&1; echo "dp_check rc=$?"; tail -4 gpurun_out/r02_dp_check.log
 for mode in graph flat torch; do
