@@ -69,6 +69,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_cast_f32_to_bf16": (c_int, [_P, _P, _LL, _P]),
     "b200_fill_f32": (c_int, [_P, c_float, _LL, _P]),
     "b200_conv3x3_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "b200_conv3x3_wgrad_nhwc_bf16": (c_int, [_P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_groupnorm_workspace_floats": (_LL, [c_int, c_int, c_int]),
     "b200_groupnorm_silu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P]),
     "b200_groupnorm_silu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -104,7 +105,7 @@ def _load() -> None:
             lib.b200_set_attention_fwd_version(int(os.environ["B200_ATTN_FWD"]))
         if os.environ.get("B200_ATTN_PREFETCH", "") in ("0", "1"):
             lib.b200_set_attention_prefetch(int(os.environ["B200_ATTN_PREFETCH"]))
-        if os.environ.get("B200_ATTN_BWD", "") in ("1", "2"):
+        if os.environ.get("B200_ATTN_BWD", "") in ("1", "2", "3"):
             lib.b200_set_attention_bwd_version(int(os.environ["B200_ATTN_BWD"]))
         if os.environ.get("B200_GEMM_MULTICAST", "") in ("0", "1", "2"):  # A/B/C switch for profiling; results are identical
             lib.b200_set_gemm_multicast(int(os.environ["B200_GEMM_MULTICAST"]))

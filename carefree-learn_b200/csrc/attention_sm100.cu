@@ -373,77 +373,87 @@ __device__ __forceinline__ void flush_rows64(const uint8_t* stage, __nv_bfloat16
     __syncwarp();
 }
 
-// One thread's share of the softmax of a unit: N chunks of 16 score columns starting at chunk `cb` of TMEM row `taddr`, kept
-// in registers (ONE pass over tensor memory).  Straight-line code for a compile-time N -- the first cut looped over
-// `if (c < nmine)` branches and serial max / sum chains: ncu showed the softmax warps (the critical path, 2 per scheduler)
-// at one instruction per ~8 cycles, 34 % fixed-latency dependency stalls and 16 % instruction-cache misses on a 35 KB body.
-// Four independent max / sum accumulators break the dependency chains; MODE selects the masking that is compiled in:
-// 0 = none, 1 = only the last chunk crosses T, 2 = every chunk (causal).
-template <int N, int MODE>
-__device__ __forceinline__ void softmax_unit(const uint32_t taddr, const int cb, const int nvalid, const float sl2, float* stats,
-                                             const int hf, const int r) {
-    uint32_t v[N][16];
-#pragma unroll
-    for (int c = 0; c < N; ++c) tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v[c]);
-    tmem_ld_wait();
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-        constexpr bool kAll = MODE == 2;
-        const bool masked = kAll || (MODE == 1 && c == N - 1);
+// One thread's share of the softmax of a unit: `n` chunks of 16 score columns starting at chunk `cb` of TMEM row `taddr`.
+// TWO passes over tensor memory (row max, then exp / sum / pack) as real loops with a ~100-instruction body.  History: the first
+// cut kept the row in registers with `if (c < nmine)` branches (35 KB body, serial max / sum chains); the second cut was
+// straight-line code per compile-time chunk count -- 15 000 SASS instructions (240 KB) for the kernel, and ncu showed the
+// softmax warps, which ARE the critical path, at one instruction per ~5.5 cycles with `no instruction` (I-cache miss) as the top
+// stall.  Tensor memory is read twice instead (16 TB/s: free), the loops stay resident in the instruction cache, the max uses
+// the 3-input max, and scale / subtract / sum run on the packed fp32x2 pipe.
+// P goes back over the thread's OWN score columns: packed chunk c -> columns (cb * 16 + c * 8 ...), inside S chunk cb + c / 2,
+// which this thread has already consumed when it stores (ascending c) -- no other thread's unread scores are touched, so the
+// only cross-thread step is the exchange of the two half-row maxima.  The PV MMA addresses the two P regions separately.
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void softmax_rows(const int n, const uint32_t taddr, const int cb, const int nvalid, const int nvalid_warp_min,
+                                             const float sl2, float* stats, const int hf, const int r) {
+    // ---- pass 1: row max over this thread's columns
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
+        tmem_ld_wait();
         const int col0 = (cb + c) * 16;
+        if (col0 + 16 <= nvalid_warp_min) {  // warp-uniform: no masking in this chunk
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            float a = __uint_as_float(v[c][jj]);
-            if (masked) a = (col0 + jj < nvalid) ? a : -INFINITY;
-            mx[jj & 3] = fmaxf(mx[jj & 3], a);
+            for (int jj = 0; jj < 16; jj += 4) {
+                mx0 = max3(mx0, __uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+                mx1 = max3(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float a = (col0 + jj < nvalid) ? __uint_as_float(v[jj]) : -INFINITY;
+                if (jj & 1) mx1 = fmaxf(mx1, a); else mx0 = fmaxf(mx0, a);
+            }
         }
     }
-    float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    float m = fmaxf(mx0, mx1);
     stats[hf * 128 + r] = m;
-    // every S column of this slot has been read into registers once all 256 threads pass this barrier: only then may the
-    // (other half's) P columns overwrite them
-    tc_fence_before_sync();
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    tc_fence_after_sync();
     m = fmaxf(stats[r], stats[128 + r]);
-    const float m2 = m * sl2;
-    float sm[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-        constexpr bool kAll = MODE == 2;
-        const bool masked = kAll || (MODE == 1 && c == N - 1);
+    // ---- pass 2: p = exp2(s * sl2 - m * sl2), row sum, bf16 pack, store over the consumed columns
+    const f32x2_t sl22 = pk2(sl2, sl2);
+    const float nm2 = -m * sl2;
+    const f32x2_t nm22 = pk2(nm2, nm2);
+    f32x2_t sum2a = pk2(0.f, 0.f), sum2b = pk2(0.f, 0.f);
+    const uint32_t pbase = taddr + static_cast<uint32_t>(cb * 16);
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
+        tmem_ld_wait();
         const int col0 = (cb + c) * 16;
-        float pv[16];
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            float e = fast_ex2(fmaf(__uint_as_float(v[c][jj]), sl2, -m2));
-            if (masked) e = (col0 + jj < nvalid) ? e : 0.f;
-            pv[jj] = e;
-            sm[jj & 3] += e;
-        }
+        const bool full = col0 + 16 <= nvalid_warp_min;
         uint32_t pk[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
-        tmem_st_32x32b_x8(taddr + static_cast<uint32_t>((cb + c) * 8), pk);  // P[row, col0 .. col0+16) -> 8 packed columns
+        for (int jj = 0; jj < 16; jj += 2) {
+            float x0, x1;
+            upk2(fma2(pk2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1])), sl22, nm22), x0, x1);
+            float e0 = fast_ex2(x0), e1 = fast_ex2(x1);
+            if (!full) {
+                if (col0 + jj >= nvalid) e0 = 0.f;
+                if (col0 + jj + 1 >= nvalid) e1 = 0.f;
+            }
+            if (jj & 2) sum2b = add2(sum2b, pk2(e0, e1)); else sum2a = add2(sum2a, pk2(e0, e1));
+            pk[jj >> 1] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x32b_x8(pbase + static_cast<uint32_t>(c * 8), pk);  // P[row, col0 .. col0+16) -> 8 packed columns
     }
     tmem_st_wait();
-    stats[256 + hf * 128 + r] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+    float s0, s1;
+    upk2(add2(sum2a, sum2b), s0, s1);
+    stats[256 + hf * 128 + r] = s0 + s1;
     if (hf == 0) stats[512 + r] = m;
-}
-template <int MODE>
-__device__ __forceinline__ void softmax_dispatch(const int n, const uint32_t taddr, const int cb, const int nvalid, const float sl2,
-                                                 float* stats, const int hf, const int r) {
-    switch (n) {
-        case 1: softmax_unit<1, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 2: softmax_unit<2, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 3: softmax_unit<3, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 4: softmax_unit<4, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 5: softmax_unit<5, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 6: softmax_unit<6, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        case 7: softmax_unit<7, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-        default: softmax_unit<8, MODE>(taddr, cb, nvalid, sl2, stats, hf, r); break;
-    }
 }
 
 __global__ void __launch_bounds__(F2_THREADS, 1)
@@ -518,6 +528,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const uint32_t idesc_s = make_idesc_bf16(128, static_cast<uint32_t>(p.tp), 0, 0);
                 const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
                 const int nkk = p.tp / 16;
+                const int nc0 = (nkk + 1) / 2;  // chunks of the first half-row thread (see the softmax warps)
+                const uint64_t dsc_v = make_smem_desc(smem_u32(smem + F2_V), 0, 1024, kSwz128);
                 auto issue_s = [&](int j) {
                     const int it = n_mt == 2 ? (j >> 1) : j, mt = n_mt == 2 ? (j & 1) : 0, s = it & 1, slot = j & 1, k = j >> 1;
                     if (mt == 0) mbar_wait(&full_bar[s], static_cast<uint32_t>((it >> 1) & 1));
@@ -538,11 +550,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     const int it = n_mt == 2 ? (j >> 1) : j, s = it & 1, slot = j & 1, k = j >> 1;
                     mbar_wait(&bar_p[slot], static_cast<uint32_t>(k & 1));
                     tc_fence_after_sync();
-                    const uint32_t v_base = smem_u32(smem + s * F2_STAGE + F2_V);
                     const uint32_t base = tmem_base + static_cast<uint32_t>(slot) * F2_SLOT_COLS;
-                    for (int kk = 0; kk < nkk; ++kk)  // A = P[128 x 16] from TMEM (8 packed columns per k-step), B = V MN-major
-                        umma_bf16_ts(base + F2_O_COL, base + static_cast<uint32_t>(kk * 8), make_smem_desc(v_base + kk * 2048, 0, 1024, kSwz128),
+                    // A = P[128 x 16] from TMEM (8 packed columns per k-step), B = V MN-major.  The two half-row threads of the
+                    // softmax each wrote their packed chunks at the start of their own score columns (softmax_rows):
+                    // k-steps [0, nc0) at column kk * 8, k-steps [nc0, nkk) at column nc0 * 16 + (kk - nc0) * 8.
+                    for (int kk = 0; kk < nkk; ++kk) {
+                        const uint32_t pcol = static_cast<uint32_t>(kk < nc0 ? kk * 8 : nc0 * 8 + kk * 8);
+                        umma_bf16_ts(base + F2_O_COL, base + pcol, desc_off(dsc_v, static_cast<uint32_t>(s) * (F2_STAGE >> 4) + kk * 128),
                                      idesc_o, kk > 0 ? 1u : 0u);
+                    }
                     umma_commit(&bar_o[slot]);
                     if (j + 2 < n_units) issue_s(j + 2);  // runs under the softmax of unit j+1
                 }
@@ -603,17 +619,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_after_sync();
             if (dead || nmine == 0) {  // no columns of this thread take part: keep the exchange / barrier protocol only
                 stats[hf * 128 + r] = -INFINITY;
-                tc_fence_before_sync();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                tc_fence_after_sync();
                 stats[256 + hf * 128 + r] = 0.f;
                 if (hf == 0) stats[512 + r] = fmaxf(stats[r], stats[128 + r]);
-            } else if (p.causal) {
-                softmax_dispatch<2>(nmine, taddr, cb, nvalid, sl2, stats, hf, r);
-            } else if ((cb + nmine) * 16 <= p.T) {  // warp-uniform: all of this thread's chunks are fully valid
-                softmax_dispatch<0>(nmine, taddr, cb, nvalid, sl2, stats, hf, r);
-            } else {                               // only the last chunk of the row crosses T
-                softmax_dispatch<1>(nmine, taddr, cb, nvalid, sl2, stats, hf, r);
+            } else {
+                // columns below nvalid_min need no mask for ANY row of this warp (causal: the warp's first row sees the fewest keys)
+                const int row_first = mt * 128 + static_cast<int>(q) * 32;
+                const int nvalid_min = p.causal ? min(p.T, row_first + 1) : p.T;
+                softmax_rows(nmine, taddr, cb, nvalid, nvalid_min, sl2, stats, hf, r);
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -976,6 +989,74 @@ __device__ __forceinline__ void flush_rows64_colsum(const uint8_t* stage, __nv_b
     __syncwarp();
 }
 
+// one 16-query chunk of a sub-tile for one key row: S^T / dP^T (fp32, tensor memory) -> P^T / dS^T (packed bf16, written back
+// over the chunk's own columns) and dS^T -> shared memory.  nls / ndl hold -lse * log2(e) and -delta of the item's queries.
+// The arithmetic runs two queries at a time on the packed fp32x2 pipe (fma.rn.f32x2 / mul.rn.f32x2).
+template <bool MASK>
+__device__ __forceinline__ void bwd2_chunk(uint32_t taddr, int c, const float* nls, const float* ndl, int i0, float sl2,
+                                           bool keyok, bool causal, int j, uint8_t* blk, uint32_t rsw) {
+    uint32_t sv[16], dv[16];
+    // this thread's columns: chunk c of the sub-tile lives at S^T / dP^T column c * 16
+    tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), sv);
+    tmem_ld_32x32b_x16(taddr + 64 + static_cast<uint32_t>(c * 16), dv);
+    float4 la[4], da[4];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+        la[k4] = *reinterpret_cast<const float4*>(nls + i0 + k4 * 4);
+        da[k4] = *reinterpret_cast<const float4*>(ndl + i0 + k4 * 4);
+    }
+    tmem_ld_wait();
+    const f32x2_t sl22 = pk2(sl2, sl2), one2 = pk2(1.0f, 1.0f);
+    uint32_t pk[8], dk[8];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int jj = k4 * 4 + h2 * 2;
+            const f32x2_t l2 = h2 == 0 ? pk2(la[k4].x, la[k4].y) : pk2(la[k4].z, la[k4].w);
+            const f32x2_t d2 = h2 == 0 ? pk2(da[k4].x, da[k4].y) : pk2(da[k4].z, da[k4].w);
+            float x0, x1;
+            upk2(fma2(pk2(__uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1])), sl22, l2), x0, x1);
+            float e0 = fast_ex2(x0), e1 = fast_ex2(x1);
+            if (MASK) {
+                if (!(keyok && (!causal || j <= i0 + jj))) e0 = 0.f;
+                if (!(keyok && (!causal || j <= i0 + jj + 1))) e1 = 0.f;
+            }
+            const f32x2_t e2 = pk2(e0, e1);
+            float g0, g1;
+            upk2(mul2(e2, fma2(pk2(__uint_as_float(dv[jj]), __uint_as_float(dv[jj + 1])), one2, d2)), g0, g1);  // e (dP - delta)
+            pk[jj >> 1] = pack_bf16x2(e0, e1);
+            dk[jj >> 1] = pack_bf16x2(g0, g1);
+        }
+    }
+    // packed values over the first 8 of the chunk's OWN 16 columns: no other thread's unread S^T / dP^T is touched
+    const uint32_t ocol = static_cast<uint32_t>(c * 16);
+    tmem_st_32x32b_x8(taddr + ocol, pk);
+    tmem_st_32x32b_x8(taddr + 64 + ocol, dk);
+    // dS^T[key r][queries i0 .. i0+16) -> 32 bytes of the [key][query] tile (swizzled 16-byte chunks)
+    const uint32_t c16 = static_cast<uint32_t>(c * 2);
+    *reinterpret_cast<uint4*>(blk + ((c16 ^ rsw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+    *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ rsw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+}
+
+// walks the (item, key tile, query sub-tile) units of this CTA without divisions (the MMA thread issues ~30 instructions per
+// unit on a single lane: every integer division on that path showed up as tensor-pipe idle time)
+struct B2Cur {
+    int g, it, kt, qs;
+    __device__ __forceinline__ void advance(int n_kt, int n_qs) {
+        ++g;
+        if (++qs == n_qs) {
+            qs = 0;
+            if (++kt == n_kt) { kt = 0; ++it; }
+        }
+    }
+};
+
+// PP: the eight compute warps work as TWO groups of four (one warp per scheduler each); group 0 owns the sub-tiles in buffer 0,
+// group 1 those in buffer 1.  While one group waits for its next S^T | dP^T (its P^T / dS^T must first be consumed by dV / dK,
+// then the tensor pipe produces the new scores: ~1500 cycles), the other group has the issue slots to itself.  !PP keeps the
+// first cut's schedule (all eight warps on one sub-tile, two threads per key row) for A/B timing.
+template <bool PP>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                  const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
@@ -1015,7 +1096,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             mbar_init(&full_kv[i], 1);
             mbar_init(&empty_kv[i], 1);
             mbar_init(&bar_sdp[i], 1);
-            mbar_init(&bar_pds[i], 8);
+            mbar_init(&bar_pds[i], PP ? 4 : 8);
             mbar_init(&bar_dsfree[i], 1);
             mbar_init(&bar_delta[i], 4);
         }
@@ -1066,27 +1147,29 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             const uint32_t idesc_ts = make_idesc_bf16(128, 64, 0, 1);   // dV, dK : A from TMEM (K-major), B MN-major
             const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // dQ     : A MN-major (smem), B MN-major
             const int G = n_my * U;
-            auto issue_sdp = [&](int g) {
-                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
-                const uint32_t par = static_cast<uint32_t>(it & 1);
-                if (qs == 0) mbar_wait(&full_kv[kt], par);
-                if (kt == 0 && (qs & 1) == 0) mbar_wait(&full_q[mt], par);
+            // descriptor bases: a 128-byte-row swizzled tile is read K-major (S^T, dP^T) and MN-major (dV, dK, dQ) with the same fields
+            const uint64_t dsc_k = make_smem_desc(smem_u32(smem + B2_SK), 0, 1024, kSwz128);
+            const uint64_t dsc_v = make_smem_desc(smem_u32(smem + B2_SV), 0, 1024, kSwz128);
+            const uint64_t dsc_q = make_smem_desc(smem_u32(smem + B2_SQ), 0, 1024, kSwz128);
+            const uint64_t dsc_do = make_smem_desc(smem_u32(smem + B2_SDO), 0, 1024, kSwz128);
+            const uint64_t dsc_ds = make_smem_desc(smem_u32(smem + B2_SDS), 16384, 1024, kSwz128);
+            auto issue_sdp = [&](const B2Cur& c) {
+                const uint32_t par = static_cast<uint32_t>(c.it & 1);
+                if (c.qs == 0) mbar_wait(&full_kv[c.kt], par);
+                if (c.kt == 0 && (c.qs & 1) == 0) mbar_wait(&full_q[c.qs >> 1], par);
                 tc_fence_after_sync();
-                const int nq = min(64, p.tp - qs * 64);
+                const int nq = min(64, p.tp - c.qs * 64);
                 const uint32_t idesc_nn = make_idesc_bf16(128, static_cast<uint32_t>(nq), 0, 0);
-                const uint32_t k_base = smem_u32(smem + B2_SK + kt * 16384), v_base = smem_u32(smem + B2_SV + kt * 16384);
-                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
-                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
-                const uint32_t d = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
+                const uint32_t kv_off = static_cast<uint32_t>(c.kt) * 1024u;   // 16 KB per key tile
+                const uint32_t q_off = static_cast<uint32_t>(c.qs) * 512u;     // 8 KB per 64-query sub-tile (two per query tile)
+                const uint32_t d = tmem_base + static_cast<uint32_t>(c.g & 1) * T2_BUF;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(d, make_smem_desc(k_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(q_base + kk * 32, 0, 1024, kSwz128),
-                              idesc_nn, kk > 0 ? 1u : 0u);
+                    umma_bf16(d, desc_off(dsc_k, kv_off + kk * 2), desc_off(dsc_q, q_off + kk * 2), idesc_nn, kk > 0 ? 1u : 0u);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(d + 64, make_smem_desc(v_base + kk * 32, 0, 1024, kSwz128), make_smem_desc(do_base + kk * 32, 0, 1024, kSwz128),
-                              idesc_nn, kk > 0 ? 1u : 0u);
-                umma_commit(&bar_sdp[g & 1]);
+                    umma_bf16(d + 64, desc_off(dsc_v, kv_off + kk * 2), desc_off(dsc_do, q_off + kk * 2), idesc_nn, kk > 0 ? 1u : 0u);
+                umma_commit(&bar_sdp[c.g & 1]);
             };
             // S^T / dP^T run up to two sub-iterations ahead of the compute warps.  Across an item boundary that is only possible
             // when the next item's first tiles can already be resident, i.e. when the current item released K_0|V_0 and
@@ -1094,47 +1177,48 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             // otherwise the look-ahead stops at the boundary -- waiting there for loads that need a LATER commit of this
             // thread would deadlock.
             const bool cross = (n_kt == 2 && n_qs >= 3);
-            int nxt = 0;
-            auto pump = [&](int g_cur) {
-                const int cur_item = g_cur < 0 ? 0 : g_cur / U;
-                const bool item_finished = g_cur >= 0 && (g_cur % U) == U - 1;
-                while (nxt < G && nxt <= g_cur + 2) {
-                    const int it2 = nxt / U;
-                    if (!cross && it2 > cur_item && !item_finished) break;
-                    if (!cross && it2 > cur_item + 1) break;
-                    issue_sdp(nxt);
-                    ++nxt;
+            B2Cur nx{0, 0, 0, 0};
+            auto pump = [&](int g_cur, int cur_item, bool item_finished) {
+                while (nx.g < G && nx.g <= g_cur + 2) {
+                    if (!cross && nx.it > cur_item && !item_finished) break;
+                    if (!cross && nx.it > cur_item + 1) break;
+                    issue_sdp(nx);
+                    nx.advance(n_kt, n_qs);
                 }
             };
-            pump(-1);
+            pump(-1, 0, false);
             int pc = 0;   // dS^T pairs completed so far (pair buffer = pc & 1)
             int kc = 0;   // key tiles completed so far
-            for (int g = 0; g < G; ++g) {
-                const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs, mt = qs >> 1;
-                const int nq = min(64, p.tp - qs * 64);
-                const int nk = min(128, p.tp - kt * 128);
+            for (B2Cur c{0, 0, 0, 0}; c.g < G; c.advance(n_kt, n_qs)) {
+                const int g = c.g, it = c.it, kt = c.kt, qs = c.qs, mt = qs >> 1;
+                const int nqc = min(64, p.tp - qs * 64) >> 4;   // 16-query steps of the sub-tile
+                const int nkc = min(128, p.tp - kt * 128) >> 4; // 16-key steps of the key tile
                 const uint32_t buf = tmem_base + static_cast<uint32_t>(g & 1) * T2_BUF;
                 mbar_wait(&bar_pds[g & 1], static_cast<uint32_t>((g >> 1) & 1));
                 if (qs == 0 && kc > 0) mbar_wait(bar_kvfree, static_cast<uint32_t>((kc - 1) & 1));  // dK / dV of the previous key tile read out
                 tc_fence_after_sync();
-                const uint32_t q_base = smem_u32(smem + B2_SQ + mt * 16384 + (qs & 1) * 8192);
-                const uint32_t do_base = smem_u32(smem + B2_SDO + mt * 16384 + (qs & 1) * 8192);
-                for (int kk = 0; kk < (nq >> 4); ++kk) {  // reduction over the queries of the sub-tile, 16 per step
-                    // every 16-query chunk was written back, packed to 8 columns, at the START of its own 16 fp32 columns
-                    const uint32_t acol = static_cast<uint32_t>(kk * 16);
-                    const uint32_t acc = (qs > 0 || kk > 0) ? 1u : 0u;
-                    umma_bf16_ts(tmem_base + T2_DV, buf + acol, make_smem_desc(do_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
-                    umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, make_smem_desc(q_base + kk * 2048, 0, 1024, kSwz128), idesc_ts, acc);
+                const uint32_t q_off = static_cast<uint32_t>(qs) * 512u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {  // reduction over the queries of the sub-tile, 16 per step
+                    if (kk < nqc) {
+                        // every 16-query chunk was written back, packed to 8 columns, at the START of its own 16 fp32 columns
+                        const uint32_t acol = static_cast<uint32_t>(kk * 16);
+                        const uint32_t acc = (qs > 0 || kk > 0) ? 1u : 0u;
+                        umma_bf16_ts(tmem_base + T2_DV, buf + acol, desc_off(dsc_do, q_off + kk * 128), idesc_ts, acc);
+                        umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, desc_off(dsc_q, q_off + kk * 128), idesc_ts, acc);
+                    }
                 }
                 const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
                 if (pair_done) {
                     if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
                     tc_fence_after_sync();
-                    const uint32_t ds_base = smem_u32(smem + B2_SDS + (pc & 1) * 32768);
-                    const uint32_t k_base = smem_u32(smem + B2_SK + kt * 16384);
-                    for (int kk = 0; kk < (nk >> 4); ++kk)  // reduction over the keys of the tile
-                        umma_bf16(tmem_base + T2_DQ + static_cast<uint32_t>(mt * 64), make_smem_desc(ds_base + kk * 2048, 16384, 1024, kSwz128),
-                                  make_smem_desc(k_base + kk * 2048, 0, 1024, kSwz128), idesc_dq, (kt > 0 || kk > 0) ? 1u : 0u);
+                    const uint32_t ds_off = static_cast<uint32_t>(pc & 1) * 2048u;  // 32 KB per pair buffer
+                    const uint32_t k_off = static_cast<uint32_t>(kt) * 1024u;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)  // reduction over the keys of the tile
+                        if (kk < nkc)
+                            umma_bf16(tmem_base + T2_DQ + static_cast<uint32_t>(mt * 64), desc_off(dsc_ds, ds_off + kk * 128),
+                                      desc_off(dsc_k, k_off + kk * 128), idesc_dq, (kt > 0 || kk > 0) ? 1u : 0u);
                     umma_commit(&bar_dsfree[pc & 1]);
                     ++pc;
                     if (kt == n_kt - 1) umma_commit(&empty_q[mt]);  // last MMAs on Q_mt / dO_mt of this item
@@ -1145,7 +1229,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     ++kc;
                     if (kt == n_kt - 1) umma_commit(bar_dq);
                 }
-                pump(g);
+                pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
             }
         }
     } else if (warp >= 10) {
@@ -1159,7 +1243,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             float* lse_s = reinterpret_cast<float*>(smem + B2_LSE) + (it & 1) * 256;
             float* delta_s = reinterpret_cast<float*>(smem + B2_DELTA) + (it & 1) * 256;
             for (int i = et; i < 256; i += 128) {
-                float dl = 0.f, ls = INFINITY;  // padded query columns: exp2(s - inf) = 0 -> P = dS = 0 for free
+                float dl = 0.f, ls = INFINITY;  // padded query columns: exp2(s - inf) = 0 -> P = dS = 0 for free (stored negated)
                 if (i < p.T) {
                     const uint4* po = reinterpret_cast<const uint4*>(o_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
                     const uint4* pd = reinterpret_cast<const uint4*>(do_in + (static_cast<long long>(b) * p.T + i) * p.D + h * 64);
@@ -1171,8 +1255,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     }
                     ls = __ldg(lse_in + (static_cast<long long>(b) * p.H + h) * p.T + i) * kLog2e;
                 }
-                lse_s[i] = ls;
-                delta_s[i] = dl;
+                lse_s[i] = -ls;
+                delta_s[i] = -dl;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_delta[it & 1]);
@@ -1237,71 +1321,42 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     } else {
         // ===================================== compute warps ======================================
         const uint32_t q = static_cast<uint32_t>(warp & 3);
-        const int hf = (warp - 2) >> 2;                  // which half of the sub-tile's query columns this thread owns
+        const int grp = (warp - 2) >> 2;                 // PP: which buffer's sub-tiles; !PP: which half of the query columns
         const int r = static_cast<int>(q) * 32 + lane;   // key row inside the key tile == TMEM lane
         const uint32_t rsw = static_cast<uint32_t>(r) & 7u;
         const float sl2 = p.scale * kLog2e;
         const int G = n_my * U;
-        int pc = 0;
-        for (int g = 0; g < G; ++g) {
-            const int it = g / U, u = g - it * U, kt = u / n_qs, qs = u - kt * n_qs;
+        const int ppk = (n_qs + 1) >> 1;                 // dS^T pairs per key tile
+        B2Cur c{0, 0, 0, 0};
+        if (PP && grp == 1) c.advance(n_kt, n_qs);
+        while (c.g < G) {
+            const int g = c.g, it = c.it, kt = c.kt, qs = c.qs;
+            const int pc = (it * n_kt + kt) * ppk + (qs >> 1);   // running index of this sub-tile's dS^T pair
             const int nq = min(64, p.tp - qs * 64);
             const int nk = min(128, p.tp - kt * 128);
             const int nch = nq >> 4;                             // 16-column chunks in this sub-tile (1..4)
-            const int cb = hf ? (nch + 1) >> 1 : 0;              // this thread's chunks [cb, ce)
-            const int ce = hf ? nch : (nch + 1) >> 1;
+            const int cb = PP ? 0 : (grp ? (nch + 1) >> 1 : 0);  // this thread's chunks [cb, ce)
+            const int ce = PP ? nch : (grp ? nch : (nch + 1) >> 1);
             const bool dead = static_cast<int>(q) * 32 >= nk;    // all 32 key rows of this warp lie outside the (padded) key tile
             const int j = kt * 128 + r;                          // key index
-            const float* lse_s = reinterpret_cast<const float*>(smem + B2_LSE) + (it & 1) * 256;
-            const float* delta_s = reinterpret_cast<const float*>(smem + B2_DELTA) + (it & 1) * 256;
+            const float* nls = reinterpret_cast<const float*>(smem + B2_LSE) + (it & 1) * 256;
+            const float* ndl = reinterpret_cast<const float*>(smem + B2_DELTA) + (it & 1) * 256;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + static_cast<uint32_t>(g & 1) * T2_BUF;
             uint8_t* blk = smem + B2_SDS + (pc & 1) * 32768 + (qs & 1) * 16384 + r * 128;
-            if (u == 0) mbar_wait(&bar_delta[it & 1], static_cast<uint32_t>((it >> 1) & 1));
-            if ((qs & 1) == 0 && pc >= 2) mbar_wait(&bar_dsfree[pc & 1], static_cast<uint32_t>(((pc >> 1) - 1) & 1));  // pair buffer consumed by its dQ MMAs
+            if (kt == 0 && qs < (PP ? 2 : 1)) mbar_wait(&bar_delta[it & 1], static_cast<uint32_t>((it >> 1) & 1));
+            if (pc >= 2) mbar_wait(&bar_dsfree[pc & 1], static_cast<uint32_t>(((pc >> 1) - 1) & 1));  // pair buffer consumed by its dQ MMAs
             mbar_wait(&bar_sdp[g & 1], static_cast<uint32_t>((g >> 1) & 1));
             tc_fence_after_sync();
             if (!dead) {
+                // warp-uniform: every key row of this warp is a real key and there is no causal mask -> no per-element selects
+                const bool nomask = !p.causal && (kt * 128 + static_cast<int>(q) * 32 + 31 < p.T);
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = cb + cc;
-                    if (c < ce) {  // warp-uniform
-                        uint32_t sv[16], dv[16];
-                        // this thread's columns: chunk c of the sub-tile lives at S^T / dP^T column c * 16
-                        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), sv);
-                        tmem_ld_32x32b_x16(taddr + 64 + static_cast<uint32_t>(c * 16), dv);
-                        const int i0 = qs * 64 + c * 16;  // first query of the chunk
-                        float ls[16], dl[16];
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const float4 a = *reinterpret_cast<const float4*>(lse_s + i0 + k4 * 4);
-                            const float4 d4 = *reinterpret_cast<const float4*>(delta_s + i0 + k4 * 4);
-                            ls[k4 * 4 + 0] = a.x; ls[k4 * 4 + 1] = a.y; ls[k4 * 4 + 2] = a.z; ls[k4 * 4 + 3] = a.w;
-                            dl[k4 * 4 + 0] = d4.x; dl[k4 * 4 + 1] = d4.y; dl[k4 * 4 + 2] = d4.z; dl[k4 * 4 + 3] = d4.w;
-                        }
-                        tmem_ld_wait();
-                        float pv[16], ds[16];
-                        const bool keyok = j < p.T;
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const float e = fast_ex2(fmaf(__uint_as_float(sv[jj]), sl2, -ls[jj]));
-                            const bool ok = keyok && (!p.causal || j <= i0 + jj);
-                            pv[jj] = ok ? e : 0.f;
-                            ds[jj] = ok ? e * (__uint_as_float(dv[jj]) - dl[jj]) : 0.f;
-                        }
-                        uint32_t pk[8], dk[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            pk[jj] = pack_bf16x2(pv[2 * jj], pv[2 * jj + 1]);
-                            dk[jj] = pack_bf16x2(ds[2 * jj], ds[2 * jj + 1]);
-                        }
-                        // packed values over the first 8 of the chunk's OWN 16 columns: no other thread's unread S^T / dP^T is touched
-                        const uint32_t ocol = static_cast<uint32_t>(c * 16);
-                        tmem_st_32x32b_x8(taddr + ocol, pk);
-                        tmem_st_32x32b_x8(taddr + 64 + ocol, dk);
-                        // dS^T[key r][queries i0 .. i0+16) -> 32 bytes of the [key][query] tile (swizzled 16-byte chunks)
-                        const uint32_t c16 = static_cast<uint32_t>(c * 2);
-                        *reinterpret_cast<uint4*>(blk + ((c16 ^ rsw) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-                        *reinterpret_cast<uint4*>(blk + (((c16 + 1) ^ rsw) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+                for (int cc = 0; cc < (PP ? 4 : 2); ++cc) {
+                    const int ch = cb + cc;
+                    if (ch < ce) {  // warp-uniform
+                        const int i0 = qs * 64 + ch * 16;  // first query of the chunk
+                        if (nomask) bwd2_chunk<false>(taddr, ch, nls, ndl, i0, sl2, true, false, j, blk, rsw);
+                        else bwd2_chunk<true>(taddr, ch, nls, ndl, i0, sl2, j < p.T, p.causal != 0, j, blk, rsw);
                     }
                 }
                 tmem_st_wait();
@@ -1310,7 +1365,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_pds[g & 1]);
-            if ((qs & 1) == 1 || qs == n_qs - 1) ++pc;
+            c.advance(n_kt, n_qs);
+            if (PP) c.advance(n_kt, n_qs);
         }
     }
     __syncwarp();
@@ -1409,23 +1465,26 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     const int dev = current_device_slot();
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
         if (e != cudaSuccess) return set_error(B200_ERR_LAUNCH, cudaGetErrorString(e));
         configured[dev] = true;
     }
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
     p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = out_bf16; p.do_base = dout_bf16;
-    if (attn_pick(g_attn_bwd_version, T) == 1) {
+    const int ver = attn_pick(g_attn_bwd_version, T);
+    if (ver == 1) {
         attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                                 reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
     } else {
         const int n_items = B * H;
         const int grid = n_items < num_sms() ? n_items : num_sms();
-        attn_bwd2_kernel<<<grid, B2_THREADS, B2_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
-                                                                reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
-                                                                reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p, n_items);
+        auto kern = ver == 3 ? attn_bwd2_kernel<false> : attn_bwd2_kernel<true>;
+        kern<<<grid, B2_THREADS, B2_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+                                                    reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,
+                                                    reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p, n_items);
     }
     return check_launch("attention_bwd");
 }
@@ -1436,10 +1495,11 @@ extern "C" int b200_set_attention_prefetch(int enable) {
     return old;
 }
 
-// 0 (default): per shape; 2: persistent backward with transposed scores and P^T / dS^T operands in tensor memory; 1: the
-// round-1 kernel.  Returns the previous setting.
+// 0 (default): per shape; 2: persistent backward with transposed scores and P^T / dS^T operands in tensor memory, compute warps
+// in two ping-pong groups; 3: the same kernel with all eight compute warps on one sub-tile (A/B timing); 1: the round-1 kernel.
+// Returns the previous setting.
 extern "C" int b200_set_attention_bwd_version(int version) {
     const int old = g_attn_bwd_version;
-    g_attn_bwd_version = (version == 1 || version == 2) ? version : 0;
+    g_attn_bwd_version = (version >= 1 && version <= 3) ? version : 0;
     return old;
 }

@@ -196,7 +196,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2));
                         const int h = static_cast<int>(cta_rank);
-                        if (p.conv) {
+                        if (p.conv == 1) {
                             const int cpb = p.conv_cin / BK;
                             const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
                             const int ky = tap / 3, kx = tap - ky * 3;
@@ -210,7 +210,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < BM / 64; ++i)
                                 tma_load_2d_2sm(a_dst + i * MN_BOX_BYTES, &tmA, lead_full, m0 + i * 64, kb * BK);
                         }
-                        if (!p.b_mn) {  // this CTA's half of the B tile (128 of the 256 n rows), at offset 0 of the stage
+                        if (p.conv == 2) {
+                            // weight gradient of the 3x3 convolution: B = the activation behind a 4-D map, k-block = 64 consecutive
+                            // pixels, every 64-channel box of the N tile shifted by ITS tap (n = tap * Cin + c)
+                            const int hw = p.conv_h * p.conv_w, p0 = kb * BK;
+                            const int bimg = p0 / hw, y0 = (p0 - bimg * hw) / p.conv_w;
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i) {
+                                const int n = n0 + (2 * h + i) * 64;
+                                const int tap = n / p.conv_cin, c0 = n - tap * p.conv_cin;
+                                const int ky = tap / 3, kx = tap - ky * 3;
+                                // (boxes past N = 9 Cin: tap >= 9 lands outside the image -> zero fill, bytes still credited)
+                                tma_load_4d_2sm(b_dst + i * MN_BOX_BYTES, &tmB, lead_full, c0, kx - 1, tap < 9 ? y0 + ky - 1 : -65536, bimg);
+                            }
+                        } else if (!p.b_mn) {  // this CTA's half of the B tile (128 of the 256 n rows), at offset 0 of the stage
                             tma_load_2d_2sm(b_dst, &tmBh, lead_full, kb * BK, n0 + h * (BN / 2));
                         } else {
 #pragma unroll
@@ -221,7 +234,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         continue;
                     }
                     mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                    if (p.conv) {
+                    if (p.conv == 1) {
                         const int cpb = p.conv_cin / BK;
                         const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
                         const int ky = tap / 3, kx = tap - ky * 3;
@@ -235,7 +248,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int i = 0; i < BM / 64; ++i)
                             tma_load_2d(a_dst + i * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
                     }
-                    if (p.cluster == 1) {
+                    if (p.conv == 2) {  // (host: cluster == 1 in this mode)
+                        const int hw = p.conv_h * p.conv_w, p0 = kb * BK;
+                        const int bimg = p0 / hw, y0 = (p0 - bimg * hw) / p.conv_w;
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i) {
+                            const int n = n0 + i * 64;
+                            const int tap = n / p.conv_cin, c0 = n - tap * p.conv_cin;
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            tma_load_4d(b_dst + i * MN_BOX_BYTES, &tmB, &full_bar[stage], c0, kx - 1, tap < 9 ? y0 + ky - 1 : -65536, bimg);
+                        }
+                    } else if (p.cluster == 1) {
                         if (!p.b_mn) {
                             tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
                         } else {
@@ -885,7 +908,7 @@ extern "C" int b200_gemm_pick_splits(int M, int N, int K) {
     return best;
 }
 
-struct ConvGeom { int B, H, W, Cin; };
+struct ConvGeom { int B, H, W, Cin, mode; };  // mode 1: forward / input gradient (A behind the 4-D map); 2: weight gradient (B)
 
 static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                          int b_mn_major, int M, int N, int K, int epilogue, const void* bias, void* out0,
@@ -909,7 +932,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
         // A: K-major [M, lda] -> dims {K, M}, box {64, 128};  MN-major [K, lda] -> dims {M, K}, box {64, 64}
         uint64_t d[2], s[1];
         uint32_t bx[2];
-        if (cg != nullptr) {
+        if (cg != nullptr && cg->mode == 1) {
             // channels-last activation [B, H, W, Cin]: dims {Cin, W, H, B}; box = 64 channels x 128 consecutive pixels
             const int hb = cg->H < BM / cg->W ? cg->H : BM / cg->W;      // image rows per tile
             const int nb = BM / (cg->W * hb);                             // images per tile (> 1 only when H * W < 128)
@@ -924,6 +947,16 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
         s[0] = static_cast<uint64_t>(lda) * 2;
         if ((rc = make_tmap(&tmA, A, 2, 2, d, s, bx, 128)) != 0) return rc;
         }
+        if (cg != nullptr && cg->mode == 2) {
+            // weight gradient: the activation as the MN-major B operand, box = 64 channels x 64 consecutive pixels (one k-block)
+            const int hb = BK / cg->W;
+            uint64_t d4[4] = {static_cast<uint64_t>(cg->Cin), static_cast<uint64_t>(cg->W), static_cast<uint64_t>(cg->H), static_cast<uint64_t>(cg->B)};
+            uint64_t s4[3] = {static_cast<uint64_t>(cg->Cin) * 2, static_cast<uint64_t>(cg->W) * cg->Cin * 2,
+                              static_cast<uint64_t>(cg->H) * cg->W * cg->Cin * 2};
+            uint32_t b4[4] = {64, static_cast<uint32_t>(cg->W), static_cast<uint32_t>(hb), 1};
+            if ((rc = make_tmap(&tmB, B, 2, 4, d4, s4, b4, 128)) != 0) return rc;
+            tmBh = tmB;
+        } else {
         if (!b_mn_major) { d[0] = K; d[1] = N; bx[0] = BK; bx[1] = BN; }
         else             { d[0] = N; d[1] = K; bx[0] = 64; bx[1] = BK; }
         s[0] = static_cast<uint64_t>(ldb) * 2;
@@ -932,6 +965,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
         if (!b_mn_major) {  // half-tile box for the multicast path (MN-major boxes are 64 wide already)
             bx[1] = BN / 2;
             if ((rc = make_tmap(&tmBh, B, 2, 2, d, s, bx, 128)) != 0) return rc;
+        }
         }
     }
     const bool out_f32 = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_PARTIAL_F32);
@@ -948,7 +982,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
     }
     GemmParams p;
     p.act = act;
-    p.conv = cg != nullptr ? 1 : 0;
+    p.conv = cg != nullptr ? cg->mode : 0;
     p.conv_h = cg != nullptr ? cg->H : 0;
     p.conv_w = cg != nullptr ? cg->W : 0;
     p.conv_cin = cg != nullptr ? cg->Cin : 0;
@@ -966,6 +1000,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
     p.ldo = ldo;
     p.cluster = (g_gemm_multicast && max_ctas != 1) ? 2 : 1;
     p.two_sm = (p.cluster == 2 && g_gemm_multicast == 2) ? 1 : 0;
+    if (p.conv == 2 && !p.two_sm) p.cluster = 1;  // the weight-gradient loads exist for the 2-SM and the single-CTA paths only
     const long long units = static_cast<long long>((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * splits;
     int grid = num_sms();
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
@@ -1006,9 +1041,27 @@ extern "C" int b200_conv3x3_nhwc_bf16(const void* x, const void* w_packed, const
     const int hb = H < BM / W ? H : BM / W;
     if (H % hb != 0 || BM % (W * hb) != 0) return set_error(B200_ERR_ARG, "conv3x3: H must be a multiple of 128 / W (or H * W must divide 128)");
     if (epilogue != EPI_BIAS_BF16 && epilogue != EPI_BIAS_RESID_F32) return set_error(B200_ERR_ARG, "conv3x3: epilogue must be BIAS_BF16 or BIAS_RESID_F32");
-    ConvGeom cg{B, H, W, Cin};
+    ConvGeom cg{B, H, W, Cin, 1};
     const long long M = static_cast<long long>(B) * H * W;
     if (M > 0x7fffffffll) return set_error(B200_ERR_ARG, "conv3x3: too many pixels");
     return gemm_dispatch(x, Cin, 0, w_packed, 9ll * Cin, 0, static_cast<int>(M), Cout, 9 * Cin, epilogue, bias, out0, nullptr, aux, ldo, 1, 0,
                          stream, &cg);
+}
+
+// Weight gradient of the same convolution: dW[co][tap][ci] = sum over pixels of dy[pixel, co] * x[pixel shifted by tap, ci], as ONE
+// split-K GEMM with M = Cout, N = 9 * Cin, K = B * H * W: A = dy MN-major (plain 2-D map), B = x MN-major behind the 4-D map, every
+// 64-channel box of an N tile shifted by its own tap (halo zero-filled by TMA).  Writes `splits` fp32 partial planes
+// [splits][Cout][9 * Cin] (b200_splitk_reduce finishes them); the plane layout IS the packed forward weight layout.
+// Replaces the weight half of torch's conv2d backward for convs/basic.py:155-174 under the UNet blocks (convs/residual.py:179-205).
+extern "C" int b200_conv3x3_wgrad_nhwc_bf16(const void* dy, long long ld_dy, const void* x, void* partials, int B, int H, int W, int Cin,
+                                            int Cout, int splits, cudaStream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return set_error(B200_ERR_ARG, "conv3x3 wgrad: non-positive size");
+    if (Cin % 64 != 0) return set_error(B200_ERR_ARG, "conv3x3 wgrad: Cin must be a multiple of 64");
+    if (W > BK || BK % W != 0) return set_error(B200_ERR_ARG, "conv3x3 wgrad: the image width must divide 64");
+    if ((static_cast<long long>(H) * W) % BK != 0) return set_error(B200_ERR_ARG, "conv3x3 wgrad: H * W must be a multiple of 64");
+    const long long K = static_cast<long long>(B) * H * W;
+    if (K > 0x7fffffffll) return set_error(B200_ERR_ARG, "conv3x3 wgrad: too many pixels");
+    ConvGeom cg{B, H, W, Cin, 2};
+    return gemm_dispatch(dy, ld_dy, 1, x, Cin, 1, Cout, 9 * Cin, static_cast<int>(K), EPI_PARTIAL_F32, nullptr, partials, nullptr, nullptr,
+                         9ll * Cin, splits, 0, stream, &cg);
 }

@@ -262,6 +262,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= static_cast<uint64_t>(layout & 7u) << 61;
     return d;
 }
+// descriptor + byte offset (>> 4): only the 14-bit start-address field changes (cheap on the single MMA-issuing lane)
+__device__ __forceinline__ uint64_t desc_off(uint64_t base, uint32_t off16) {
+    return (base & 0xffffffff00000000ull) | static_cast<uint64_t>(static_cast<uint32_t>(base) + off16);
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate:
 //   [4,6) c_format = 1 (F32)  [7,10) a_format = 1 (BF16)  [10,13) b_format = 1 (BF16)
 //   [15] a_major (0 = K-major, 1 = MN-major)  [16] b_major  [17,23) N >> 3  [24,29) M >> 4

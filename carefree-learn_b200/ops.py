@@ -360,6 +360,34 @@ def pack_conv3x3_weight_dgrad(w: Tensor) -> Tensor:
     return pack_conv3x3_weight(w.flip(2, 3).transpose(0, 1))
 
 
+def conv3x3_wgrad(dy: Tensor, x: Tensor, out: Optional[Tensor] = None, *, round_bf16: bool = True, accumulate: bool = False) -> Tensor:
+    """Weight gradient of ``conv3x3``: dy bf16 [B, H, W, Cout], x bf16 [B, H, W, Cin] -> fp32 [Cout, 9 * Cin] in the PACKED layout
+    of ``pack_conv3x3_weight`` (``unpack_conv3x3_weight`` gives the reference's [Cout, Cin, 3, 3]).  One split-K implicit GEMM over
+    the B * H * W pixels plus the split-K reduction; ``round_bf16`` rounds like eager's bf16 conv backward does."""
+    _need_cuda(dy, x, out)
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.dim() != 4 or x.dim() != 4 or not dy.is_contiguous() or not x.is_contiguous():
+        raise B200Error("conv3x3_wgrad: need contiguous bf16 dy [B, H, W, Cout] and x [B, H, W, Cin]")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    if tuple(dy.shape[:3]) != (B, H, W):
+        raise B200Error("conv3x3_wgrad: dy and x disagree on [B, H, W]")
+    if out is None:
+        out = torch.empty((Cout, 9 * Cin), dtype=torch.float32, device=x.device)
+        accumulate = False
+    n = Cout * 9 * Cin
+    splits = pick_splits(Cout, 9 * Cin, B * H * W)
+    part = WORKSPACE.get(x.device, splits * n, "splitk")[: splits * n]
+    call("b200_conv3x3_wgrad_nhwc_bf16", dy.data_ptr(), Cout, x.data_ptr(), part.data_ptr(), B, H, W, Cin, Cout, splits, _stream())
+    call("b200_splitk_reduce", part.data_ptr(), splits, n, out.data_ptr(), int(round_bf16), int(accumulate), _stream())
+    return out
+
+
+def unpack_conv3x3_weight(w_packed: Tensor, cin: int) -> Tensor:
+    """[Cout, 9 * Cin] (tap-major) -> [Cout, Cin, 3, 3], the reference's Conv2d.weight layout."""
+    co = w_packed.shape[0]
+    return w_packed.view(co, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+
+
 def conv3x3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor] = None, *, epilogue: int = EPI_BIAS_BF16, aux: Optional[Tensor] = None) -> Tensor:
     """x: bf16 [B, H, W, Cin] channels-last; w_packed: bf16 [Cout, 9 * Cin] -> bf16 (or fp32 with the residual epilogue) [B, H, W, Cout]."""
     _need_cuda(x, w_packed, bias, aux)

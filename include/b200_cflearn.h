@@ -27,7 +27,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define B200_ABI_VERSION 3
+#define B200_ABI_VERSION 4
 
 enum {
     B200_OK = 0,
@@ -129,7 +129,7 @@ int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int B, 
  * For A/B timing and tests of both kernels; results agree to fp32 rounding. */
 int b200_set_attention_fwd_version(int version);
 /* same for the backward kernel: 0 (default) = per shape; 2 = persistent, transposed scores, P^T / dS^T operands in tensor
- * memory; 1 = round 1 */
+ * memory, compute warps in two ping-pong groups; 3 = version 2 with all compute warps on one sub-tile; 1 = round 1 */
 int b200_set_attention_bwd_version(int version);
 /* version-2 kernels: cooperative L2 prefetch of the next item's image as whole contiguous rows (default 0: measured neutral) */
 int b200_set_attention_prefetch(int enable);
@@ -241,6 +241,12 @@ int b200_fill_f32(float* dst, float value, long long n, cudaStream_t stream);
  * --------------------------------------------------------------------------------------------------------- */
 int b200_conv3x3_nhwc_bf16(const void* x, const void* w_packed, const void* bias, void* out0, const void* aux, long long ldo,
                            int B, int H, int W, int Cin, int Cout, int epilogue, cudaStream_t stream);
+/* weight gradient of that convolution: ONE split-K GEMM with M = Cout, N = 9 * Cin, K = B * H * W (dy MN-major, x behind the
+ * 4-D map, each 64-channel box shifted by its own tap).  dy: bf16 [B*H*W, ld_dy]; partials: f32 [splits][Cout][9 * Cin]
+ * (finish with b200_splitk_reduce; the plane layout is the packed forward weight layout).  Cin % 64 == 0, W divides 64,
+ * H * W % 64 == 0.  Replaces the weight half of conv2d's backward for cflearn/modules/core/convs/basic.py:155-174. */
+int b200_conv3x3_wgrad_nhwc_bf16(const void* dy, long long ld_dy, const void* x, void* partials, int B, int H, int W, int Cin,
+                                 int Cout, int splits, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * GroupNorm(32) (+ SiLU) on channels-last bf16 activations x [B, HW, C] (C contiguous, C % 32 == 0, C <= 2560): the

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     exported = set(_cabi.exported_symbols())
     assert set(declared) == set(_cabi.SIGNATURES), (set(declared) ^ set(_cabi.SIGNATURES))
     assert not [n for n in declared if n not in exported]
-    assert _cabi.lib().b200_abi_version() == 3
+    assert _cabi.lib().b200_abi_version() == 4
     assert _cabi.lib().b200_gemm_pick_splits(768, 768, 50432) >= 1
 
 

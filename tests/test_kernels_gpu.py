@@ -347,10 +347,17 @@ def test_attention_fwd(B, T, H, causal, version):
 
 def test_attention_fwd_many_items_per_cta():
     """More (batch, head) items than SMs: every persistent CTA walks several items through both ring stages and both TMEM
-    slots (the small cases above give each CTA at most one item)."""
-    _attention_fwd_case(40, 197, 12, False)
-    _attention_fwd_case(64, 77, 8, True)
-    _attention_fwd_case(37, 50, 12, False)
+    slots (the small cases above give each CTA at most one item).  Version 2 is forced: the per-shape default picks the
+    round-1 kernel for single-tile items."""
+    from cflearn_b200 import _cabi
+
+    prev = _cabi.lib().b200_set_attention_fwd_version(2)
+    try:
+        _attention_fwd_case(40, 197, 12, False)
+        _attention_fwd_case(64, 77, 8, True)
+        _attention_fwd_case(37, 50, 12, False)
+    finally:
+        _cabi.lib().b200_set_attention_fwd_version(prev)
 
 
 def _attention_fwd_case(B, T, H, causal):
@@ -367,9 +374,10 @@ def _attention_fwd_case(B, T, H, causal):
 
 
 @pytest.mark.parametrize("B,T,H,causal", [(2, 197, 12, False), (3, 77, 8, True), (2, 50, 12, False), (1, 256, 2, False), (2, 130, 2, False), (2, 16, 1, True)])
-@pytest.mark.parametrize("version", [2, 1])
+@pytest.mark.parametrize("version", [2, 3, 1])
 def test_attention_bwd(B, T, H, causal, version):
-    """version 2: persistent kernel, transposed scores, P^T / dS^T operands in tensor memory (default); version 1: round 1."""
+    """version 2: persistent kernel, transposed scores, P^T / dS^T operands in tensor memory, compute warps in two ping-pong
+    groups (chosen for T > 128); version 3: the same kernel with all compute warps on one sub-tile; version 1: round 1."""
     from cflearn_b200 import _cabi
 
     prev = _cabi.lib().b200_set_attention_bwd_version(version)
@@ -379,13 +387,22 @@ def test_attention_bwd(B, T, H, causal, version):
         _cabi.lib().b200_set_attention_bwd_version(prev)
 
 
-def test_attention_bwd_many_items_per_cta():
+@pytest.mark.parametrize("version", [2, 3])
+def test_attention_bwd_many_items_per_cta(version):
     """More (batch, head) items than SMs: operand buffers, TMEM buffers, dS^T pair buffers and the lse / delta parity
-    buffers are all recycled several times per persistent CTA (with and without the cross-item look-ahead)."""
-    _attention_bwd_case(40, 197, 12, False)
-    _attention_bwd_case(64, 77, 8, True)
-    _attention_bwd_case(37, 50, 12, False)
-    _attention_bwd_case(30, 130, 6, False)
+    buffers are all recycled several times per persistent CTA (with and without the cross-item look-ahead; odd and even
+    numbers of sub-tiles per item, so the ping-pong groups swap buffers between items)."""
+    from cflearn_b200 import _cabi
+
+    prev = _cabi.lib().b200_set_attention_bwd_version(version)
+    try:
+        _attention_bwd_case(40, 197, 12, False)
+        _attention_bwd_case(64, 77, 8, True)
+        _attention_bwd_case(37, 50, 12, False)
+        _attention_bwd_case(30, 130, 6, False)
+        _attention_bwd_case(33, 256, 5, True)
+    finally:
+        _cabi.lib().b200_set_attention_bwd_version(prev)
 
 
 def _attention_bwd_case(B, T, H, causal):
@@ -570,3 +587,29 @@ def test_conv3x3_implicit_gemm_matches_conv2d(B, H, W, Cin, Cout):
         dx = ops.conv3x3(dy.permute(0, 2, 3, 1).contiguous(), ops.pack_conv3x3_weight_dgrad(w))
         torch.cuda.synchronize()
         _assert_bf16_close(dx.reshape(-1, Cin), xr.grad.permute(0, 2, 3, 1).reshape(-1, Cin), "conv3x3 input gradient")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 8, 8, 1280, 1280), (3, 8, 8, 1280, 640), (2, 32, 32, 640, 320),
+                                            (1, 16, 16, 2560, 1280), (2, 16, 16, 64, 8)])
+def test_conv3x3_weight_gradient_matches_conv2d(B, H, W, Cin, Cout):
+    """dW of the 3x3 convolution as ONE split-K implicit GEMM over the pixels (dy MN-major, the activation behind a 4-D tensor map,
+    every 64-channel box shifted by its own tap) against autograd of F.conv2d in fp32 on the same bf16 operands."""
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    dy = torch.randn(B, Cout, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    w = torch.zeros(Cout, Cin, 3, 3, device=DEV, requires_grad=True)
+    F.conv2d(x.float(), w, None, padding=1).backward(dy.float())
+    dw = ops.conv3x3_wgrad(dy.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous(), round_bf16=False)
+    torch.cuda.synchronize()
+    assert tuple(dw.shape) == (Cout, 9 * Cin)
+    got = ops.unpack_conv3x3_weight(dw, Cin)
+    e = _relerr(got, w.grad)
+    assert e < 2e-5, e   # fp32 accumulation of exact bf16 products: only the summation order differs
+    # every tap separately (a shifted tap shows up as an O(1) error in that tap only)
+    for ky in range(3):
+        for kx in range(3):
+            assert _relerr(got[:, :, ky, kx], w.grad[:, :, ky, kx]) < 5e-5, (ky, kx)
+    # rounded like eager's bf16 backward, accumulated into an existing gradient
+    acc = torch.ones(Cout, 9 * Cin, device=DEV)
+    ops.conv3x3_wgrad(dy.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous(), acc, accumulate=True)
+    assert torch.equal(acc - 1.0, (dw.to(torch.bfloat16).float() + 1.0) - 1.0) or _relerr(acc - 1.0, dw.to(torch.bfloat16).float()) < 1e-3

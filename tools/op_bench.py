@@ -50,6 +50,15 @@ if only_attn:
     dout = bf(B, T, D)
     rows.append(("attention fwd  B256 T197 H12", timeit(lambda: ops.attention_fwd(qkv, B, T, H)), 4 * B * H * T * T * 64))
     rows.append(("attention bwd  B256 T197 H12", timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, T, H)), 10 * B * H * T * T * 64))
+    from cflearn_b200 import _cabi
+    for ver in (1, 2, 3):  # forced kernels (the first two rows use the per-shape default unless B200_ATTN_* is set)
+        prev = _cabi.lib().b200_set_attention_bwd_version(ver)
+        rows.append((f"attention bwd  B256 T197 H12, forced version {ver}", timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, T, H)), 10 * B * H * T * T * 64))
+        _cabi.lib().b200_set_attention_bwd_version(prev)
+    for ver in (1, 2):
+        prev = _cabi.lib().b200_set_attention_fwd_version(ver)
+        rows.append((f"attention fwd  B256 T197 H12, forced version {ver}", timeit(lambda: ops.attention_fwd(qkv, B, T, H)), 4 * B * H * T * T * 64))
+        _cabi.lib().b200_set_attention_fwd_version(prev)
     qk = bf(256, 77, 3 * 512)
     rows.append(("attention fwd  B256 T77 H8 causal (CLIP text)", timeit(lambda: ops.attention_fwd(qk, 256, 77, 8, causal=True)), 4 * 256 * 8 * 77 * 77 * 64))
     qv = bf(256, 50, 3 * 768)

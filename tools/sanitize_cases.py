@@ -44,10 +44,13 @@ if which in ("all", "conv"):
     w = bf(72, 128, 3, 3, scale=0.05)
     ops.conv3x3(x, ops.pack_conv3x3_weight(w), bf(72, scale=0.1))
     torch.cuda.synchronize()
+    dyc = bf(2, 16, 16, 72)
+    ops.conv3x3_wgrad(dyc, x)
+    torch.cuda.synchronize()
     print("conv case done")
 if which in ("all", "attn"):
-    for ver in (2, 1):
-        _cabi.lib().b200_set_attention_fwd_version(ver)
+    for ver in (2, 3, 1):
+        _cabi.lib().b200_set_attention_fwd_version(min(ver, 2))
         _cabi.lib().b200_set_attention_bwd_version(ver)
         for (B, T, H, causal) in ((14, 197, 12, False), (20, 77, 8, True), (3, 50, 2, False)):
             qkv = bf(B, T, 3 * H * 64)
