@@ -28,7 +28,7 @@ CLIP_FLOP_PER_PAIR_FWD_BWD = 3 * 14_780_000_000  # 14.78 G
 CONFIG_NAME = "vit_b16"
 PER_GPU_BATCH = 256
 # N > 1 gradient exchange used by default ("graph" once validated on real multi-GPU boxes; see --dp-mode)
-DEFAULT_DP_MODE = "torch"
+DEFAULT_DP_MODE = "graph"  # validated on 2 GPUs (tools/dp_check.py: eager = graphed = flat = 2.2e-3 vs the single-process global batch)
 
 
 def _peaks():
@@ -550,6 +550,7 @@ def run_b200(args):
     eager = None
     if not args.no_eager_baseline and not is_clip:
         if gstep is not None:
+            gstep.release()
             gstep = None  # free the graph's private pool (~17 GB) before eager allocates its ~40 GB of activations
         torch.cuda.empty_cache()
         eager = eager_gpu_leg(rank, world, dev, steps=min(args.steps, 10), warmup=3)
@@ -585,8 +586,13 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "eager_gpu": eager, "dp_parity_rel": dp_parity, "loss": round(final_loss, 4),
         }
         print(json.dumps(line), flush=True)
+    if gstep is not None:  # ncclCommDestroy waits for every graph that captured the communicator: destroy the graph first
+        gstep.release()
+        gstep = None
     if comm is not None:
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         comm.close()
     if world > 1:
         dist.destroy_process_group()

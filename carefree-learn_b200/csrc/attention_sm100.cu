@@ -1428,7 +1428,7 @@ extern "C" int b200_attention_fwd(const void* qkv_bf16, void* out_bf16, float* l
         attn_fwd_kernel<<<B * H * n_mt, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p);
     } else {
         const int n_items = B * H;
-        const int grid = n_items < num_sms() ? n_items : num_sms();
+        const int grid = n_items < persistent_ctas() ? n_items : persistent_ctas();
         attn_fwd2_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, p, n_items);
     }
     return check_launch("attention_fwd");
@@ -1480,7 +1480,7 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_part, p);
     } else {
         const int n_items = B * H;
-        const int grid = n_items < num_sms() ? n_items : num_sms();
+        const int grid = n_items < persistent_ctas() ? n_items : persistent_ctas();
         auto kern = ver == 3 ? attn_bwd2_kernel<false> : attn_bwd2_kernel<true>;
         kern<<<grid, B2_THREADS, B2_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                     reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,

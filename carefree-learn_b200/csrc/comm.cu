@@ -28,6 +28,7 @@ enum { kNcclFloat32 = 7 };
 
 typedef int (*PFN_GetUniqueId)(NcclUniqueId*);
 typedef int (*PFN_CommInitRank)(ncclComm_t*, int, NcclUniqueId, int);
+typedef int (*PFN_CommInitRankConfig)(ncclComm_t*, int, NcclUniqueId, int, void*);
 typedef int (*PFN_CommDestroy)(ncclComm_t);
 typedef int (*PFN_CommAbort)(ncclComm_t);
 typedef int (*PFN_CommGetAsyncError)(ncclComm_t, int*);
@@ -39,6 +40,7 @@ struct NcclApi {
     void* handle = nullptr;
     PFN_GetUniqueId GetUniqueId = nullptr;
     PFN_CommInitRank CommInitRank = nullptr;
+    PFN_CommInitRankConfig CommInitRankConfig = nullptr;
     PFN_CommDestroy CommDestroy = nullptr;
     PFN_CommAbort CommAbort = nullptr;
     PFN_CommGetAsyncError CommGetAsyncError = nullptr;
@@ -60,6 +62,7 @@ int load_api() {
     a.handle = h;
     a.GetUniqueId = reinterpret_cast<PFN_GetUniqueId>(dlsym(h, "ncclGetUniqueId"));
     a.CommInitRank = reinterpret_cast<PFN_CommInitRank>(dlsym(h, "ncclCommInitRank"));
+    a.CommInitRankConfig = reinterpret_cast<PFN_CommInitRankConfig>(dlsym(h, "ncclCommInitRankConfig"));
     a.CommDestroy = reinterpret_cast<PFN_CommDestroy>(dlsym(h, "ncclCommDestroy"));
     a.CommAbort = reinterpret_cast<PFN_CommAbort>(dlsym(h, "ncclCommAbort"));
     a.CommGetAsyncError = reinterpret_cast<PFN_CommGetAsyncError>(dlsym(h, "ncclCommGetAsyncError"));
@@ -77,6 +80,21 @@ int nccl_fail(const char* what, int rc) {
     snprintf(msg, sizeof(msg), "%s: NCCL error %d (%s)", what, rc, g_api.GetErrorString ? g_api.GetErrorString(rc) : "?");
     return b200::set_error(B200_ERR_LAUNCH, msg);
 }
+
+// ncclConfig_t as of NCCL 2.17 (nccl.h: size / magic / version, then the user fields).  NCCL copies min(size, its own sizeof)
+// bytes and fills every field the caller's `version` does not know with its defaults, so this prefix is valid for all later
+// releases (2.28.9 here).  Only maxCTAs is set: the limit applies to THIS communicator, not to torch.distributed's.
+struct NcclConfigV21700 {
+    size_t size;
+    unsigned int magic;
+    unsigned int version;
+    int blocking;
+    int cgaClusterSize;
+    int minCTAs;
+    int maxCTAs;
+    const char* netName;
+};
+constexpr int kNcclUndefInt = -2147483647 - 1;  // NCCL_CONFIG_UNDEF_INT (INT_MIN)
 
 struct Comm {
     ncclComm_t nccl;
@@ -96,7 +114,7 @@ extern "C" int b200_comm_unique_id(void* id_out_128) {
     return 0;
 }
 
-extern "C" int b200_comm_init(const void* id_128, int rank, int world, void** comm_out) {
+extern "C" int b200_comm_init(const void* id_128, int rank, int world, int max_ctas, void** comm_out) {
     if (id_128 == nullptr || comm_out == nullptr || world < 1 || rank < 0 || rank >= world)
         return b200::set_error(B200_ERR_ARG, "comm_init: bad arguments");
     int rc = load_api();
@@ -104,8 +122,15 @@ extern "C" int b200_comm_init(const void* id_128, int rank, int world, void** co
     NcclUniqueId id;
     memcpy(id.internal, id_128, sizeof(id.internal));
     ncclComm_t c = nullptr;
-    rc = g_api.CommInitRank(&c, world, id, rank);  // collective over the ranks; uses the CURRENT device
-    if (rc != kNcclSuccess) return nccl_fail("ncclCommInitRank", rc);
+    if (max_ctas > 0 && g_api.CommInitRankConfig != nullptr) {
+        NcclConfigV21700 cfg{sizeof(NcclConfigV21700), 0xcafebeefu, 21700u, kNcclUndefInt, kNcclUndefInt, kNcclUndefInt, max_ctas, nullptr};
+        if (cfg.maxCTAs > 32) cfg.maxCTAs = 32;
+        rc = g_api.CommInitRankConfig(&c, world, id, rank, &cfg);  // collective over the ranks; uses the CURRENT device
+        if (rc != kNcclSuccess) return nccl_fail("ncclCommInitRankConfig", rc);
+    } else {
+        rc = g_api.CommInitRank(&c, world, id, rank);
+        if (rc != kNcclSuccess) return nccl_fail("ncclCommInitRank", rc);
+    }
     Comm* out = new Comm{c, rank, world};
     *comm_out = out;
     return 0;

@@ -832,6 +832,20 @@ int num_sms() {
     return cached[dev];
 }
 
+// Upper bound on the grid of every persistent kernel (GEMM, attention version 2), 0 = all SMs.  The data-parallel step lowers it
+// by the communicator's CTA count while gradient buckets are in flight: these kernels assign their tiles to CTAs statically, and
+// a CTA whose SM is held by an NCCL kernel starts only when that all-reduce is over -- with its full share of tiles still to do.
+static int g_persistent_ctas = 0;
+int persistent_ctas() {
+    const int n = num_sms();
+    return (g_persistent_ctas > 0 && g_persistent_ctas < n) ? g_persistent_ctas : n;
+}
+extern "C" int b200_set_persistent_ctas(int n) {
+    const int old = g_persistent_ctas;
+    g_persistent_ctas = n > 0 ? n : 0;
+    return old;
+}
+
 static int g_gemm_multicast = 2;  // 0: one CTA per tile; 1: CTA pairs + TMA multicast; 2 (default): CTA pairs + cta_group::2 MMA, 6-stage ring
 
 template <int EPI, bool TWO_SM, bool QUICK>
@@ -1002,7 +1016,7 @@ static int gemm_dispatch(const void* A, long long lda, int a_mn_major, const voi
     p.two_sm = (p.cluster == 2 && g_gemm_multicast == 2) ? 1 : 0;
     if (p.conv == 2 && !p.two_sm) p.cluster = 1;  // the weight-gradient loads exist for the 2-SM and the single-CTA paths only
     const long long units = static_cast<long long>((p.num_m_tiles + p.cluster - 1) / p.cluster) * p.num_n_tiles * splits;
-    int grid = num_sms();
+    int grid = persistent_ctas();
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
     int nclusters = grid / p.cluster;
     if (nclusters < 1) nclusters = 1;

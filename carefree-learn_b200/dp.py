@@ -118,10 +118,11 @@ class NativeComm:
     def __init__(self, rank: int, world: int, device: torch.device, bootstrap_group: Any = None):
         if not dist.is_initialized():
             raise RuntimeError("NativeComm needs an initialised torch.distributed group to ship the NCCL unique id")
-        # NCCL kernels and the persistent GEMMs of the backward share the SMs: cap the channels NCCL may use so that the
-        # engine can leave exactly that many SMs free while a bucket is in flight (B200_COMM_CTAS, default 16)
-        self.ctas = int(os.environ.get("B200_COMM_CTAS", "16"))
-        os.environ.setdefault("NCCL_MAX_CTAS", str(self.ctas))
+        # NCCL kernels and the persistent kernels of the backward share the SMs: cap the channels NCCL may use so that the
+        # step can leave exactly that many SMs free while buckets are in flight (B200_COMM_CTAS, default 8: the bucket
+        # all-reduces hide under ~20 ms of backward, so they need little bandwidth -- and every CTA costs the GEMMs an SM)
+        # (ncclConfig_t.maxCTAs of THIS communicator only: torch.distributed's own communicator keeps NCCL's defaults)
+        self.ctas = int(os.environ.get("B200_COMM_CTAS", "8"))
         self.rank, self.world, self.device = rank, world, device
         lib = _cabi.lib()
         buf = ctypes.create_string_buffer(128)
@@ -135,7 +136,7 @@ class NativeComm:
         raw = bytes(t.cpu().numpy().tobytes())
         handle = ctypes.c_void_p()
         with torch.cuda.device(device):
-            _cabi.check(lib.b200_comm_init(raw, rank, world, ctypes.byref(handle)), "b200_comm_init")
+            _cabi.check(lib.b200_comm_init(raw, rank, world, self.ctas, ctypes.byref(handle)), "b200_comm_init")
         self._h = handle
         self.nccl_version = int(lib.b200_comm_nccl_version())
 
@@ -151,6 +152,8 @@ class NativeComm:
         _cabi.call("b200_comm_async_error", self._h)
 
     def close(self, abort: bool = False) -> None:
+        """``ncclCommDestroy`` (``abort``: ``ncclCommAbort``).  Every CUDA graph that captured this communicator must have been
+        destroyed first (``GraphedTrainStep.release()``): NCCL waits for them."""
         if self._h is not None and self._h.value:
             _cabi.lib().b200_comm_finalize(self._h, int(abort))
             self._h = None
@@ -179,9 +182,10 @@ class NativeBucketReducer(GradBucketReducer):
     """Same bucket protocol as ``GradBucketReducer`` over a ``NativeComm``: works eagerly AND under stream capture.
 
     ``ready(key)`` forks the communication stream off the compute stream (event) and enqueues the bucket's all-reduce
-    there; ``finish()`` joins.  While a bucket is in flight the engine launches its next GEMM on ``148 - comm.ctas`` SMs
-    (``engine.shrink_next``): the persistent GEMM statically assigns its tiles to its CTAs, so CTAs that cannot start
-    because NCCL holds their SM would otherwise stretch the kernel by the whole duration of the all-reduce."""
+    there; ``finish()`` joins.  From the first bucket to the join every persistent kernel of the library (GEMMs, attention)
+    is launched on ``SMs - comm.ctas`` CTAs (``b200_set_persistent_ctas``): they assign their tiles to CTAs statically, so a
+    CTA that cannot start because NCCL holds its SM would stretch its kernel by the whole duration of the all-reduce.
+    ``B200_DP_SHRINK=next`` restores the first schedule (only the GEMM right after a bucket is shrunk) for A/B timing."""
 
     def __init__(self, arena, num_layers: int, comm: NativeComm, engine: Any = None):
         super().__init__(arena, num_layers, process_group=None)
@@ -189,6 +193,7 @@ class NativeBucketReducer(GradBucketReducer):
         self.world = comm.world
         self.engine = engine
         self._launched = False
+        self._prev_limit: Optional[int] = None
 
     def ready(self, key: BucketKey, grad: Optional[torch.Tensor] = None) -> None:
         if self.world == 1:
@@ -205,15 +210,23 @@ class NativeBucketReducer(GradBucketReducer):
         cs.wait_event(ev)
         with torch.cuda.stream(cs):
             self.comm.allreduce_(grad[lo:hi], average=True)
+        if os.environ.get("B200_DP_SHRINK", "all") == "next":
+            if self.engine is not None and key != "stem":
+                self.engine.shrink_next = self.comm.ctas
+        elif not self._launched and self.comm.ctas > 0:
+            from . import ops
+
+            self._prev_limit = _cabi.lib().b200_set_persistent_ctas(max(2, (ops.num_sms() - self.comm.ctas) // 2 * 2))
         self._launched = True
-        if self.engine is not None and key != "stem":
-            self.engine.shrink_next = self.comm.ctas
 
     def finish(self) -> None:
         if self.world == 1 or not self._launched:
             return
         torch.cuda.current_stream().wait_stream(self._stream())
         self._launched = False
+        if self._prev_limit is not None:
+            _cabi.lib().b200_set_persistent_ctas(self._prev_limit)
+            self._prev_limit = None
 
     def _stream(self) -> torch.cuda.Stream:
         if self.comm_stream is None:

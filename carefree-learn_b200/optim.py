@@ -298,6 +298,15 @@ class GraphedTrainStep:
             self.optimizer.step()
         return self.loss
 
+    def release(self) -> None:
+        """Destroy the captured graph.  REQUIRED before ``comm.close()`` when the graph holds NCCL kernels: ``ncclCommDestroy``
+        waits for every CUDA graph that captured the communicator to be destroyed (it hung the 2-GPU bench at exit until the
+        graph was dropped first -- profiles/r02_dp_notes.md)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def check_labels(self) -> None:
         """Synchronises and raises ``ValueError`` if the last replay saw a label outside [0, num_classes)."""
         if int(self.bad_label.item()) != 0:

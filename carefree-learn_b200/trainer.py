@@ -47,6 +47,12 @@ class B200TrainStep:
 
             dp.attach_native_reducers(model, comm)
 
+    def close(self) -> None:
+        """Destroy the captured graph (must happen before the communicator it captured is closed)."""
+        if self._graph is not None:
+            self._graph.release()
+            self._graph = None
+
     def step(self, *batch: Tensor) -> Tensor:
         """One optimisation step on ``batch`` (device tensors or pinned host tensors); returns the loss (device scalar)."""
         if self._graph is not None:

@@ -248,6 +248,13 @@ int b200_conv3x3_nhwc_bf16(const void* x, const void* w_packed, const void* bias
 int b200_conv3x3_wgrad_nhwc_bf16(const void* dy, long long ld_dy, const void* x, void* partials, int B, int H, int W, int Cin,
                                  int Cout, int splits, cudaStream_t stream);
 
+/* Upper bound on the grid of every persistent kernel of this library (the GEMMs, attention version 2); 0 = all SMs (default).
+ * Returns the previous value.  The data-parallel step sets it to (SMs - communicator CTAs) between the first gradient bucket's
+ * all-reduce and the join before the optimizer: tiles are assigned to CTAs statically, so a CTA that has to wait for an SM held
+ * by an NCCL kernel would stretch its kernel by the whole all-reduce.  (DistributedDataParallel's overlap, accelerate.prepare,
+ * cflearn/schema.py:1174-1180, has no such knob: eager kernels are not persistent.) */
+int b200_set_persistent_ctas(int n);
+
 /* ---------------------------------------------------------------------------------------------------------
  * GroupNorm(32) (+ SiLU) on channels-last bf16 activations x [B, HW, C] (C contiguous, C % 32 == 0, C <= 2560): the
  * normalisation in front of every 3x3 convolution of the SD-v1.5 UNet (BASELINE.json configs[4]).
@@ -271,13 +278,14 @@ int b200_groupnorm_silu_bwd(const void* x_bf16, const void* dy_bf16, const float
  * 266-273; the all-reduce sits between backward and optimizer.step, cflearn/schema.py:980-984).  One communicator per
  * process / GPU over NCCL (libnccl.so.2 is dlopen'ed at first use).  b200_comm_unique_id: rank 0 creates the 128-byte
  * id (HOST pointer) and ships it to the other ranks by any means; b200_comm_init is collective over all ranks and
- * binds to the CURRENT device; b200_comm_allreduce_bucket enqueues an in-place fp32 all-reduce (average != 0: mean
+ * binds to the CURRENT device (max_ctas > 0: ncclConfig_t.maxCTAs of THIS communicator -- its kernels share the SMs with the
+ * backward's persistent kernels, see b200_set_persistent_ctas; 0: NCCL's default); b200_comm_allreduce_bucket enqueues an in-place fp32 all-reduce (average != 0: mean
  * over ranks, else sum) of buf[0..n) on `stream` -- an ordinary stream operation, capturable in a CUDA graph;
  * b200_comm_async_error polls the communicator (0 healthy, negative: abort the job); b200_comm_finalize destroys
- * (abort != 0: ncclCommAbort) the communicator.
+ * (abort != 0: ncclCommAbort) the communicator -- every CUDA graph that captured it must have been destroyed first (NCCL waits).
  * --------------------------------------------------------------------------------------------------------- */
 int b200_comm_unique_id(void* id_out_128);
-int b200_comm_init(const void* id_128, int rank, int world, void** comm_out);
+int b200_comm_init(const void* id_128, int rank, int world, int max_ctas, void** comm_out);
 int b200_comm_allreduce_bucket(void* comm, float* buf, long long n, int average, cudaStream_t stream);
 int b200_comm_async_error(void* comm);
 int b200_comm_finalize(void* comm, int abort);

@@ -71,6 +71,8 @@ def main():
         if rank == 0:
             results[mode] = ((g_dp - g_one).norm() / g_one.norm()).item()
         m.engine.reducer = None
+        if mode != "eager":
+            gs.release()  # (ncclCommDestroy below waits for every graph that captured the communicator)
         del m
     if rank == 0:
         # same bf16 noise-floor argument as tests/test_model_gpu.py: shard-wise bf16 rounding of the weight grads
