@@ -339,26 +339,34 @@ constexpr uint32_t F2_O_COL = 192;
 
 // this warp's 32 accumulator rows (TMEM lane == row) x 64 fp32 columns -> bf16 * sc -> warp-private 4 KB staging area
 // (row r at r * 128 B, its eight 16-byte chunks XOR-swizzled with r & 7: both passes are bank-conflict free)
-__device__ __forceinline__ void stage_rows64(uint8_t* stage, uint32_t taddr, float sc, int lane) {
-    uint8_t* mine = stage + lane * 128;
-    const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+// 32 rows x 64 fp32 columns of tensor memory (this warp's lanes) -> scaled, packed bf16 in registers (one row per lane)
+__device__ __forceinline__ void pack_rows64(uint4 (&o)[8], uint32_t taddr, float sc) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
         tmem_ld_wait();
-        uint4 o0, o1;
-        o0.x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-        o0.y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-        o0.z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-        o0.w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-        o1.x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-        o1.y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-        o1.z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-        o1.w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
-        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c) ^ sw) << 4)) = o0;
-        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(2 * c + 1) ^ sw) << 4)) = o1;
+        o[2 * c].x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
+        o[2 * c].y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
+        o[2 * c].z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
+        o[2 * c].w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
+        o[2 * c + 1].x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
+        o[2 * c + 1].y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
+        o[2 * c + 1].z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
+        o[2 * c + 1].w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
     }
+}
+// ... -> the warp's 4 KB staging tile (128-byte rows, 16-byte chunks XOR-swizzled by the row)
+__device__ __forceinline__ void store_rows64(uint8_t* stage, const uint4 (&o)[8], int lane) {
+    uint8_t* mine = stage + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane) & 7u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(c) ^ sw) << 4)) = o[c];
+}
+__device__ __forceinline__ void stage_rows64(uint8_t* stage, uint32_t taddr, float sc, int lane) {
+    uint4 o[8];
+    pack_rows64(o, taddr, sc);
+    store_rows64(stage, o, lane);
 }
 // staged rows -> global: 8 lanes x 16 B write one whole 128-byte row, 4 rows per instruction
 __device__ __forceinline__ void flush_rows64(const uint8_t* stage, __nv_bfloat16* g0, long long row_stride, int rows_valid, int lane) {
@@ -393,29 +401,59 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// The masked and the unmasked chunk are SEPARATE code paths behind a warp-uniform branch: with the column test inside the
+// unrolled element loop ptxas if-converted it and every element paid ISETP + FSEL (ncu, third cut: 15 of 69 M warp instructions).
+template <bool MASK>
+__device__ __forceinline__ void softmax_max_chunk(const uint32_t (&v)[16], int col0, int nvalid, float& mx0, float& mx1) {
+    if (!MASK) {
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) {
+            mx0 = max3(mx0, __uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
+            mx1 = max3(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 2) {
+            mx0 = fmaxf(mx0, (col0 + jj < nvalid) ? __uint_as_float(v[jj]) : -INFINITY);
+            mx1 = fmaxf(mx1, (col0 + jj + 1 < nvalid) ? __uint_as_float(v[jj + 1]) : -INFINITY);
+        }
+    }
+}
+template <bool MASK>
+__device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[16], int col0, int nvalid, f32x2_t sl22, f32x2_t nm22,
+                                                  f32x2_t& sum2a, f32x2_t& sum2b, uint32_t (&pk)[8]) {
+#pragma unroll
+    for (int jj = 0; jj < 16; jj += 2) {
+        float x0, x1;
+        upk2(fma2(pk2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1])), sl22, nm22), x0, x1);
+        float e0 = fast_ex2(x0), e1 = fast_ex2(x1);
+        if (MASK) {
+            if (col0 + jj >= nvalid) e0 = 0.f;
+            if (col0 + jj + 1 >= nvalid) e1 = 0.f;
+        }
+        if (jj & 2) sum2b = add2(sum2b, pk2(e0, e1)); else sum2a = add2(sum2a, pk2(e0, e1));
+        pk[jj >> 1] = pack_bf16x2(e0, e1);
+    }
+}
 __device__ __forceinline__ void softmax_rows(const int n, const uint32_t taddr, const int cb, const int nvalid, const int nvalid_warp_min,
                                              const float sl2, float* stats, const int hf, const int r) {
+    // chunks [0, nfull) need no mask for any row of this warp
+    const int nfull = max(0, min(n, nvalid_warp_min / 16 - cb));
     // ---- pass 1: row max over this thread's columns
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) {
+    for (int c = 0; c < nfull; ++c) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
         tmem_ld_wait();
-        const int col0 = (cb + c) * 16;
-        if (col0 + 16 <= nvalid_warp_min) {  // warp-uniform: no masking in this chunk
-#pragma unroll
-            for (int jj = 0; jj < 16; jj += 4) {
-                mx0 = max3(mx0, __uint_as_float(v[jj]), __uint_as_float(v[jj + 1]));
-                mx1 = max3(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
-            }
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const float a = (col0 + jj < nvalid) ? __uint_as_float(v[jj]) : -INFINITY;
-                if (jj & 1) mx1 = fmaxf(mx1, a); else mx0 = fmaxf(mx0, a);
-            }
-        }
+        softmax_max_chunk<false>(v, 0, 0, mx0, mx1);
+    }
+#pragma unroll 1
+    for (int c = nfull; c < n; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
+        tmem_ld_wait();
+        softmax_max_chunk<true>(v, (cb + c) * 16, nvalid, mx0, mx1);
     }
     float m = fmaxf(mx0, mx1);
     stats[hf * 128 + r] = m;
@@ -428,26 +466,20 @@ __device__ __forceinline__ void softmax_rows(const int n, const uint32_t taddr, 
     f32x2_t sum2a = pk2(0.f, 0.f), sum2b = pk2(0.f, 0.f);
     const uint32_t pbase = taddr + static_cast<uint32_t>(cb * 16);
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-        uint32_t v[16];
+    for (int c = 0; c < nfull; ++c) {
+        uint32_t v[16], pk[8];
         tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
         tmem_ld_wait();
-        const int col0 = (cb + c) * 16;
-        const bool full = col0 + 16 <= nvalid_warp_min;
-        uint32_t pk[8];
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 2) {
-            float x0, x1;
-            upk2(fma2(pk2(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1])), sl22, nm22), x0, x1);
-            float e0 = fast_ex2(x0), e1 = fast_ex2(x1);
-            if (!full) {
-                if (col0 + jj >= nvalid) e0 = 0.f;
-                if (col0 + jj + 1 >= nvalid) e1 = 0.f;
-            }
-            if (jj & 2) sum2b = add2(sum2b, pk2(e0, e1)); else sum2a = add2(sum2a, pk2(e0, e1));
-            pk[jj >> 1] = pack_bf16x2(e0, e1);
-        }
+        softmax_exp_chunk<false>(v, 0, 0, sl22, nm22, sum2a, sum2b, pk);
         tmem_st_32x32b_x8(pbase + static_cast<uint32_t>(c * 8), pk);  // P[row, col0 .. col0+16) -> 8 packed columns
+    }
+#pragma unroll 1
+    for (int c = nfull; c < n; ++c) {
+        uint32_t v[16], pk[8];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>((cb + c) * 16), v);
+        tmem_ld_wait();
+        softmax_exp_chunk<true>(v, (cb + c) * 16, nvalid, sl22, nm22, sum2a, sum2b, pk);
+        tmem_st_32x32b_x8(pbase + static_cast<uint32_t>(c * 8), pk);
     }
     tmem_st_wait();
     float s0, s1;
@@ -1057,7 +1089,7 @@ struct B2Cur {
 // then the tensor pipe produces the new scores: ~1500 cycles), the other group has the issue slots to itself.  !PP keeps the
 // first cut's schedule (all eight warps on one sub-tile, two threads per key row) for A/B timing.
 template <bool PP>
-__global__ void __launch_bounds__(B2_THREADS, 1)
+__global__ void __maxnreg__(144)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                  const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
                  const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_part,
@@ -1177,6 +1209,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             // otherwise the look-ahead stops at the boundary -- waiting there for loads that need a LATER commit of this
             // thread would deadlock.
             const bool cross = (n_kt == 2 && n_qs >= 3);
+            // With >= 4 sub-tiles per key tile every buffer a look-ahead needs was released in an EARLIER iteration, so the next
+            // S^T / dP^T can be queued right behind dV / dK -- ahead of this iteration's dQ MMAs and commits -- and reach the compute
+            // warps a dQ (8 MMAs) sooner.  Otherwise the releases of this very iteration may be needed: pump after them.
+            const bool pump_early = (n_kt == 2 && n_qs >= 4);
             B2Cur nx{0, 0, 0, 0};
             auto pump = [&](int g_cur, int cur_item, bool item_finished) {
                 while (nx.g < G && nx.g <= g_cur + 2) {
@@ -1208,6 +1244,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, desc_off(dsc_q, q_off + kk * 128), idesc_ts, acc);
                     }
                 }
+                if (pump_early) pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
                 const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
                 if (pair_done) {
                     if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
@@ -1229,7 +1266,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     ++kc;
                     if (kt == n_kt - 1) umma_commit(bar_dq);
                 }
-                pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
+                if (!pump_early) pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
             }
         }
     } else if (warp >= 10) {
@@ -1276,33 +1313,46 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const uint32_t taddr = tmem_base + ((q * 32u) << 16);
                 const bool live = key0 < p.T;
                 __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + key0) * D3 + h * 64;
+                // both accumulators leave tensor memory FIRST (dK through the staging tile, dV into registers): the MMA thread waits for
+                // `bar_kvfree` before it may start the next key tile -- and with it the S^T / dP^T look-ahead (ncu, third cut: 2 700
+                // cycles per key tile when the arrival came after dK's global stores)
+                uint4 dv_regs[8];
                 if (live) {
                     stage_rows64(stage, taddr + T2_DK, p.scale, lane);
-                    flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
-                    stage_rows64(stage, taddr + T2_DV, 1.0f, lane);
+                    pack_rows64(dv_regs, taddr + T2_DV, 1.0f);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_kvfree);
-                if (live) flush_rows64_colsum(stage, g0 + 2 * p.D, D3, p.T - key0, lane, csum + (16 + kt * 4 + static_cast<int>(q)) * 64);
+                if (live) {
+                    flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
+                    __syncwarp();  // (every lane has read its share of the dK tile)
+                    store_rows64(stage, dv_regs, lane);
+                    __syncwarp();
+                    flush_rows64_colsum(stage, g0 + 2 * p.D, D3, p.T - key0, lane, csum + (16 + kt * 4 + static_cast<int>(q)) * 64);
+                }
             }
             mbar_wait(bar_dq, static_cast<uint32_t>(it & 1));
             tc_fence_after_sync();
-            for (int mt = 0; mt < n_kt; ++mt) {
-                const int row0 = mt * 128 + static_cast<int>(q) * 32;
-                if (row0 < p.T) {
-                    stage_rows64(stage, tmem_base + ((q * 32u) << 16) + T2_DQ + static_cast<uint32_t>(mt * 64), p.scale, lane);
-                    if (mt == n_kt - 1) {  // everything of this item has left tensor memory
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_dqfree);
-                    }
-                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + row0) * D3 + h * 64, D3, p.T - row0, lane,
-                                        csum + (mt * 4 + static_cast<int>(q)) * 64);
-                } else if (mt == n_kt - 1) {
-                    tc_fence_before_sync();
+            {   // dQ of both query tiles leaves tensor memory first (tile 0 through the staging tile, tile 1 into registers), then the
+                // arrival that lets the MMA thread start the next item's dQ, then the global stores
+                const int rowa = static_cast<int>(q) * 32, rowb = 128 + static_cast<int>(q) * 32;
+                const bool live_a = rowa < p.T, live_b = n_kt == 2 && rowb < p.T;
+                uint4 dq_regs[8];
+                if (live_a) stage_rows64(stage, tmem_base + ((q * 32u) << 16) + T2_DQ, p.scale, lane);
+                if (live_b) pack_rows64(dq_regs, tmem_base + ((q * 32u) << 16) + T2_DQ + 64u, p.scale);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dqfree);
+                if (live_a)
+                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + rowa) * D3 + h * 64, D3, p.T - rowa, lane,
+                                        csum + static_cast<int>(q) * 64);
+                if (live_b) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_dqfree);
+                    store_rows64(stage, dq_regs, lane);
+                    __syncwarp();
+                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + rowb) * D3 + h * 64, D3, p.T - rowb, lane,
+                                        csum + (4 + static_cast<int>(q)) * 64);
                 }
             }
             if (dbias_part != nullptr) {
@@ -1390,6 +1440,8 @@ using namespace b200;
 static int g_attn_fwd_version = 0;
 static int g_attn_bwd_version = 0;
 static inline int attn_pick(int forced, int T) { return forced != 0 ? forced : (T > 128 ? 2 : 1); }
+// (backward: 3 = all eight compute warps on one sub-tile measured 276 us against 290 us for the ping-pong groups of 2)
+static inline int attn_pick_bwd(int forced, int T) { return forced != 0 ? forced : (T > 128 ? 3 : 1); }
 static int g_attn_prefetch = 0;  // measured neutral (tools/probe_layout.py: the kernels are not DRAM-pattern bound), kept as a switch
 
 static int attn_check(int B, int T, int H, int Dh) {
@@ -1473,7 +1525,7 @@ extern "C" int b200_attention_bwd(const void* qkv_bf16, const void* out_bf16, co
     AttnParams p;
     p.B = B; p.T = T; p.H = H; p.D = D; p.tp = (T + 15) / 16 * 16; p.scale = scale; p.causal = causal;
     p.prefetch = g_attn_prefetch; p.qkv_base = qkv_bf16; p.o_base = out_bf16; p.do_base = dout_bf16;
-    const int ver = attn_pick(g_attn_bwd_version, T);
+    const int ver = attn_pick_bwd(g_attn_bwd_version, T);
     if (ver == 1) {
         attn_bwd_kernel<<<B * H, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
                                                                 reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse,

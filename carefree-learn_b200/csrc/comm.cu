@@ -126,6 +126,10 @@ extern "C" int b200_comm_init(const void* id_128, int rank, int world, int max_c
         NcclConfigV21700 cfg{sizeof(NcclConfigV21700), 0xcafebeefu, 21700u, kNcclUndefInt, kNcclUndefInt, kNcclUndefInt, max_ctas, nullptr};
         if (cfg.maxCTAs > 32) cfg.maxCTAs = 32;
         rc = g_api.CommInitRankConfig(&c, world, id, rank, &cfg);  // collective over the ranks; uses the CURRENT device
+        if (rc == 4 /* ncclInvalidArgument: the config is checked before any communication, identically on every rank */) {
+            c = nullptr;
+            rc = g_api.CommInitRank(&c, world, id, rank);
+        }
         if (rc != kNcclSuccess) return nccl_fail("ncclCommInitRankConfig", rc);
     } else {
         rc = g_api.CommInitRank(&c, world, id, rank);

@@ -43,6 +43,6 @@ for i, r in enumerate(data):
         if v: agg[line][k] += v
 print("opcode mismatches", mism, "total samples", tot)
 srcl = open(src).read().split("\n") if src else None
-for line, c in sorted(agg.items(), key=lambda x: -x[1]["samples"])[:45]:
+for line, c in sorted(agg.items(), key=lambda x: -x[1]["samples"])[:int(__import__("os").environ.get("NCU_LINES_TOP", "45"))]:
     top = [(k[6:], v) for k, v in c.most_common(6) if k.startswith("stall_")][:3]
     print(f"{line:5d} {c['samples']:6d} {100*c['samples']/tot:5.1f}% inst {c['inst']:9d} {top}  | {srcl[line-1].strip()[:90] if srcl and line and line > 0 else ''}")
