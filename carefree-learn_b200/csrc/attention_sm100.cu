@@ -1088,8 +1088,10 @@ struct B2Cur {
 // group 1 those in buffer 1.  While one group waits for its next S^T | dP^T (its P^T / dS^T must first be consumed by dV / dK,
 // then the tensor pipe produces the new scores: ~1500 cycles), the other group has the issue slots to itself.  !PP keeps the
 // first cut's schedule (all eight warps on one sub-tile, two threads per key row) for A/B timing.
+// (14 warps put 4 on one scheduler: 16 384 registers / 4 warps = 128 per thread is the hardware ceiling for this block size --
+// __maxnreg__(144) compiles and then fails to launch)
 template <bool PP>
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                  const __nv_bfloat16* __restrict__ o_in, const __nv_bfloat16* __restrict__ do_in,
                  const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias_part,
