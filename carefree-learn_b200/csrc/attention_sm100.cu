@@ -342,18 +342,23 @@ constexpr uint32_t F2_O_COL = 192;
 // 32 rows x 64 fp32 columns of tensor memory (this warp's lanes) -> scaled, packed bf16 in registers (one row per lane)
 __device__ __forceinline__ void pack_rows64(uint4 (&o)[8], uint32_t taddr, float sc) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(c * 16), v);
+    for (int hh = 0; hh < 2; ++hh) {  // two loads in flight per wait (four would need 64 raw registers on top of the packed rows)
+        uint32_t v[2][16];
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(hh * 32), v[0]);
+        tmem_ld_32x32b_x16(taddr + static_cast<uint32_t>(hh * 32 + 16), v[1]);
         tmem_ld_wait();
-        o[2 * c].x = pack_bf16x2(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc);
-        o[2 * c].y = pack_bf16x2(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc);
-        o[2 * c].z = pack_bf16x2(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc);
-        o[2 * c].w = pack_bf16x2(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc);
-        o[2 * c + 1].x = pack_bf16x2(__uint_as_float(v[8]) * sc, __uint_as_float(v[9]) * sc);
-        o[2 * c + 1].y = pack_bf16x2(__uint_as_float(v[10]) * sc, __uint_as_float(v[11]) * sc);
-        o[2 * c + 1].z = pack_bf16x2(__uint_as_float(v[12]) * sc, __uint_as_float(v[13]) * sc);
-        o[2 * c + 1].w = pack_bf16x2(__uint_as_float(v[14]) * sc, __uint_as_float(v[15]) * sc);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = hh * 2 + cc;
+            o[2 * c].x = pack_bf16x2(__uint_as_float(v[cc][0]) * sc, __uint_as_float(v[cc][1]) * sc);
+            o[2 * c].y = pack_bf16x2(__uint_as_float(v[cc][2]) * sc, __uint_as_float(v[cc][3]) * sc);
+            o[2 * c].z = pack_bf16x2(__uint_as_float(v[cc][4]) * sc, __uint_as_float(v[cc][5]) * sc);
+            o[2 * c].w = pack_bf16x2(__uint_as_float(v[cc][6]) * sc, __uint_as_float(v[cc][7]) * sc);
+            o[2 * c + 1].x = pack_bf16x2(__uint_as_float(v[cc][8]) * sc, __uint_as_float(v[cc][9]) * sc);
+            o[2 * c + 1].y = pack_bf16x2(__uint_as_float(v[cc][10]) * sc, __uint_as_float(v[cc][11]) * sc);
+            o[2 * c + 1].z = pack_bf16x2(__uint_as_float(v[cc][12]) * sc, __uint_as_float(v[cc][13]) * sc);
+            o[2 * c + 1].w = pack_bf16x2(__uint_as_float(v[cc][14]) * sc, __uint_as_float(v[cc][15]) * sc);
+        }
     }
 }
 // ... -> the warp's 4 KB staging tile (128-byte rows, 16-byte chunks XOR-swizzled by the row)
@@ -1211,10 +1216,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             // otherwise the look-ahead stops at the boundary -- waiting there for loads that need a LATER commit of this
             // thread would deadlock.
             const bool cross = (n_kt == 2 && n_qs >= 3);
-            // With >= 4 sub-tiles per key tile every buffer a look-ahead needs was released in an EARLIER iteration, so the next
-            // S^T / dP^T can be queued right behind dV / dK -- ahead of this iteration's dQ MMAs and commits -- and reach the compute
-            // warps a dQ (8 MMAs) sooner.  Otherwise the releases of this very iteration may be needed: pump after them.
-            const bool pump_early = (n_kt == 2 && n_qs >= 4);
             B2Cur nx{0, 0, 0, 0};
             auto pump = [&](int g_cur, int cur_item, bool item_finished) {
                 while (nx.g < G && nx.g <= g_cur + 2) {
@@ -1246,7 +1247,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, desc_off(dsc_q, q_off + kk * 128), idesc_ts, acc);
                     }
                 }
-                if (pump_early) pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
+                // the key tile's dK | dV are complete with these MMAs: commit NOW (not behind dQ and the look-ahead) -- the epilogue's
+                // drain of the two accumulators is what the next key tile's first dV / dK wait for
+                if (qs == n_qs - 1) umma_commit(bar_kv);
                 const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
                 if (pair_done) {
                     if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
@@ -1263,12 +1266,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     if (kt == n_kt - 1) umma_commit(&empty_q[mt]);  // last MMAs on Q_mt / dO_mt of this item
                 }
                 if (qs == n_qs - 1) {
-                    umma_commit(bar_kv);
-                    umma_commit(&empty_kv[kt]);
+                    umma_commit(&empty_kv[kt]);  // (behind dQ: its B operand is this key tile)
                     ++kc;
                     if (kt == n_kt - 1) umma_commit(bar_dq);
                 }
-                if (!pump_early) pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
+                pump(g, it, kt == n_kt - 1 && qs == n_qs - 1);
             }
         }
     } else if (warp >= 10) {
@@ -1318,15 +1320,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 // both accumulators leave tensor memory FIRST (dK through the staging tile, dV into registers): the MMA thread waits for
                 // `bar_kvfree` before it may start the next key tile -- and with it the S^T / dP^T look-ahead (ncu, third cut: 2 700
                 // cycles per key tile when the arrival came after dK's global stores)
-                uint4 dv_regs[8];
+                uint4 dk_regs[8], dv_regs[8];
                 if (live) {
-                    stage_rows64(stage, taddr + T2_DK, p.scale, lane);
+                    pack_rows64(dk_regs, taddr + T2_DK, p.scale);
                     pack_rows64(dv_regs, taddr + T2_DV, 1.0f);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_kvfree);
                 if (live) {
+                    store_rows64(stage, dk_regs, lane);
                     flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
                     __syncwarp();  // (every lane has read its share of the dK tile)
                     store_rows64(stage, dv_regs, lane);
