@@ -1247,9 +1247,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                         umma_bf16_ts(tmem_base + T2_DK, buf + 64 + acol, desc_off(dsc_q, q_off + kk * 128), idesc_ts, acc);
                     }
                 }
-                // the key tile's dK | dV are complete with these MMAs: commit NOW (not behind dQ and the look-ahead) -- the epilogue's
-                // drain of the two accumulators is what the next key tile's first dV / dK wait for
-                if (qs == n_qs - 1) umma_commit(bar_kv);
                 const bool pair_done = (qs & 1) == 1 || qs == n_qs - 1;
                 if (pair_done) {
                     if (kt == 0 && mt == 0 && it > 0) mbar_wait(bar_dqfree, static_cast<uint32_t>((it - 1) & 1));  // previous item's dQ read out
@@ -1266,7 +1263,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                     if (kt == n_kt - 1) umma_commit(&empty_q[mt]);  // last MMAs on Q_mt / dO_mt of this item
                 }
                 if (qs == n_qs - 1) {
-                    umma_commit(&empty_kv[kt]);  // (behind dQ: its B operand is this key tile)
+                    umma_commit(bar_kv);
+                    umma_commit(&empty_kv[kt]);
                     ++kc;
                     if (kt == n_kt - 1) umma_commit(bar_dq);
                 }
@@ -1317,47 +1315,33 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                 const uint32_t taddr = tmem_base + ((q * 32u) << 16);
                 const bool live = key0 < p.T;
                 __nv_bfloat16* g0 = dqkv + (static_cast<long long>(b) * p.T + key0) * D3 + h * 64;
-                // both accumulators leave tensor memory FIRST (dK through the staging tile, dV into registers): the MMA thread waits for
-                // `bar_kvfree` before it may start the next key tile -- and with it the S^T / dP^T look-ahead (ncu, third cut: 2 700
-                // cycles per key tile when the arrival came after dK's global stores)
-                uint4 dk_regs[8], dv_regs[8];
                 if (live) {
-                    pack_rows64(dk_regs, taddr + T2_DK, p.scale);
-                    pack_rows64(dv_regs, taddr + T2_DV, 1.0f);
+                    stage_rows64(stage, taddr + T2_DK, p.scale, lane);
+                    flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
+                    stage_rows64(stage, taddr + T2_DV, 1.0f, lane);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_kvfree);
-                if (live) {
-                    store_rows64(stage, dk_regs, lane);
-                    flush_rows64_colsum(stage, g0 + p.D, D3, p.T - key0, lane, csum + (8 + kt * 4 + static_cast<int>(q)) * 64);
-                    __syncwarp();  // (every lane has read its share of the dK tile)
-                    store_rows64(stage, dv_regs, lane);
-                    __syncwarp();
-                    flush_rows64_colsum(stage, g0 + 2 * p.D, D3, p.T - key0, lane, csum + (16 + kt * 4 + static_cast<int>(q)) * 64);
-                }
+                if (live) flush_rows64_colsum(stage, g0 + 2 * p.D, D3, p.T - key0, lane, csum + (16 + kt * 4 + static_cast<int>(q)) * 64);
             }
             mbar_wait(bar_dq, static_cast<uint32_t>(it & 1));
             tc_fence_after_sync();
-            {   // dQ of both query tiles leaves tensor memory first (tile 0 through the staging tile, tile 1 into registers), then the
-                // arrival that lets the MMA thread start the next item's dQ, then the global stores
-                const int rowa = static_cast<int>(q) * 32, rowb = 128 + static_cast<int>(q) * 32;
-                const bool live_a = rowa < p.T, live_b = n_kt == 2 && rowb < p.T;
-                uint4 dq_regs[8];
-                if (live_a) stage_rows64(stage, tmem_base + ((q * 32u) << 16) + T2_DQ, p.scale, lane);
-                if (live_b) pack_rows64(dq_regs, tmem_base + ((q * 32u) << 16) + T2_DQ + 64u, p.scale);
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_dqfree);
-                if (live_a)
-                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + rowa) * D3 + h * 64, D3, p.T - rowa, lane,
-                                        csum + static_cast<int>(q) * 64);
-                if (live_b) {
+            for (int mt = 0; mt < n_kt; ++mt) {
+                const int row0 = mt * 128 + static_cast<int>(q) * 32;
+                if (row0 < p.T) {
+                    stage_rows64(stage, tmem_base + ((q * 32u) << 16) + T2_DQ + static_cast<uint32_t>(mt * 64), p.scale, lane);
+                    if (mt == n_kt - 1) {  // everything of this item has left tensor memory
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_dqfree);
+                    }
+                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + row0) * D3 + h * 64, D3, p.T - row0, lane,
+                                        csum + (mt * 4 + static_cast<int>(q)) * 64);
+                } else if (mt == n_kt - 1) {
+                    tc_fence_before_sync();
                     __syncwarp();
-                    store_rows64(stage, dq_regs, lane);
-                    __syncwarp();
-                    flush_rows64_colsum(stage, dqkv + (static_cast<long long>(b) * p.T + rowb) * D3 + h * 64, D3, p.T - rowb, lane,
-                                        csum + (4 + static_cast<int>(q)) * 64);
+                    if (lane == 0) mbar_arrive(bar_dqfree);
                 }
             }
             if (dbias_part != nullptr) {

@@ -2,6 +2,8 @@
 # round-2 trip 5 (2 GPUs, short): the in-graph gradient exchange with every persistent kernel shrunk while buckets are in flight;
 # communicator CTA count swept; N=1 on the same box first (box-to-box clocks differ by ~8 %).
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -k "attention" > gpurun_out/pytest_attn.log 2>&1; echo "attention tests rc=$?"; tail -1 gpurun_out/pytest_attn.log
+timeout 200 python tools/op_bench.py attn > gpurun_out/r02_op_bench_attn_final.txt 2>&1; head -8 gpurun_out/r02_op_bench_attn_final.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541"
 B="bench.py --steps 10 --warmup 3 --no-eager-baseline --no-cpu-baseline"
 timeout 300 python $B --gpus 1 > gpurun_out/r02_sweep_n1.log 2>&1; echo "n1: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/r02_sweep_n1.log | head -1)"
