@@ -517,8 +517,8 @@ def run_b200(args):
          lambda: ops.gemm(x3072, w_2, bias=b_o, epilogue=ops.EPI_BIAS_RESID_F32, aux=resid, out0=o_res)),
         ("gemm_bf16_kernel<EPI_DGELU_BF16> ff2-dgrad 50432x3072x768", gf,
          lambda: ops.gemm(x768, w_2, b_mn_major=True, epilogue=ops.EPI_DGELU_BF16, aux=hpre, out0=o_ff0)),
-        ("attn_fwd_kernel B256 T197 H12", 4.0 * B * H_ * 197 * 197 * 64, lambda: ops.attention_fwd(qkv, B, 197, H_)),
-        ("attn_bwd_kernel B256 T197 H12", 10.0 * B * H_ * 197 * 197 * 64,
+        ("attn_fwd2_kernel B256 T197 H12 (per-shape default)", 4.0 * B * H_ * 197 * 197 * 64, lambda: ops.attention_fwd(qkv, B, 197, H_)),
+        ("attn_bwd2_kernel<PP=false> B256 T197 H12 (per-shape default)", 10.0 * B * H_ * 197 * 197 * 64,
          lambda: ops.attention_bwd(qkv, att_o, att_do, att_lse, B, 197, H_, dqkv=att_dqkv)),
     ]
     timed = []

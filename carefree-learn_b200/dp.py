@@ -119,10 +119,9 @@ class NativeComm:
         if not dist.is_initialized():
             raise RuntimeError("NativeComm needs an initialised torch.distributed group to ship the NCCL unique id")
         # NCCL kernels and the persistent kernels of the backward share the SMs: cap the channels NCCL may use so that the
-        # step can leave exactly that many SMs free while buckets are in flight (B200_COMM_CTAS, default 8: the bucket
-        # all-reduces hide under ~20 ms of backward, so they need little bandwidth -- and every CTA costs the GEMMs an SM)
-        # (ncclConfig_t.maxCTAs of THIS communicator only: torch.distributed's own communicator keeps NCCL's defaults)
-        self.ctas = int(os.environ.get("B200_COMM_CTAS", "8"))
+        # step can leave exactly that many SMs free for the GEMM that starts while a bucket is in flight (B200_COMM_CTAS,
+        # default 16; ncclConfig_t.maxCTAs of THIS communicator only: torch.distributed's own communicator keeps NCCL's defaults)
+        self.ctas = int(os.environ.get("B200_COMM_CTAS", "16"))
         self.rank, self.world, self.device = rank, world, device
         lib = _cabi.lib()
         buf = ctypes.create_string_buffer(128)
@@ -182,10 +181,11 @@ class NativeBucketReducer(GradBucketReducer):
     """Same bucket protocol as ``GradBucketReducer`` over a ``NativeComm``: works eagerly AND under stream capture.
 
     ``ready(key)`` forks the communication stream off the compute stream (event) and enqueues the bucket's all-reduce
-    there; ``finish()`` joins.  From the first bucket to the join every persistent kernel of the library (GEMMs, attention)
-    is launched on ``SMs - comm.ctas`` CTAs (``b200_set_persistent_ctas``): they assign their tiles to CTAs statically, so a
-    CTA that cannot start because NCCL holds its SM would stretch its kernel by the whole duration of the all-reduce.
-    ``B200_DP_SHRINK=next`` restores the first schedule (only the GEMM right after a bucket is shrunk) for A/B timing."""
+    there; ``finish()`` joins.  The persistent kernels assign their tiles to CTAs statically, so a CTA that cannot start
+    because NCCL holds its SM stretches its kernel by the whole duration of the all-reduce: the GEMM launched right behind a
+    bucket runs on ``SMs - comm.ctas`` CTAs (``engine.shrink_next``).  ``B200_DP_SHRINK=all`` shrinks EVERY persistent kernel
+    from the first bucket to the join instead (``b200_set_persistent_ctas``) -- measured slower on 2 GPUs (35.6 - 38.3 ms
+    against 34.9 ms: the smaller grids cost a wave on every backward GEMM), kept for A/B timing."""
 
     def __init__(self, arena, num_layers: int, comm: NativeComm, engine: Any = None):
         super().__init__(arena, num_layers, process_group=None)
@@ -210,7 +210,7 @@ class NativeBucketReducer(GradBucketReducer):
         cs.wait_event(ev)
         with torch.cuda.stream(cs):
             self.comm.allreduce_(grad[lo:hi], average=True)
-        if os.environ.get("B200_DP_SHRINK", "all") == "next":
+        if os.environ.get("B200_DP_SHRINK", "next") == "next":
             if self.engine is not None and key != "stem":
                 self.engine.shrink_next = self.comm.ctas
         elif not self._launched and self.comm.ctas > 0:
