@@ -70,7 +70,7 @@ SIGNATURES: Dict[str, Any] = {
     "b200_fill_f32": (c_int, [_P, c_float, _LL, _P]),
     "b200_conv3x3_nhwc_bf16": (c_int, [_P, _P, _P, _P, _P, _LL, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_conv3x3_wgrad_nhwc_bf16": (c_int, [_P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "b200_set_persistent_ctas": (c_int, [c_int]),
+    "b200_set_persistent_ctas": (c_int, [c_int, c_int]),
     "b200_groupnorm_workspace_floats": (_LL, [c_int, c_int, c_int]),
     "b200_groupnorm_silu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P]),
     "b200_groupnorm_silu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

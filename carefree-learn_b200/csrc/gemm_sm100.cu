@@ -836,13 +836,17 @@ int num_sms() {
 // by the communicator's CTA count while gradient buckets are in flight: these kernels assign their tiles to CTAs statically, and
 // a CTA whose SM is held by an NCCL kernel starts only when that all-reduce is over -- with its full share of tiles still to do.
 static int g_persistent_ctas = 0;
-int persistent_ctas() {
+static int g_persistent_window = 0;  // > 0: the limit lapses after that many more persistent launches
+int persistent_ctas() {  // (called exactly once per persistent launch)
     const int n = num_sms();
-    return (g_persistent_ctas > 0 && g_persistent_ctas < n) ? g_persistent_ctas : n;
+    const int r = (g_persistent_ctas > 0 && g_persistent_ctas < n) ? g_persistent_ctas : n;
+    if (g_persistent_window > 0 && --g_persistent_window == 0) g_persistent_ctas = 0;
+    return r;
 }
-extern "C" int b200_set_persistent_ctas(int n) {
+extern "C" int b200_set_persistent_ctas(int n, int launches) {
     const int old = g_persistent_ctas;
     g_persistent_ctas = n > 0 ? n : 0;
+    g_persistent_window = (n > 0 && launches > 0) ? launches : 0;
     return old;
 }
 

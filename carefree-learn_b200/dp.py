@@ -210,13 +210,19 @@ class NativeBucketReducer(GradBucketReducer):
         cs.wait_event(ev)
         with torch.cuda.stream(cs):
             self.comm.allreduce_(grad[lo:hi], average=True)
-        if os.environ.get("B200_DP_SHRINK", "next") == "next":
+        mode = os.environ.get("B200_DP_SHRINK", "next")
+        if mode == "next":  # the ONE GEMM launched right behind the bucket (the next block's FF2 input gradient)
             if self.engine is not None and key != "stem":
                 self.engine.shrink_next = self.comm.ctas
-        elif not self._launched and self.comm.ctas > 0:
+        elif self.comm.ctas > 0:
             from . import ops
 
-            self._prev_limit = _cabi.lib().b200_set_persistent_ctas(max(2, (ops.num_sms() - self.comm.ctas) // 2 * 2))
+            limit = max(2, (ops.num_sms() - self.comm.ctas) // 2 * 2)
+            if mode.startswith("next") and mode[4:].isdigit():  # "next3": the next three persistent launches
+                if key != "stem":
+                    _cabi.lib().b200_set_persistent_ctas(limit, int(mode[4:]))
+            elif not self._launched:                             # "all": from the first bucket to the join
+                self._prev_limit = _cabi.lib().b200_set_persistent_ctas(limit, 0)
         self._launched = True
 
     def finish(self) -> None:
@@ -224,8 +230,10 @@ class NativeBucketReducer(GradBucketReducer):
             return
         torch.cuda.current_stream().wait_stream(self._stream())
         self._launched = False
+        if os.environ.get("B200_DP_SHRINK", "next") not in ("next", "all"):
+            _cabi.lib().b200_set_persistent_ctas(0, 0)
         if self._prev_limit is not None:
-            _cabi.lib().b200_set_persistent_ctas(self._prev_limit)
+            _cabi.lib().b200_set_persistent_ctas(self._prev_limit, 0)
             self._prev_limit = None
 
     def _stream(self) -> torch.cuda.Stream:
