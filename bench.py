@@ -28,7 +28,7 @@ CLIP_FLOP_PER_PAIR_FWD_BWD = 3 * 14_780_000_000  # 14.78 G
 CONFIG_NAME = "vit_b16"
 PER_GPU_BATCH = 256
 # N > 1 gradient exchange used by default ("graph" once validated on real multi-GPU boxes; see --dp-mode)
-DEFAULT_DP_MODE = "graph"  # validated on 2 GPUs (tools/dp_check.py: eager = graphed = flat = 2.2e-3 vs the single-process global batch)
+DEFAULT_DP_MODE = "auto"  # graph (in-graph bucketed exchange) for N <= 2, flat (one uncapped all-reduce behind the graph) for N >= 3: see --dp-mode
 
 
 def _peaks():
@@ -336,7 +336,9 @@ def run_b200(args):
     if world > 1:
         # the library's own NCCL communicator (csrc/comm.cu): its all-reduces are plain stream operations, so the bucketed
         # exchange is captured INSIDE the step's CUDA graph on a forked stream, overlapped with the remaining backward
-        comm = dp.TorchComm(rank, world, dev) if args.dp_mode == "torch" else dp.NativeComm(rank, world, dev)
+        # (flat: nothing overlaps the all-reduce, so the communicator is not capped to a few CTAs)
+        comm = (dp.TorchComm(rank, world, dev) if args.dp_mode == "torch" else
+                dp.NativeComm(rank, world, dev, max_ctas=0 if args.dp_mode == "flat" and "B200_COMM_CTAS" not in os.environ else None))
         dp.broadcast_parameters(model)
         dp_parity = dp_gradient_parity(comm, rank, world, dev, flat=args.flat_allreduce)  # (the ViT path's reducer; CLIP reuses it per tower)
     use_graph = not args.no_graph
@@ -607,12 +609,15 @@ def main():
     ap.add_argument("--config", default="vit", choices=["vit", "clip"], help="vit: BASELINE.json configs[1]/[2] (the metric); clip: configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--dp-mode", default=os.environ.get("B200_DP_MODE", DEFAULT_DP_MODE), choices=["graph", "flat", "torch"],
+    ap.add_argument("--dp-mode", default=os.environ.get("B200_DP_MODE", DEFAULT_DP_MODE), choices=["auto", "graph", "flat", "torch"],
                     help="N > 1 gradient exchange: graph = per-block bucket all-reduces on the library's own NCCL communicator, captured "
-                         "inside the step graph and overlapped with backward; flat = same communicator, ONE all-reduce behind the graph; "
-                         "torch = torch.distributed, one all-reduce behind the graph (round 1's schedule)")
+                         "inside the step graph and overlapped with backward; flat = same communicator (uncapped), ONE all-reduce behind the "
+                         "graph; torch = torch.distributed, one all-reduce behind the graph (round 1's schedule); auto = graph for N <= 2, "
+                         "flat for N >= 3 (measured: graph 0.990 at N = 2 but 0.894 at N = 8, DESIGN.md section 4)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg")
     args = ap.parse_args()
+    if args.dp_mode == "auto":
+        args.dp_mode = "graph" if int(os.environ.get("WORLD_SIZE", "1")) <= 2 else "flat"
     args.flat_allreduce = args.dp_mode in ("flat", "torch")
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

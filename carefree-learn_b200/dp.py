@@ -115,13 +115,14 @@ class NativeComm:
     The 128-byte NCCL unique id is created by rank 0 and handed to the other ranks through whatever process group
     already exists (``bootstrap_group``; gloo or nccl), exactly once."""
 
-    def __init__(self, rank: int, world: int, device: torch.device, bootstrap_group: Any = None):
+    def __init__(self, rank: int, world: int, device: torch.device, bootstrap_group: Any = None, max_ctas: Optional[int] = None):
         if not dist.is_initialized():
             raise RuntimeError("NativeComm needs an initialised torch.distributed group to ship the NCCL unique id")
         # NCCL kernels and the persistent kernels of the backward share the SMs: cap the channels NCCL may use so that the
         # step can leave exactly that many SMs free for the GEMM that starts while a bucket is in flight (B200_COMM_CTAS,
         # default 16; ncclConfig_t.maxCTAs of THIS communicator only: torch.distributed's own communicator keeps NCCL's defaults)
-        self.ctas = int(os.environ.get("B200_COMM_CTAS", "16"))
+        # ``max_ctas=0``: NCCL's own default (for an all-reduce that is NOT overlapped with compute: nothing to leave room for)
+        self.ctas = int(os.environ.get("B200_COMM_CTAS", "16")) if max_ctas is None else int(max_ctas)
         self.rank, self.world, self.device = rank, world, device
         lib = _cabi.lib()
         buf = ctypes.create_string_buffer(128)
