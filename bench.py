@@ -228,6 +228,7 @@ def dp_gradient_parity(comm, rank, world, dev, flat=False):
         if not rel < 5e-3:
             raise SystemExit(f"bench.py: data-parallel gradient parity failed: rel L2 {rel:.3e} >= 5e-3")
     m.engine.reducer = None
+    gs.release()  # (a graph that captured the communicator must be gone before the communicator is closed)
     del gs, m
     return rel
 
