@@ -295,6 +295,9 @@ class GraphedTrainStep:
         if self.flat:
             for a in self.optimizer.arenas():
                 self.comm.allreduce_(a.grad, average=True)
+            hook = getattr(self.model, "clip_norm_hook", None)
+            if hook is not None:
+                hook()  # (clipping sees the AVERAGED gradients, as under DDP)
             self.optimizer.step()
         return self.loss
 

@@ -27,7 +27,7 @@ from .optim import ArenaAdam, GraphedTrainStep
 
 class B200TrainStep:
     def __init__(self, model: Any, optimizer: ArenaAdam, *, scheduler: Any = None, clip_norm: float = 0.0, comm: Any = None,
-                 graph: bool = False, batch: Optional[int] = None, static_inputs: Optional[List[Tensor]] = None):
+                 graph: bool = False, batch: Optional[int] = None, static_inputs: Optional[List[Tensor]] = None, flat: bool = False):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.clip_norm = float(clip_norm)
         self.comm = comm
@@ -41,7 +41,8 @@ class B200TrainStep:
                 model.clip_norm_hook = lambda: optimizer.clip_grad_norm_(self.clip_norm)
             if batch is None and static_inputs is None:
                 raise ValueError("graph=True needs the batch size (or the static input tensors)")
-            self._graph = GraphedTrainStep(model, optimizer, batch or static_inputs[0].shape[0], comm=comm, inputs=static_inputs)
+            self._graph = GraphedTrainStep(model, optimizer, batch or static_inputs[0].shape[0], comm=comm, inputs=static_inputs,
+                                           flat=flat)  # flat: ONE all-reduce behind the graph instead of in-graph buckets
         elif comm is not None and comm.world > 1:
             from . import dp
 
