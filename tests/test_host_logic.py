@@ -399,3 +399,39 @@ def test_reference_warmup_scheduler_drives_arena_adam():
         seq_r.append(ref.param_groups[0]["lr"])
     assert seq_o == seq_r and max(seq_o) == pytest.approx(3e-3) and seq_o[-1] < 1e-3
     assert ours._hyper_tuple()[0] == seq_o[-1]  # what the next step pushes to the device
+
+
+def test_persistent_cta_bound_is_a_plain_host_setting():
+    """``b200_set_persistent_ctas`` (grid bound of the persistent kernels while an all-reduce holds SMs) touches no device: it
+    returns the previous bound, 0 / negative clears it."""
+    lib = _cabi.lib()
+    first = lib.b200_set_persistent_ctas(132, 0)
+    try:
+        assert lib.b200_set_persistent_ctas(140, 3) == 132
+        assert lib.b200_set_persistent_ctas(0, 0) == 140
+        assert lib.b200_set_persistent_ctas(-5, 7) == 0
+        assert lib.b200_set_persistent_ctas(0, 0) == 0
+    finally:
+        lib.b200_set_persistent_ctas(first, 0)
+
+
+def test_bench_dp_mode_auto_resolves_by_world_size(monkeypatch):
+    """``bench.py --dp-mode auto``: the in-graph bucketed exchange up to 2 GPUs, one all-reduce behind the graph from 3 GPUs up
+    (what measured best at each size)."""
+    import importlib
+    import sys as _sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in _sys.path:
+        _sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    seen = {}
+    monkeypatch.setattr(bench, "run_b200", lambda args: seen.update(mode=args.dp_mode, flat=args.flat_allreduce))
+    for world, mode, flat in (("1", "graph", False), ("2", "graph", False), ("4", "flat", True), ("8", "flat", True)):
+        monkeypatch.setenv("WORLD_SIZE", world)
+        monkeypatch.setattr(_sys, "argv", ["bench.py"])
+        bench.main()
+        assert seen == dict(mode=mode, flat=flat), (world, seen)
+    monkeypatch.setattr(_sys, "argv", ["bench.py", "--dp-mode", "graph"])
+    bench.main()
+    assert seen["mode"] == "graph"
