@@ -435,3 +435,18 @@ def test_bench_dp_mode_auto_resolves_by_world_size(monkeypatch):
     monkeypatch.setattr(_sys, "argv", ["bench.py", "--dp-mode", "graph"])
     bench.main()
     assert seen["mode"] == "graph"
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: ``include/b200_cflearn.h`` must parse as C99 on its own (no CUDA headers, no C++), which is what a
+    cgo / JNI / ctypesgen consumer would feed it to."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-x", "c", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", os.path.join(root, "include", "b200_cflearn.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
