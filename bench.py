@@ -41,6 +41,39 @@ def _peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# multi-GPU watchdog: a collective that never completes (a dead peer, a rank that took another code path) would otherwise sit in
+# an NCCL kernel until the caller's own limit; say where it happened and leave, so the launcher tears the other ranks down
+# ------------------------------------------------------------------------------------------------------------------
+class Watchdog:
+    def __init__(self, seconds: float, rank: int):
+        self.phase, self.rank, self.seconds = "start", rank, seconds
+        self._timer = None
+        if seconds > 0:
+            self._timer = threading.Timer(seconds, self._fire)
+            self._timer.daemon = True
+            self._timer.start()
+
+    def _fire(self):
+        sys.stderr.write(f"bench.py: rank {self.rank} made no progress for {self.seconds:.0f} s in phase '{self.phase}' -- aborting "
+                         f"(B200_BENCH_WATCHDOG_S=0 disables; --dp-mode flat / torch select other gradient-exchange schedules)\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    def enter(self, phase: str):
+        self.phase = phase
+        if self._timer is not None:  # every phase gets the full allowance
+            self._timer.cancel()
+            self._timer = threading.Timer(self.seconds, self._fire)
+            self._timer.daemon = True
+            self._timer.start()
+
+    def done(self):
+        if self._timer is not None:
+            self._timer.cancel()
+            self._timer = None
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # clocks sampler (pynvml; nvidia-smi fields of the profiling recipe)
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -320,7 +353,10 @@ def run_b200(args):
             raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # N > 1 only: no phase of a healthy run takes anywhere near this long, even on a cold box
+    dog = Watchdog(float(os.environ.get("B200_BENCH_WATCHDOG_S", "300")) if world > 1 else 0.0, rank)
     if world > 1:
+        dog.enter("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
@@ -338,6 +374,7 @@ def run_b200(args):
         # the library's own NCCL communicator (csrc/comm.cu): its all-reduces are plain stream operations, so the bucketed
         # exchange is captured INSIDE the step's CUDA graph on a forked stream, overlapped with the remaining backward
         # (flat: nothing overlaps the all-reduce, so the communicator is not capped to a few CTAs)
+        dog.enter("communicator init + gradient parity check")
         comm = (dp.TorchComm(rank, world, dev) if args.dp_mode == "torch" else
                 dp.NativeComm(rank, world, dev, max_ctas=0 if args.dp_mode == "flat" and "B200_COMM_CTAS" not in os.environ else None))
         dp.broadcast_parameters(model)
@@ -359,6 +396,7 @@ def run_b200(args):
     dev_x = [h.to(dev) for h in host_x]
     dev_y = [h.to(dev) for h in host_y]
 
+    dog.enter("graph capture")
     gstep = None
     if use_graph:  # zero_grad + fwd + loss + bwd + (N > 1: per-block bucket all-reduces on a forked stream) + Adam as ONE CUDA graph
         from cflearn_b200.optim import GraphedTrainStep
@@ -392,6 +430,7 @@ def run_b200(args):
         return t.item()
 
     # ---- device-resident timing ---------------------------------------------------------------------------------
+    dog.enter("warm-up + timed steps")
     for i in range(args.warmup):
         step_resident(i)
     barrier()
@@ -415,6 +454,7 @@ def run_b200(args):
     if not (final_loss == final_loss and abs(final_loss) < 1e4):
         raise SystemExit(f"bench.py: loss diverged ({final_loss})")
 
+    dog.enter("end-to-end steps")
     # ---- end to end: pinned host batches -> H2D on a copy stream (prefetched one step ahead) -> step -> loss D2H --
     copy_stream = torch.cuda.Stream()
     stage_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
@@ -550,6 +590,7 @@ def run_b200(args):
     }
 
     # ---- the real bar: the reference path in PyTorch eager on the same GPU(s) (DDP at N > 1), same run ---------------
+    dog.enter("per-kernel timing + eager DDP leg")
     eager = None
     if not args.no_eager_baseline and not is_clip:
         if gstep is not None:
@@ -589,6 +630,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "eager_gpu": eager, "dp_parity_rel": dp_parity, "loss": round(final_loss, 4),
         }
         print(json.dumps(line), flush=True)
+    dog.enter("teardown")
     if gstep is not None:  # ncclCommDestroy waits for every graph that captured the communicator: destroy the graph first
         gstep.release()
         gstep = None
@@ -599,6 +641,7 @@ def run_b200(args):
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+    dog.done()
 
 
 def main():
