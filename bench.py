@@ -443,9 +443,9 @@ def run_b200(args):
         loss = step_resident(i)
     e1.record()
     barrier()
-    launches = _cabi.launch_count() - launches0
+    launches = _cabi.launch_count() - launches0  # (flat / torch exchange: the Adam launches behind each replay are counted here)
     if gstep is not None:  # graph replays launch the captured kernels without going through the host-side counter
-        launches = gstep.launches_per_replay * args.steps
+        launches += gstep.launches_per_replay * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
