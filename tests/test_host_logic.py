@@ -450,3 +450,28 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, "-x", "c", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", os.path.join(root, "include", "b200_cflearn.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_product_code_never_touches_the_oracle():
+    """``oracle/`` is test infrastructure: nothing under the package may import, read or execute it, and the package has no CPU
+    path to fall back to (a CPU tensor raises)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "carefree-learn_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for m in re.finditer(r"^\s*(?:from|import)\s+([\w\.]*oracle[\w\.]*)|oracle/|vit_oracle|clip_oracle|unet_oracle|fcnn_oracle", text, re.M):
+                    line = text[: m.start()].count("\n") + 1
+                    src = text.splitlines()[line - 1]
+                    if "import" in src or "open(" in src or "sys.path" in src:
+                        offenders.append((f, line, src.strip()))
+    assert not offenders, offenders
+    import torch
+
+    from cflearn_b200 import ops
+    from cflearn_b200._cabi import B200Error
+
+    with pytest.raises(B200Error):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
